@@ -1,0 +1,266 @@
+"""CUDA backend: turns tensor-level op requests into pre-bound launches of ``libdinopose_sm100a.so``.
+
+The engine (``engine.py``) describes a forward / backward pass ONCE per (batch, resolution, mode)
+plan as a sequence of backend calls on statically allocated tensors; each call here validates the
+tensors, freezes the raw pointers / shapes into ctypes arguments and appends ``(fn, args)`` to a
+``Program``.  Running a step is then a tight loop of ctypes calls on the current CUDA stream (and is
+CUDA-graph capturable: no allocation, no synchronisation).
+
+The method set is the op vocabulary of the C ABI (include/dinopose.h), one method per entry point.
+``tests/emulator.py`` implements the same vocabulary in plain torch so the engine's orchestration
+and weight-packing logic can be checked on a CPU-only box; it is test infrastructure and is never
+imported by the package.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import GemmArgs, WgradArgs
+
+ACT = {"none": 0, "relu": 1, "gelu": 2}
+ROWMAP = {"identity": 0, "patch_tokens": 1, "nchw": 2, "shuffle2x2": 3}
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t, dtype, name, contiguous=True):
+    if t is None:
+        return
+    if not t.is_cuda:
+        raise _lib.DinoPoseError(f"{name}: expected a CUDA tensor (no CPU path exists)")
+    if t.dtype != dtype:
+        raise _lib.DinoPoseError(f"{name}: expected {dtype}, got {t.dtype}")
+    if contiguous and not t.is_contiguous():
+        raise _lib.DinoPoseError(f"{name}: expected a contiguous tensor")
+
+
+class Program:
+    """A recorded list of launches; ``run()`` replays them on the current stream."""
+
+    def __init__(self):
+        self.calls = []       # (fn, args, name)
+        self.keep = []        # keep ctypes structs / tensors alive
+        self.lib = _lib.lib()
+
+    def add(self, name, fn, *args, keep=()):
+        self.calls.append((fn, args, name))
+        self.keep.extend(keep)
+
+    def add_callable(self, name, fn):
+        """Host-side step (e.g. a torch op on static tensors) recorded in order with the launches."""
+        self.calls.append((None, fn, name))
+
+    def __len__(self):
+        return sum(1 for fn, _a, _n in self.calls if fn is not None)
+
+    def run(self):
+        stream = torch.cuda.current_stream().cuda_stream
+        for fn, args, name in self.calls:
+            if fn is None:
+                args()
+                continue
+            rc = fn(*args, stream)
+            if rc != 0:
+                _lib.check(rc, name)
+
+
+class CudaBackend:
+    """Records launches of the sm_100a kernels into a ``Program``."""
+
+    name = "cuda"
+
+    def __init__(self):
+        self.lib = _lib.lib()
+        self.prog = None
+
+    def begin(self):
+        self.prog = Program()
+        return self.prog
+
+    # ------------------------------------------------------------------ GEMM family
+    def gemm(self, A, W, out, *, M, N, K, lda=None, ldw=None, ldo=None, out_dtype="bf16", bias=None, scale=None,
+             ls=None, residual=None, ldr=None, aux_out=None, aux_in=None, ld_aux=0, act="none", row_map="identity",
+             n_valid=0, map_a=0, map_b=0, conv=None, OH=0, OW=0, NB=0, block_n=0, name="gemm"):
+        """out = epilogue(A[M,K] @ W[N,K]^T).  ``conv`` = dict(KH, KW, pad, OH, OW) makes A an NHWC
+        [NB,IH,IW,C] activation (any strides with unit channel stride) read as an implicit conv."""
+        _chk(W, torch.bfloat16, name + ".W", contiguous=False)
+        a = GemmArgs()
+        a.A, a.W, a.out = _p(A), _p(W), _p(out)
+        a.M, a.N, a.K = M, N, K
+        a.block_n = block_n
+        a.ldw = ldw if ldw is not None else W.stride(0)
+        if conv is not None:
+            _chk(A, torch.bfloat16, name + ".A", contiguous=False)
+            assert A.dim() == 4 and A.stride(3) == 1
+            a.a_mode = 1
+            a.NB, a.IH, a.IW, a.C = A.shape
+            a.a_stride_b, a.a_stride_h, a.a_stride_w = A.stride(0), A.stride(1), A.stride(2)
+            a.KH, a.KW = conv["KH"], conv["KW"]
+            a.pad_y = a.pad_x = conv["pad"]
+            a.OH, a.OW = conv["OH"], conv["OW"]
+            a.lda = 0
+        else:
+            _chk(A, torch.bfloat16, name + ".A", contiguous=False)
+            a.a_mode = 0
+            a.lda = lda if lda is not None else A.stride(0)
+            a.OH, a.OW, a.NB = OH, OW, NB
+        a.ldo = ldo if ldo is not None else (out.stride(0) if out.dim() == 2 else 0)
+        a.out_dtype = 0 if out_dtype == "bf16" else 1
+        _chk(out, torch.bfloat16 if out_dtype == "bf16" else torch.float32, name + ".out", contiguous=False)
+        for t, nm in ((bias, "bias"), (scale, "scale"), (ls, "ls")):
+            _chk(t, torch.float32, f"{name}.{nm}")
+        a.bias, a.scale, a.ls = _p(bias), _p(scale), _p(ls)
+        if residual is not None:
+            a.residual = _p(residual)
+            a.res_is_bf16 = 1 if residual.dtype == torch.bfloat16 else 0
+            a.ldr = ldr if ldr is not None else residual.stride(0)
+        a.aux_out, a.aux_in, a.ld_aux = _p(aux_out), _p(aux_in), ld_aux
+        a.act = ACT[act]
+        a.row_map = ROWMAP[row_map]
+        a.n_valid, a.map_a, a.map_b = n_valid, map_a, map_b
+        self.prog.add(name, self.lib.dp_gemm_bf16, C.byref(a),
+                      keep=(a, A, W, out, bias, scale, ls, residual, aux_out, aux_in))
+
+    def wgrad(self, A, B, out, *, Mc, Nc, so_m, so_n, so_t=0, so_mo=0, so_no=0, m_inner=0, n_inner=0, conv=None,
+              P=0, lda=None, ldb=None, block_n=0, splits=0, name="wgrad"):
+        """out[off(m)+off(n)+tap*so_t] += sum_p A[p,m] * B[p(+tap),n] (fp32 atomics; out pre-zeroed)."""
+        _chk(A, torch.bfloat16, name + ".A", contiguous=False)
+        _chk(B, torch.bfloat16, name + ".B", contiguous=False)
+        _chk(out, torch.float32, name + ".out", contiguous=False)
+        a = WgradArgs()
+        a.A, a.B, a.out = _p(A), _p(B), _p(out)
+        a.Mc, a.Nc = Mc, Nc
+        a.so_m, a.so_mo, a.so_n, a.so_no, a.so_t = so_m, so_mo, so_n, so_no, so_t
+        a.m_inner, a.n_inner = m_inner, n_inner
+        a.block_n, a.splits = block_n, splits
+        if conv is not None:
+            assert A.dim() == 4 and B.dim() == 4 and A.stride(3) == 1 and B.stride(3) == 1
+            a.mode = 1
+            a.NB, a.OH, a.OW = A.shape[0], A.shape[1], A.shape[2]
+            a.IH, a.IW = B.shape[1], B.shape[2]
+            a.a_sb, a.a_sh, a.a_sw = A.stride(0), A.stride(1), A.stride(2)
+            a.b_sb, a.b_sh, a.b_sw = B.stride(0), B.stride(1), B.stride(2)
+            a.KH, a.KW = conv["KH"], conv["KW"]
+            a.pad_y = a.pad_x = conv["pad"]
+        else:
+            a.mode = 0
+            a.P = P
+            a.lda = lda if lda is not None else A.stride(0)
+            a.ldb = ldb if ldb is not None else B.stride(0)
+            a.KH = a.KW = 1
+        self.prog.add(name, self.lib.dp_wgrad_bf16, C.byref(a), keep=(a, A, B, out))
+
+    # ------------------------------------------------------------------ backbone row-wise
+    def layernorm_fwd(self, x, gamma, beta, y_bf16, y_f32, *, rows, D, T=0, drop_cls=False, eps=1e-6):
+        _chk(x, torch.float32, "ln.x", False)
+        self.prog.add("layernorm_fwd", self.lib.dp_layernorm_fwd, _p(x), _p(gamma), _p(beta), _p(y_bf16), _p(y_f32),
+                      rows, D, T, int(drop_cls), eps, keep=(x, gamma, beta, y_bf16, y_f32))
+
+    def layernorm_bwd(self, dy, x, gamma, add_in, dx, *, rows, D, T=0, drop_cls=False, eps=1e-6, ls=None,
+                      dx_scaled=None):
+        self.prog.add("layernorm_bwd", self.lib.dp_layernorm_bwd, _p(dy), int(dy.dtype == torch.bfloat16), _p(x),
+                      _p(gamma), _p(add_in), _p(dx), _p(ls), _p(dx_scaled), rows, D, T, int(drop_cls), eps,
+                      keep=(dy, x, gamma, add_in, dx, ls, dx_scaled))
+
+    def patch_im2col(self, px, out, *, B, H, W, Kp):
+        _chk(px, torch.float32, "patch_im2col.pixel_values")
+        self.prog.add("patch_im2col", self.lib.dp_patch_im2col, _p(px), _p(out), B, H, W, Kp, keep=(px, out))
+
+    def fill_cls(self, x, cls_row, *, B, T, D):
+        self.prog.add("fill_cls", self.lib.dp_fill_cls, _p(x), _p(cls_row), B, T, D, keep=(x, cls_row))
+
+    def lora_fwd(self, y, A, Bm, lambda1, x_in, x_out, u_save, *, rows, D, R, scaling, p_drop, seed):
+        self.prog.add("lora_fwd", self.lib.dp_lora_fwd, _p(y), _p(A), _p(Bm), _p(lambda1), _p(x_in), _p(x_out),
+                      _p(u_save), rows, D, R, scaling, p_drop, _p(seed), keep=(y, A, Bm, lambda1, x_in, x_out, u_save, seed))
+
+    def lora_bwd(self, g, y, u_saved, Bm, lambda1, dA, dB, *, rows, D, R, scaling, p_drop, seed):
+        self.prog.add("lora_bwd", self.lib.dp_lora_bwd, _p(g), _p(y), _p(u_saved), _p(Bm), _p(lambda1), _p(dA), _p(dB),
+                      rows, D, R, scaling, p_drop, _p(seed), keep=(g, y, u_saved, Bm, lambda1, dA, dB, seed))
+
+    def attention_fwd(self, qkv, ctx, *, B, T, heads, scale):
+        _chk(qkv, torch.bfloat16, "attention.qkv")
+        self.prog.add("attention_fwd", self.lib.dp_attention_fwd, _p(qkv), _p(ctx), B, T, heads, scale, keep=(qkv, ctx))
+
+    def decode(self, hm, idx, xy, conf, *, maps, H, W, target_w, target_h):
+        _chk(hm, torch.float32, "decode.heatmaps")
+        self.prog.add("decode", self.lib.dp_decode, _p(hm), maps, H, W, float(target_w), float(target_h), _p(idx),
+                      _p(xy), _p(conf), keep=(hm, idx, xy, conf))
+
+    # ------------------------------------------------------------------ heads
+    def im2col(self, x, col, *, NB, IH, IW, C, OH, OW, KH, KW, stride, pad):
+        self.prog.add("im2col", self.lib.dp_im2col, _p(x), _p(col), NB, IH, IW, C, OH, OW, KH, KW, stride, pad,
+                      keep=(x, col))
+
+    def col2im(self, col, bias, big, *, NB, SH, SW, C, BH, BW, KH, KW, stride, pad):
+        self.prog.add("col2im", self.lib.dp_col2im, _p(col), _p(bias), _p(big), NB, SH, SW, C, BH, BW, KH, KW, stride,
+                      pad, keep=(col, bias, big))
+
+    def dwconv3x3(self, x, w, bias, add, out, *, NB, H, W, C, flip=False):
+        self.prog.add("dwconv3x3", self.lib.dp_dwconv3x3, _p(x), _p(w), _p(bias), _p(add), _p(out), NB, H, W, C,
+                      int(flip), keep=(x, w, bias, add, out))
+
+    def dwconv3x3_wgrad(self, x, dout, dw, *, NB, H, W, C):
+        self.prog.add("dwconv3x3_wgrad", self.lib.dp_dwconv3x3_wgrad, _p(x), _p(dout), _p(dw), NB, H, W, C,
+                      keep=(x, dout, dw))
+
+    def bn_stats(self, raw, sums, *, P, C):
+        self.prog.add("bn_stats", self.lib.dp_bn_stats, _p(raw), _p(sums), P, C, keep=(raw, sums))
+
+    def bn_finalize(self, sums, gamma, beta, rm, rv, scale, shift, mean, invstd, *, C, count, eps=1e-5, momentum=0.1):
+        self.prog.add("bn_finalize", self.lib.dp_bn_finalize, _p(sums), _p(gamma), _p(beta), _p(rm), _p(rv), _p(scale),
+                      _p(shift), _p(mean), _p(invstd), C, float(count), eps, momentum,
+                      keep=(sums, gamma, beta, rm, rv, scale, shift, mean, invstd))
+
+    def bn_fold_eval(self, gamma, beta, rm, rv, conv_bias, scale, shift, *, C, eps=1e-5):
+        self.prog.add("bn_fold_eval", self.lib.dp_bn_fold_eval, _p(gamma), _p(beta), _p(rm), _p(rv), _p(conv_bias),
+                      _p(scale), _p(shift), C, eps, keep=(gamma, beta, rm, rv, conv_bias, scale, shift))
+
+    def bn_apply(self, raw, scale, shift, add1, add2, out, *, P, C, relu=True, mode=0):
+        self.prog.add("bn_apply", self.lib.dp_bn_apply, _p(raw), _p(scale), _p(shift), _p(add1), _p(add2), _p(out), P,
+                      C, int(relu), mode, keep=(raw, scale, shift, add1, add2, out))
+
+    def bn_bwd_reduce(self, dout, raw, add1, scale, shift, mean, invstd, sums, *, P, C, relu=True, mode=0):
+        self.prog.add("bn_bwd_reduce", self.lib.dp_bn_bwd_reduce, _p(dout), _p(raw), _p(add1), _p(scale), _p(shift),
+                      _p(mean), _p(invstd), _p(sums), P, C, int(relu), mode,
+                      keep=(dout, raw, add1, scale, shift, mean, invstd, sums))
+
+    def bn_bwd_apply(self, dout, raw, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta, *, P, C,
+                     relu=True, mode=0, eval_mode=False, shuffle_oh=0, shuffle_ow=0):
+        self.prog.add("bn_bwd_apply", self.lib.dp_bn_bwd_apply, _p(dout), _p(raw), _p(add1), _p(gamma), _p(scale),
+                      _p(shift), _p(mean), _p(invstd), _p(sums), _p(draw), _p(dres), _p(dgamma), _p(dbeta), P, C,
+                      int(relu), mode, int(eval_mode), shuffle_oh, shuffle_ow,
+                      keep=(dout, raw, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta))
+
+    def avgpool2(self, x, out, *, planes, OH, OW):
+        self.prog.add("avgpool2", self.lib.dp_avgpool2, _p(x), _p(out), planes, OH, OW, keep=(x, out))
+
+    def hm_grad_to_nhwc(self, g, out, *, NB, K, Kp, OH, OW, up):
+        _chk(g, torch.float32, "hm_grad")
+        self.prog.add("hm_grad_to_nhwc", self.lib.dp_hm_grad_to_nhwc, _p(g), _p(out), NB, K, Kp, OH, OW, up,
+                      keep=(g, out))
+
+    def mean_tokens(self, feat, out, *, B, N, D):
+        self.prog.add("mean_tokens", self.lib.dp_mean_tokens, _p(feat), _p(out), B, N, D, keep=(feat, out))
+
+    def mean_tokens_bwd(self, dfeat, dmean, *, B, N, D):
+        self.prog.add("mean_tokens_bwd", self.lib.dp_mean_tokens_bwd, _p(dfeat), _p(dmean), B, N, D, keep=(dfeat, dmean))
+
+    def sgemm_small(self, A, sa_m, sa_k, Bm, sb_k, sb_n, Cm, ldc, *, M, N, K, bias=None, relu=False, mask_ref=None,
+                    ld_ref=0, p_drop=0.0, seed=None, accumulate=False):
+        self.prog.add("sgemm_small", self.lib.dp_sgemm_small, _p(A), sa_m, sa_k, _p(Bm), sb_k, sb_n, _p(Cm), ldc, M, N, K,
+                      _p(bias), int(relu), _p(mask_ref), ld_ref, p_drop, _p(seed), int(accumulate),
+                      keep=(A, Bm, Cm, bias, mask_ref, seed))
+
+    def colsum(self, x, out, *, P, C, ld):
+        self.prog.add("colsum", self.lib.dp_colsum, _p(x), int(x.dtype == torch.bfloat16), _p(out), P, C, ld,
+                      keep=(x, out))
+
+    # ------------------------------------------------------------------ host-side steps on static tensors
+    def host(self, name, fn):
+        """Record a torch-level step (memset of gradient buffers, seed increment, ...)."""
+        self.prog.add_callable(name, fn)

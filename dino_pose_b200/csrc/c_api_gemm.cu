@@ -1,0 +1,234 @@
+// Host side of the tcgen05 GEMM / implicit-conv / weight-gradient entry points: argument checking,
+// TMA tensor-map encoding (driver entry point fetched through the runtime, no libcuda link
+// dependency), tile-shape selection and launch.
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/dinopose.h"
+#include "gemm_tc.cuh"
+
+namespace dp {
+cudaError_t launch_gemm(const GemmParams& p, int block_n, int grid, cudaStream_t s);
+cudaError_t launch_wgrad(const WgradParams& p, int block_n, int grid, cudaStream_t s);
+
+static thread_local char g_err[512] = "";
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_error(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return int(e);
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 tensor map, 128B swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..rank-1.
+static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
+                     const uint32_t* box) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return set_error(-10, "cuTensorMapEncodeTiled entry point unavailable");
+  if (reinterpret_cast<uintptr_t>(ptr) & 15) return set_error(-11, "TMA base pointer %p not 16-byte aligned", ptr);
+  cuuint64_t d[5], st[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    d[i] = dims[i];
+    b[i] = box[i];
+    es[i] = 1;
+    if (box[i] == 0 || box[i] > 256) return set_error(-12, "TMA box dim %d = %u out of range", i, box[i]);
+  }
+  for (int i = 0; i + 1 < rank; ++i) {
+    st[i] = strides[i];
+    if (strides[i] & 15) return set_error(-13, "TMA stride %d = %llu bytes not a multiple of 16", i,
+                                          (unsigned long long)strides[i]);
+  }
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), d, st, b, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_error(-14, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
+  return 0;
+}
+
+static int pow2_ge(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+// pixel box (bw, bh, bb) with bw*bh*bb == pixels for an OW x OH output map
+static void choose_box(int OW, int OH, int pixels, int* bw, int* bh, int* bb) {
+  int w = OW >= 16 ? 16 : pow2_ge(OW);
+  if (w > pixels) w = pixels;
+  int h = pow2_ge(OH);
+  if (h > pixels / w) h = pixels / w;
+  *bw = w;
+  *bh = h;
+  *bb = pixels / (w * h);
+}
+
+}  // namespace dp
+
+using namespace dp;
+
+extern "C" const char* dp_last_error(void) { return g_err; }
+extern "C" int dp_abi_version(void) { return DP_ABI_VERSION; }
+extern "C" int dp_sizeof_gemm_args(void) { return int(sizeof(dp_gemm_args)); }
+extern "C" int dp_sizeof_wgrad_args(void) { return int(sizeof(dp_wgrad_args)); }
+
+extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
+  if (!a || !a->A || !a->W || !a->out) return set_error(-1, "dp_gemm_bf16: null pointer");
+  if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(-2, "dp_gemm_bf16: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  int bn = a->block_n;
+  if (bn == 0) bn = a->N >= 128 ? 128 : (a->N > 32 ? 64 : 32);
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(-3, "dp_gemm_bf16: block_n %d", bn);
+  p.N = a->N;
+  p.n_tiles = (a->N + bn - 1) / bn;
+  p.a_mode = a->a_mode;
+  int rc;
+  if (a->a_mode == 0) {
+    p.M = a->M;
+    p.m_tiles = (a->M + 127) / 128;
+    p.num_k_blocks = (a->K + 63) / 64;
+    const uint64_t dims[2] = {uint64_t(a->K), uint64_t(a->M)};
+    const uint64_t st[1] = {uint64_t(a->lda) * 2};
+    const uint32_t box[2] = {64, 128};
+    if ((rc = make_tmap(&p.tmA, a->A, 2, dims, st, box))) return rc;
+    p.OH = a->OH > 0 ? a->OH : 1;
+    p.OW = a->OW > 0 ? a->OW : 1;
+    p.NB = a->NB;
+  } else {
+    if (a->C % 64) return set_error(-4, "dp_gemm_bf16: implicit conv needs C %% 64 == 0 (C=%d)", a->C);
+    if (a->K != a->KH * a->KW * a->C) return set_error(-5, "dp_gemm_bf16: K != KH*KW*C");
+    if (a->M != a->NB * a->OH * a->OW) return set_error(-5, "dp_gemm_bf16: M != NB*OH*OW");
+    choose_box(a->OW, a->OH, 128, &p.bw, &p.bh, &p.bb);
+    p.OW = a->OW; p.OH = a->OH; p.NB = a->NB;
+    p.tiles_x = (a->OW + p.bw - 1) / p.bw;
+    p.tiles_y = (a->OH + p.bh - 1) / p.bh;
+    const int tiles_b = (a->NB + p.bb - 1) / p.bb;
+    p.M = a->M;
+    p.m_tiles = p.tiles_x * p.tiles_y * tiles_b;
+    p.kw = a->KW; p.pad_x = a->pad_x; p.pad_y = a->pad_y;
+    p.cin_blocks = a->C / 64;
+    p.num_k_blocks = a->KH * a->KW * p.cin_blocks;
+    const uint64_t dims[4] = {uint64_t(a->C), uint64_t(a->IW), uint64_t(a->IH), uint64_t(a->NB)};
+    const uint64_t st[3] = {uint64_t(a->a_stride_w) * 2, uint64_t(a->a_stride_h) * 2, uint64_t(a->a_stride_b) * 2};
+    const uint32_t box[4] = {64, uint32_t(p.bw), uint32_t(p.bh), uint32_t(p.bb)};
+    if ((rc = make_tmap(&p.tmA, a->A, 4, dims, st, box))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {uint64_t(a->K), uint64_t(a->N)};
+    const uint64_t st[1] = {uint64_t(a->ldw) * 2};
+    const uint32_t box[2] = {64, uint32_t(bn)};
+    if ((rc = make_tmap(&p.tmB, a->W, 2, dims, st, box))) return rc;
+  }
+  Epilogue& e = p.epi;
+  e.out = a->out; e.bias = a->bias; e.scale = a->scale; e.ls = a->ls; e.residual = static_cast<const float*>(a->residual); e.res_is_bf16 = a->res_is_bf16;
+  e.aux_out = a->aux_out; e.aux_in = a->aux_in;
+  e.ldo = a->ldo; e.ldr = a->ldr; e.ld_aux = a->ld_aux;
+  e.out_dtype = a->out_dtype; e.act = a->act; e.row_map = a->row_map;
+  e.n_valid = a->n_valid > 0 ? a->n_valid : a->N;
+  e.map_a = a->map_a; e.map_b = a->map_b;
+  if (e.n_valid > a->N) return set_error(-6, "dp_gemm_bf16: n_valid > N");
+  if (e.row_map == DP_ROWMAP_IDENTITY || e.row_map == DP_ROWMAP_PATCH_TOKENS) {
+    const long long align = (e.out_dtype == DP_OUT_BF16) ? 8 : 4;
+    if (e.ldo % align) return set_error(-7, "dp_gemm_bf16: ldo %lld must be a multiple of %lld", e.ldo, align);
+  }
+  if (e.row_map == DP_ROWMAP_SHUFFLE2X2 && (e.map_a % 32 || e.map_a <= 0))
+    return set_error(-8, "dp_gemm_bf16: shuffle map needs Cout %% 32 == 0");
+  if ((e.row_map == DP_ROWMAP_NCHW || e.row_map == DP_ROWMAP_SHUFFLE2X2) && (a->OH <= 0 || a->OW <= 0))
+    return set_error(-8, "dp_gemm_bf16: row map needs OH/OW");
+  const int tiles = p.m_tiles * p.n_tiles;
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  return cuda_error(launch_gemm(p, bn, grid, static_cast<cudaStream_t>(stream)), "dp_gemm_bf16 launch");
+}
+
+extern "C" int dp_wgrad_bf16(const dp_wgrad_args* a, void* stream) {
+  if (!a || !a->A || !a->B || !a->out) return set_error(-1, "dp_wgrad_bf16: null pointer");
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  int bn = a->block_n;
+  if (bn == 0) bn = a->Nc >= 128 ? 128 : 64;
+  if (bn != 64 && bn != 128) return set_error(-3, "dp_wgrad_bf16: block_n %d", bn);
+  p.out = a->out;
+  p.so_m = a->so_m; p.so_mo = a->so_mo; p.so_n = a->so_n; p.so_no = a->so_no; p.so_t = a->so_t;
+  p.m_inner = a->m_inner > 0 ? a->m_inner : 0x7fffffff;
+  p.n_inner = a->n_inner > 0 ? a->n_inner : 0x7fffffff;
+  p.Mc = a->Mc; p.Nc = a->Nc;
+  p.m_tiles = (a->Mc + 127) / 128;
+  p.n_tiles = (a->Nc + bn - 1) / bn;
+  p.mode = a->mode;
+  int rc;
+  if (a->mode == 0) {
+    p.taps = 1; p.kw = 1;
+    p.total_k_blocks = (a->P + 63) / 64;
+    const uint64_t da[2] = {uint64_t(a->Mc), uint64_t(a->P)};
+    const uint64_t sa[1] = {uint64_t(a->lda) * 2};
+    const uint64_t db[2] = {uint64_t(a->Nc), uint64_t(a->P)};
+    const uint64_t sb[1] = {uint64_t(a->ldb) * 2};
+    const uint32_t box[2] = {64, 64};
+    if ((rc = make_tmap(&p.tmA, a->A, 2, da, sa, box))) return rc;
+    if ((rc = make_tmap(&p.tmB, a->B, 2, db, sb, box))) return rc;
+  } else {
+    p.taps = a->KH * a->KW; p.kw = a->KW; p.pad_x = a->pad_x; p.pad_y = a->pad_y;
+    choose_box(a->OW, a->OH, 64, &p.bw, &p.bh, &p.bb);
+    p.tiles_x = (a->OW + p.bw - 1) / p.bw;
+    p.tiles_y = (a->OH + p.bh - 1) / p.bh;
+    p.tiles_b = (a->NB + p.bb - 1) / p.bb;
+    p.total_k_blocks = p.tiles_x * p.tiles_y * p.tiles_b;
+    const uint64_t da[4] = {uint64_t(a->Mc), uint64_t(a->OW), uint64_t(a->OH), uint64_t(a->NB)};
+    const uint64_t sa[3] = {uint64_t(a->a_sw) * 2, uint64_t(a->a_sh) * 2, uint64_t(a->a_sb) * 2};
+    const uint64_t db[4] = {uint64_t(a->Nc), uint64_t(a->IW), uint64_t(a->IH), uint64_t(a->NB)};
+    const uint64_t sb[3] = {uint64_t(a->b_sw) * 2, uint64_t(a->b_sh) * 2, uint64_t(a->b_sb) * 2};
+    const uint32_t box[4] = {64, uint32_t(p.bw), uint32_t(p.bh), uint32_t(p.bb)};
+    if ((rc = make_tmap(&p.tmA, a->A, 4, da, sa, box))) return rc;
+    if ((rc = make_tmap(&p.tmB, a->B, 4, db, sb, box))) return rc;
+  }
+  const int base_items = p.taps * p.m_tiles * p.n_tiles;
+  int splits = a->splits;
+  if (splits <= 0) {
+    splits = (2 * sm_count() + base_items - 1) / base_items;
+    const int max_by_k = (p.total_k_blocks + 3) / 4;  // at least 4 k-blocks per split
+    if (splits > max_by_k) splits = max_by_k;
+    if (splits < 1) splits = 1;
+  }
+  if (splits > p.total_k_blocks) splits = p.total_k_blocks;
+  // make sure no split is empty
+  while (splits > 1 && ((p.total_k_blocks + splits - 1) / splits) * (splits - 1) >= p.total_k_blocks) --splits;
+  p.splits = splits;
+  const int items = base_items * splits;
+  const int grid = items < sm_count() ? items : sm_count();
+  return cuda_error(launch_wgrad(p, bn, grid, static_cast<cudaStream_t>(stream)), "dp_wgrad_bf16 launch");
+}

@@ -1,0 +1,659 @@
+// Memory-bound kernels of the pose heads (reference model/pose_heads.py:211-400), NHWC bf16 activations:
+// im2col / col2im for the strided and transposed convolutions, depthwise 3x3, train-mode BatchNorm
+// (statistics, finalize + running-stat update, apply with fused ReLU / residual adds) and its backward,
+// bilinear 2x reduction, token mean-pool, fp32 SIMT GEMM for the tiny z-head MLP, layout conversions.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace dp {
+
+namespace {
+
+__device__ __forceinline__ void unpack8(const uint4& t, float (&f)[8]) {
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+    f[2 * k] = __low2float(h);
+    f[2 * k + 1] = __high2float(h);
+  }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  uint4 t;
+  t.x = pack_bf16x2(f[0], f[1]);
+  t.y = pack_bf16x2(f[2], f[3]);
+  t.z = pack_bf16x2(f[4], f[5]);
+  t.w = pack_bf16x2(f[6], f[7]);
+  return t;
+}
+inline unsigned grid_for(long long n, int block, int max_blocks = 148 * 16) {
+  long long g = (n + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return unsigned(g);
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col: in NHWC [NB,IH,IW,C] -> col [NB*OH*OW, KH*KW*C], column = (ky*KW + kx)*C + c, zero padding.
+__global__ void __launch_bounds__(256) im2col_kernel(const uint4* __restrict__ in, uint4* __restrict__ col, int NB, int IH,
+                                                     int IW, int C8, int OH, int OW, int KH, int KW, int stride, int pad) {
+  const long long total = (long long)NB * OH * OW * KH * KW * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C8);
+    long long r = i / C8;
+    const int kx = int(r % KW); r /= KW;
+    const int ky = int(r % KH); r /= KH;
+    const int ox = int(r % OW); r /= OW;
+    const int oy = int(r % OH);
+    const int b = int(r / OH);
+    const int iy = oy * stride - pad + ky, ix = ox * stride - pad + kx;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (iy >= 0 && iy < IH && ix >= 0 && ix < IW) v = __ldg(in + (((long long)b * IH + iy) * IW + ix) * C8 + c);
+    col[i] = v;
+  }
+}
+
+// col2im (gather form): big[b,y,x,c] = bias[c] + sum_{ky,kx} col[(b,sy,sx), (ky*KW+kx)*C + c]
+// over taps with y = sy*stride - pad + ky, x = sx*stride - pad + kx, (sy,sx) inside the small SHxSW grid.
+// Forward of ConvTranspose2d (small = input grid) and input-gradient of a strided Conv2d (small = output grid).
+__global__ void __launch_bounds__(256) col2im_kernel(const uint4* __restrict__ col, const float* __restrict__ bias,
+                                                     uint4* __restrict__ big, int NB, int SH, int SW, int C8, int BH, int BW,
+                                                     int KH, int KW, int stride, int pad) {
+  const long long total = (long long)NB * BH * BW * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C8);
+    long long r = i / C8;
+    const int x = int(r % BW); r /= BW;
+    const int y = int(r % BH);
+    const int b = int(r / BH);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? __ldg(bias + c * 8 + j) : 0.f;
+    for (int ky = 0; ky < KH; ++ky) {
+      const int ty = y + pad - ky;
+      if (ty < 0 || ty % stride) continue;
+      const int sy = ty / stride;
+      if (sy >= SH) continue;
+      for (int kx = 0; kx < KW; ++kx) {
+        const int tx = x + pad - kx;
+        if (tx < 0 || tx % stride) continue;
+        const int sx = tx / stride;
+        if (sx >= SW) continue;
+        const uint4 t = __ldg(col + ((((long long)b * SH + sy) * SW + sx) * (KH * KW) + (ky * KW + kx)) * C8 + c);
+        float f[8];
+        unpack8(t, f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+      }
+    }
+    big[i] = pack8(acc);
+  }
+}
+
+// depthwise 3x3, pad 1 (HourglassModule.depthwise_conv[0], pose_heads.py:219).  w fp32 [C,1,3,3].
+// flip = 1 gives the input-gradient (correlation with the flipped kernel).
+__global__ void __launch_bounds__(256) dwconv3x3_kernel(const uint4* __restrict__ in, const float* __restrict__ w,
+                                                        const float* __restrict__ bias, const uint4* __restrict__ add,
+                                                        uint4* __restrict__ out, int NB, int H, int W, int C8, int flip) {
+  const long long total = (long long)NB * H * W * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C8);
+    long long r = i / C8;
+    const int x = int(r % W); r /= W;
+    const int y = int(r % H);
+    const int b = int(r / H);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias ? __ldg(bias + c * 8 + j) : 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int iy = y + ky - 1;
+      if (iy < 0 || iy >= H) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = x + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        const uint4 t = __ldg(in + (((long long)b * H + iy) * W + ix) * C8 + c);
+        float f[8];
+        unpack8(t, f);
+        const int tap = flip ? (2 - ky) * 3 + (2 - kx) : ky * 3 + kx;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j] * __ldg(w + (c * 8 + j) * 9 + tap);
+      }
+    }
+    if (add != nullptr) {
+      float f[8];
+      unpack8(__ldg(add + i), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    out[i] = pack8(acc);
+  }
+}
+
+// depthwise weight gradient: dW[c,tap] += sum_p dRaw[p,c] * in[p+tap,c].  One block per (row chunk, 64 channels).
+__global__ void __launch_bounds__(256) dwconv3x3_wgrad_kernel(const __nv_bfloat16* __restrict__ in,
+                                                              const __nv_bfloat16* __restrict__ dout, float* __restrict__ dw,
+                                                              int NB, int H, int W, int C, int rows_per_block) {
+  // thread = (channel within 64-block, pixel lane); each thread accumulates 9 taps for one channel
+  const int c = blockIdx.y * 64 + (threadIdx.x & 63);
+  const int pl = threadIdx.x >> 6;  // 0..3
+  const long long P = (long long)NB * H * W;
+  const long long p0 = (long long)blockIdx.x * rows_per_block;
+  const long long p1 = min(p0 + rows_per_block, P);
+  float acc[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
+  if (c < C) {
+    for (long long p = p0 + pl; p < p1; p += 4) {
+      const int x = int(p % W);
+      const int y = int((p / W) % H);
+      const long long b = p / ((long long)W * H);
+      const float g = __bfloat162float(dout[p * C + c]);
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int iy = y + ky - 1;
+        if (iy < 0 || iy >= H) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int ix = x + kx - 1;
+          if (ix < 0 || ix >= W) continue;
+          acc[ky * 3 + kx] += g * __bfloat162float(in[((b * H + iy) * W + ix) * C + c]);
+        }
+      }
+    }
+  }
+  __shared__ float red[4][64][9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) red[pl][threadIdx.x & 63][t] = acc[t];
+  __syncthreads();
+  if (pl == 0 && c < C) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int cc = threadIdx.x & 63;
+      atomicAdd(dw + c * 9 + t, red[0][cc][t] + red[1][cc][t] + red[2][cc][t] + red[3][cc][t]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm statistics: per-channel sum and sum of squares of raw bf16 [P, C] (fp32 partials per block,
+// fp64 atomics across blocks).  blockDim.x = C/2 (one bf16 pair per thread).
+__global__ void bn_stats_kernel(const __nv_bfloat162* __restrict__ raw, double* __restrict__ sums, long long P, int C2,
+                                int rows_per_block) {
+  const int c = threadIdx.x + blockIdx.y * blockDim.x;
+  if (c >= C2) return;
+  const long long p0 = (long long)blockIdx.x * rows_per_block;
+  const long long p1 = min(p0 + rows_per_block, P);
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (long long p = p0; p < p1; ++p) {
+    const __nv_bfloat162 v = raw[p * C2 + c];
+    const float a = __low2float(v), b = __high2float(v);
+    s0 += a; s1 += b;
+    q0 += a * a; q1 += b * b;
+  }
+  atomicAdd(sums + 2 * c, double(s0));
+  atomicAdd(sums + 2 * c + 1, double(s1));
+  atomicAdd(sums + 2 * C2 + 2 * c, double(q0));
+  atomicAdd(sums + 2 * C2 + 2 * c + 1, double(q1));
+}
+
+// finalize: batch mean / biased var -> scale, shift (y = raw*scale + shift), saved mean / invstd,
+// running statistics update with momentum (unbiased variance), then zero `sums` for the next step.
+__global__ void bn_finalize_kernel(double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ invstd_out, int C, double count, float eps, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double mean = sums[c] / count;
+  double var = sums[C + c] / count - mean * mean;
+  if (var < 0) var = 0;
+  const float invstd = float(1.0 / sqrt(var + double(eps)));
+  const float sc = gamma[c] * invstd;
+  scale[c] = sc;
+  shift[c] = beta[c] - float(mean) * sc;
+  mean_out[c] = float(mean);
+  invstd_out[c] = invstd;
+  if (running_mean != nullptr) {
+    const double unbiased = count > 1 ? var * count / (count - 1) : var;
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * float(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * float(unbiased);
+  }
+  sums[c] = 0.0;
+  sums[C + c] = 0.0;
+}
+
+// eval-mode fold: scale = gamma / sqrt(running_var + eps); shift = beta + (conv_bias - running_mean) * scale
+__global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                                    const float* __restrict__ rm, const float* __restrict__ rv,
+                                    const float* __restrict__ conv_bias, float* __restrict__ scale,
+                                    float* __restrict__ shift, int C, float eps) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const float sc = gamma[c] * rsqrtf(rv[c] + eps);
+  scale[c] = sc;
+  shift[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * sc;
+}
+
+// apply: y = raw*scale + shift;  mode 0: out = relu?(y) + add1 + add2      (HourglassModule 3-way sum, :285)
+//                                 mode 1: out = relu(y + add1)              (bottleneck residual, :277-278)
+__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ scale,
+                                                       const float* __restrict__ shift, const uint4* __restrict__ add1,
+                                                       const uint4* __restrict__ add2, uint4* __restrict__ out,
+                                                       long long P, int C8, int relu, int mode) {
+  const long long total = P * C8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C8) * 8;
+    float f[8], a[8];
+    unpack8(__ldg(raw + i), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] * __ldg(scale + c + j) + __ldg(shift + c + j);
+    if (mode == 1) {
+      unpack8(__ldg(add1 + i), a);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j] + a[j], 0.f);
+    } else {
+      if (relu) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      }
+      if (add1 != nullptr) {
+        unpack8(__ldg(add1 + i), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += a[j];
+      }
+      if (add2 != nullptr) {
+        unpack8(__ldg(add2 + i), a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += a[j];
+      }
+    }
+    out[i] = pack8(f);
+  }
+}
+
+// BatchNorm backward, pass 1: with y = raw*scale+shift, xhat = (raw-mean)*invstd,
+//   dy = dout * [y > 0]            (mode 0, relu)      | dy = dout * [y + add1 > 0]   (mode 1)
+//   sums[c] += dy ; sums[C + c] += dy * xhat
+// blockDim.x = C/2.
+__global__ void bn_bwd_reduce_kernel(const __nv_bfloat162* __restrict__ dout, const __nv_bfloat162* __restrict__ raw,
+                                     const __nv_bfloat162* __restrict__ add1, const float* __restrict__ scale,
+                                     const float* __restrict__ shift, const float* __restrict__ mean,
+                                     const float* __restrict__ invstd, double* __restrict__ sums, long long P, int C2,
+                                     int rows_per_block, int relu, int mode) {
+  const int c = threadIdx.x + blockIdx.y * blockDim.x;
+  if (c >= C2) return;
+  const float sc0 = scale[2 * c], sc1 = scale[2 * c + 1], sh0 = shift[2 * c], sh1 = shift[2 * c + 1];
+  const float m0 = mean[2 * c], m1 = mean[2 * c + 1], i0 = invstd[2 * c], i1 = invstd[2 * c + 1];
+  const long long p0 = (long long)blockIdx.x * rows_per_block;
+  const long long p1 = min(p0 + rows_per_block, P);
+  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+  for (long long p = p0; p < p1; ++p) {
+    const __nv_bfloat162 r = raw[p * C2 + c];
+    const __nv_bfloat162 g = dout[p * C2 + c];
+    const float ra = __low2float(r), rb = __high2float(r);
+    float ga = __low2float(g), gb = __high2float(g);
+    float ya = ra * sc0 + sh0, yb = rb * sc1 + sh1;
+    if (mode == 1) {
+      const __nv_bfloat162 a = add1[p * C2 + c];
+      ya += __low2float(a);
+      yb += __high2float(a);
+    }
+    if (relu || mode == 1) {
+      ga = ya > 0.f ? ga : 0.f;
+      gb = yb > 0.f ? gb : 0.f;
+    }
+    s0 += ga; s1 += gb;
+    q0 += ga * (ra - m0) * i0;
+    q1 += gb * (rb - m1) * i1;
+  }
+  atomicAdd(sums + 2 * c, double(s0));
+  atomicAdd(sums + 2 * c + 1, double(s1));
+  atomicAdd(sums + 2 * C2 + 2 * c, double(q0));
+  atomicAdd(sums + 2 * C2 + 2 * c + 1, double(q1));
+}
+
+// pass 2: draw = gamma*invstd * (dy - S1/P - xhat*S2/P)  (train)   |   draw = dy * scale (eval_mode)
+// Also emits dgamma = S2, dbeta = S1 (block 0) and, for mode 1, the masked gradient of the residual branch.
+// shuffle_cout > 0: write draw in the un-shuffled [P/4, 4*Cout] "col" layout of a k2 s2 transposed conv
+// (row = input pixel, column = tap*Cout + co), the operand layout of its weight / input gradients.
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ raw,
+                                                           const uint4* __restrict__ add1, const float* __restrict__ gamma,
+                                                           const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                           const double* __restrict__ sums, uint4* __restrict__ draw,
+                                                           uint4* __restrict__ dres, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, long long P, int C8, int relu,
+                                                           int mode, int eval_mode, int shuffle_oh, int shuffle_ow) {
+  const int C = C8 * 8;
+  const long long total = P * C8;
+  const float invP = 1.0f / float(P);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C8) * 8;
+    float r[8], g[8], a[8], o[8];
+    unpack8(__ldg(raw + i), r);
+    unpack8(__ldg(dout + i), g);
+    if (mode == 1) unpack8(__ldg(add1 + i), a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = r[j] * __ldg(scale + c + j) + __ldg(shift + c + j);
+      if (mode == 1) y += a[j];
+      if ((relu || mode == 1) && !(y > 0.f)) g[j] = 0.f;
+      if (eval_mode) {
+        o[j] = g[j] * __ldg(scale + c + j);
+      } else {
+        const float xhat = (r[j] - __ldg(mean + c + j)) * __ldg(invstd + c + j);
+        const float s1 = float(sums[c + j]) * invP, s2 = float(sums[C + c + j]) * invP;
+        o[j] = __ldg(gamma + c + j) * __ldg(invstd + c + j) * (g[j] - s1 - xhat * s2);
+      }
+    }
+    long long oi = i;
+    if (shuffle_oh > 0) {
+      // i indexes the shuffled NHWC output [NB, 2*ih, 2*iw, C]; destination is [NB*ih*iw, 4*C]
+      long long p = i / C8;
+      const int x = int(p % shuffle_ow); p /= shuffle_ow;
+      const int y = int(p % shuffle_oh);
+      const long long b = p / shuffle_oh;
+      const int ih = shuffle_oh / 2, iw = shuffle_ow / 2;
+      const int tap = (y & 1) * 2 + (x & 1);
+      oi = (((b * ih + (y >> 1)) * iw + (x >> 1)) * 4 + tap) * C8 + (i % C8);
+    }
+    draw[oi] = pack8(o);
+    if (dres != nullptr) dres[i] = pack8(g);
+  }
+  if (blockIdx.x == 0 && dgamma != nullptr) {
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      dbeta[c] = float(sums[c]);
+      dgamma[c] = float(sums[C + c]);
+    }
+  }
+}
+
+__global__ void zero_f64_kernel(double* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2x2 mean (bilinear align_corners=False at exact scale 1/2, pose_heads.py:353-359) fp32 NCHW; and its adjoint.
+__global__ void avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, long long planes, int OH, int OW) {
+  const long long total = planes * OH * OW;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int x = int(i % OW);
+    const int y = int((i / OW) % OH);
+    const long long pl = i / ((long long)OW * OH);
+    const float* s = in + (pl * 2 * OH + 2 * y) * (2 * OW) + 2 * x;
+    // same association as the separable bilinear kernel: horizontal lerp then vertical lerp, weights 0.5
+    const float top = 0.5f * s[0] + 0.5f * s[1];
+    const float bot = 0.5f * s[2 * OW] + 0.5f * s[2 * OW + 1];
+    out[i] = 0.5f * top + 0.5f * bot;
+  }
+}
+
+// heat-map gradient fp32 NCHW [NB,K,GH,GW] -> bf16 NHWC [NB*OH*OW, Kp] (zero padded channels);
+// up = 2 additionally applies the adjoint of avgpool2 (each fine pixel gets 0.25 * coarse gradient).
+__global__ void hm_grad_to_nhwc_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ out, int NB, int K, int Kp,
+                                       int OH, int OW, int up) {
+  const long long total = (long long)NB * OH * OW * Kp;
+  const int GH = OH / up, GW = OW / up;
+  const float w = up == 2 ? 0.25f : 1.0f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = int(i % Kp);
+    long long r = i / Kp;
+    const int x = int(r % OW); r /= OW;
+    const int y = int(r % OH);
+    const long long b = r / OH;
+    float v = 0.f;
+    if (k < K) v = w * __ldg(g + ((b * K + k) * GH + y / up) * GW + x / up);
+    out[i] = __float2bfloat16_rn(v);
+  }
+}
+
+// mean over the N patch tokens: feat bf16 [B, N, D] -> fp32 [B, D]   (pose_heads.py:397)
+__global__ void mean_tokens_kernel(const __nv_bfloat16* __restrict__ feat, float* __restrict__ out, int N, int D) {
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  float s = 0.f;
+  for (int n = 0; n < N; ++n) s += __bfloat162float(feat[((long long)b * N + n) * D + d]);
+  out[(long long)b * D + d] = s / float(N);
+}
+// adjoint: dfeat[b, n, :] += dmean[b, :] / N   (bf16 in place)
+__global__ void mean_tokens_bwd_kernel(__nv_bfloat16* __restrict__ dfeat, const float* __restrict__ dmean, int N, int D,
+                                       long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = int(i % D);
+    const long long b = i / ((long long)N * D);
+    dfeat[i] = __float2bfloat16_rn(__bfloat162float(dfeat[i]) + __ldg(dmean + b * D + d) / float(N));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Small fp32 GEMM for the z-head MLP (M = batch): C[m,n] = sum_k A(m,k) * B(k,n), generic strides,
+// 64x64x16 shared-memory tiles, 256 threads x (4x4).  Epilogue: + bias[n]; relu; dropout (forward);
+// or multiply by the saved forward activation's mask (backward): C *= (ref[m,n] > 0) [* dropout mask].
+__device__ __forceinline__ uint32_t mix32h(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return uint32_t((z ^ (z >> 31)) >> 16);
+}
+
+__global__ void __launch_bounds__(256) sgemm_small_kernel(const float* __restrict__ A, long long sa_m, long long sa_k,
+                                                          const float* __restrict__ Bm, long long sb_k, long long sb_n,
+                                                          float* __restrict__ Cc, long long ldc, int M, int N, int K,
+                                                          const float* __restrict__ bias, int relu,
+                                                          const float* __restrict__ mask_ref, long long ld_ref,
+                                                          float p_drop, const unsigned long long* __restrict__ seed_ptr, int accumulate) {
+  const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
+  __shared__ float As[16][64 + 1];
+  __shared__ float Bs[16][64 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
+      const int kk = i & 15, mm = i >> 4;
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < M && k < K) ? A[m * sa_m + k * sa_k] : 0.f;
+      const int n = n0 + mm;
+      Bs[kk][mm] = (n < N && k < K) ? Bm[k * sb_k + n * sb_n] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+    }
+    __syncthreads();
+  }
+  const uint32_t thresh = p_drop > 0.f ? uint32_t(fminf(p_drop, 0.999999f) * 4294967296.0f) : 0u;
+  const float keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j];
+      if (bias) v += bias[n];
+      if (relu) v = fmaxf(v, 0.f);
+      if (mask_ref) v = mask_ref[m * ld_ref + n] > 0.f ? v : 0.f;
+      if (p_drop > 0.f) v = (mix32h(seed * 0xD1342543DE82EF95ull + uint64_t(m) * N + n) >= thresh) ? v * keep : 0.f;
+      if (accumulate) v += Cc[m * ldc + n];
+      Cc[m * ldc + n] = v;
+    }
+  }
+}
+
+// column sums: out[c] (+)= sum_p x[p, c]   (bias gradients).  x fp32 or bf16.
+template <typename T>
+__global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long P, int C, long long ld,
+                              int rows_per_block) {
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long p0 = (long long)blockIdx.x * rows_per_block;
+  const long long p1 = min(p0 + rows_per_block, P);
+  float s = 0.f;
+  for (long long p = p0; p < p1; ++p) {
+    if constexpr (sizeof(T) == 2) s += __bfloat162float(x[p * ld + c]);
+    else s += x[p * ld + c];
+  }
+  atomicAdd(out + c, s);
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------- launchers
+cudaError_t launch_im2col(const void* in, void* col, int NB, int IH, int IW, int C, int OH, int OW, int KH, int KW,
+                          int stride, int pad, cudaStream_t s) {
+  const long long total = (long long)NB * OH * OW * KH * KW * (C / 8);
+  im2col_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(col), NB,
+                                                     IH, IW, C / 8, OH, OW, KH, KW, stride, pad);
+  return cudaGetLastError();
+}
+cudaError_t launch_col2im(const void* col, const float* bias, void* big, int NB, int SH, int SW, int C, int BH, int BW,
+                          int KH, int KW, int stride, int pad, cudaStream_t s) {
+  const long long total = (long long)NB * BH * BW * (C / 8);
+  col2im_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(col), bias,
+                                                     reinterpret_cast<uint4*>(big), NB, SH, SW, C / 8, BH, BW, KH, KW,
+                                                     stride, pad);
+  return cudaGetLastError();
+}
+cudaError_t launch_dwconv3x3(const void* in, const float* w, const float* bias, const void* add, void* out, int NB, int H,
+                             int W, int C, int flip, cudaStream_t s) {
+  const long long total = (long long)NB * H * W * (C / 8);
+  dwconv3x3_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), w, bias,
+                                                        reinterpret_cast<const uint4*>(add),
+                                                        reinterpret_cast<uint4*>(out), NB, H, W, C / 8, flip);
+  return cudaGetLastError();
+}
+cudaError_t launch_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, int NB, int H, int W, int C,
+                                   cudaStream_t s) {
+  const long long P = (long long)NB * H * W;
+  int rpb = int((P + 295) / 296);
+  if (rpb < 64) rpb = 64;
+  dim3 grid(unsigned((P + rpb - 1) / rpb), unsigned((C + 63) / 64));
+  dwconv3x3_wgrad_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in),
+                                              reinterpret_cast<const __nv_bfloat16*>(dout), dw, NB, H, W, C, rpb);
+  return cudaGetLastError();
+}
+static void stats_grid(long long P, int C2, dim3* grid, int* block, int* rpb) {
+  *block = C2 > 256 ? 256 : C2;
+  const int gy = (C2 + *block - 1) / *block;
+  int r = int((P + 591) / 592);
+  if (r < 16) r = 16;
+  *rpb = r;
+  *grid = dim3(unsigned((P + r - 1) / r), unsigned(gy));
+}
+cudaError_t launch_bn_stats(const void* raw, double* sums, long long P, int C, cudaStream_t s) {
+  dim3 grid;
+  int block, rpb;
+  stats_grid(P, C / 2, &grid, &block, &rpb);
+  bn_stats_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat162*>(raw), sums, P, C / 2, rpb);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_finalize(double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,
+                               float* shift, float* mean, float* invstd, int C, double count, float eps, float momentum,
+                               cudaStream_t s) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, gamma, beta, rm, rv, scale, shift, mean, invstd, C, count, eps,
+                                                     momentum);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
+                                const float* conv_bias, float* scale, float* shift, int C, float eps, cudaStream_t s) {
+  bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, rm, rv, conv_bias, scale, shift, C, eps);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_apply(const void* raw, const float* scale, const float* shift, const void* add1, const void* add2,
+                            void* out, long long P, int C, int relu, int mode, cudaStream_t s) {
+  bn_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, s>>>(
+      reinterpret_cast<const uint4*>(raw), scale, shift, reinterpret_cast<const uint4*>(add1),
+      reinterpret_cast<const uint4*>(add2), reinterpret_cast<uint4*>(out), P, C / 8, relu, mode);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_bwd_reduce(const void* dout, const void* raw, const void* add1, const float* scale,
+                                 const float* shift, const float* mean, const float* invstd, double* sums, long long P,
+                                 int C, int relu, int mode, cudaStream_t s) {
+  dim3 grid;
+  int block, rpb;
+  stats_grid(P, C / 2, &grid, &block, &rpb);
+  bn_bwd_reduce_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat162*>(dout),
+                                              reinterpret_cast<const __nv_bfloat162*>(raw),
+                                              reinterpret_cast<const __nv_bfloat162*>(add1), scale, shift, mean, invstd,
+                                              sums, P, C / 2, rpb, relu, mode);
+  return cudaGetLastError();
+}
+cudaError_t launch_bn_bwd_apply(const void* dout, const void* raw, const void* add1, const float* gamma,
+                                const float* scale, const float* shift, const float* mean, const float* invstd,
+                                const double* sums, void* draw, void* dres, float* dgamma, float* dbeta, long long P, int C,
+                                int relu, int mode, int eval_mode, int shuffle_oh, int shuffle_ow, cudaStream_t s) {
+  bn_bwd_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, s>>>(
+      reinterpret_cast<const uint4*>(dout), reinterpret_cast<const uint4*>(raw), reinterpret_cast<const uint4*>(add1),
+      gamma, scale, shift, mean, invstd, sums, reinterpret_cast<uint4*>(draw), reinterpret_cast<uint4*>(dres), dgamma,
+      dbeta, P, C / 8, relu, mode, eval_mode, shuffle_oh, shuffle_ow);
+  return cudaGetLastError();
+}
+cudaError_t launch_zero_f64(double* p, int n, cudaStream_t s) {
+  zero_f64_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n);
+  return cudaGetLastError();
+}
+cudaError_t launch_avgpool2(const float* in, float* out, long long planes, int OH, int OW, cudaStream_t s) {
+  avgpool2_kernel<<<grid_for(planes * OH * OW, 256), 256, 0, s>>>(in, out, planes, OH, OW);
+  return cudaGetLastError();
+}
+cudaError_t launch_hm_grad_to_nhwc(const float* g, void* out, int NB, int K, int Kp, int OH, int OW, int up,
+                                   cudaStream_t s) {
+  hm_grad_to_nhwc_kernel<<<grid_for((long long)NB * OH * OW * Kp, 256), 256, 0, s>>>(
+      g, reinterpret_cast<__nv_bfloat16*>(out), NB, K, Kp, OH, OW, up);
+  return cudaGetLastError();
+}
+cudaError_t launch_mean_tokens(const void* feat, float* out, int B, int N, int D, cudaStream_t s) {
+  dim3 grid((D + 127) / 128, B);
+  mean_tokens_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(feat), out, N, D);
+  return cudaGetLastError();
+}
+cudaError_t launch_mean_tokens_bwd(void* dfeat, const float* dmean, int B, int N, int D, cudaStream_t s) {
+  const long long total = (long long)B * N * D;
+  mean_tokens_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(dfeat), dmean, N, D, total);
+  return cudaGetLastError();
+}
+cudaError_t launch_sgemm_small(const float* A, long long sa_m, long long sa_k, const float* B, long long sb_k,
+                               long long sb_n, float* C, long long ldc, int M, int N, int K, const float* bias, int relu,
+                               const float* mask_ref, long long ld_ref, float p_drop, const unsigned long long* seed,
+                               int accumulate, cudaStream_t s) {
+  dim3 grid((N + 63) / 64, (M + 63) / 64);
+  sgemm_small_kernel<<<grid, 256, 0, s>>>(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, bias, relu, mask_ref, ld_ref,
+                                          p_drop, seed, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t launch_colsum(const void* x, int is_bf16, float* out, long long P, int C, long long ld, cudaStream_t s) {
+  int rpb = int((P + 295) / 296);
+  if (rpb < 32) rpb = 32;
+  const int block = C >= 128 ? 128 : 32;
+  dim3 grid(unsigned((P + rpb - 1) / rpb), unsigned((C + block - 1) / block));
+  if (is_bf16)
+    colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, P, C, ld, rpb);
+  else
+    colsum_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(x), out, P, C, ld, rpb);
+  return cudaGetLastError();
+}
+
+}  // namespace dp

@@ -1,0 +1,168 @@
+/* libdinopose_sm100a.so -- C ABI of the B200-native dino_pose hot path.
+ *
+ * The reference (seungjoohan/dino_pose) is pure Python/PyTorch: it has no FFI of its own, its
+ * "operator API" is the nn.Module surface of model/dinov2_pose.py, model/pose_heads.py,
+ * model/lora.py and the numpy decode in src/model_utils.py.  This header is
+ * the level BELOW that surface: every ATen / numpy call the reference makes on the hot path is
+ * replaced by one of these entry points; dino_pose_b200/model/*.py (same class names, constructor
+ * arguments, forward() signatures and state_dict keys as the reference) binds them with ctypes.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name says host; no torch types cross the ABI
+ *   - `stream` is a cudaStream_t passed as void*; all calls are asynchronous on that stream,
+ *     allocate nothing and never synchronise (CUDA-graph capturable)
+ *   - return value: 0 = ok, negative = invalid argument (dp_last_error() has the text),
+ *     positive = cudaError_t from the launch
+ *   - activations are bf16 NHWC / [rows, channels] row-major; the residual stream, LayerNorm
+ *     statistics, accumulators, gradients of parameters and the heat-map / z outputs are fp32
+ */
+#ifndef DINOPOSE_H_
+#define DINOPOSE_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DP_ABI_VERSION 1
+
+const char* dp_last_error(void);
+int dp_abi_version(void);
+/* sizeof() of the argument structs, so the ctypes mirror can be checked at load time */
+int dp_sizeof_gemm_args(void);
+int dp_sizeof_wgrad_args(void);
+
+/* ---- activation / row-map / dtype codes (dp_gemm_args) ---- */
+enum { DP_ACT_NONE = 0, DP_ACT_RELU = 1, DP_ACT_GELU = 2 };
+enum { DP_ROWMAP_IDENTITY = 0, DP_ROWMAP_PATCH_TOKENS = 1, DP_ROWMAP_NCHW = 2, DP_ROWMAP_SHUFFLE2X2 = 3 };
+enum { DP_OUT_BF16 = 0, DP_OUT_F32 = 1 };
+
+/* C[M,N] = A[M,K] * W[N,K]^T (+ fused epilogue), bf16 x bf16 -> fp32 on tcgen05.
+ * Replaces: nn.Linear q/k/v/dense/fc1/fc2 (HF modeling_dinov2.py:211-213,250,325-327), the patch
+ * conv (HF:139,148), and -- with a_mode = 1 (implicit convolution over an NHWC activation) -- the
+ * stride-1 nn.Conv2d / ConvTranspose2d(k4,s1) of model/pose_heads.py:306-340.
+ * Epilogue (per element): v = acc*scale[c] + bias[c]; aux_out = bf16(v); v = act(v);
+ *   v *= gelu'(aux_in); v *= ls[c]; v += residual[row,c]; out[row_map(row), c] = v            */
+typedef struct {
+  const void* A;          /* bf16 */
+  const void* W;          /* bf16 [N, K] row-major, row pitch ldw */
+  long long lda, ldw;     /* elements */
+  int M, N, K;
+  int block_n;            /* 32 / 64 / 128 / 256, 0 = auto */
+  int a_mode;             /* 0: A is [M,K]; 1: A is NHWC [NB,IH,IW,C], K = KH*KW*C, M = NB*OH*OW */
+  int C, IW, IH, NB;
+  long long a_stride_w, a_stride_h, a_stride_b; /* elements */
+  int KH, KW, pad_y, pad_x, OH, OW;
+  void* out;
+  long long ldo;
+  int out_dtype;
+  int act;
+  const float* bias;
+  const float* scale;
+  const float* ls;
+  const void* residual;   /* fp32 (or bf16 when res_is_bf16) [rows, ldr] */
+  long long ldr;
+  int res_is_bf16;
+  void* aux_out;
+  const void* aux_in;
+  long long ld_aux;
+  int row_map, n_valid, map_a, map_b;
+} dp_gemm_args;
+int dp_gemm_bf16(const dp_gemm_args* a, void* stream);
+
+/* Weight gradient: out[off(m)+off(n)+tap*so_t] += sum_p A[p,m] * B[p (+tap), n]  (fp32 atomics,
+ * caller zeroes `out`).  Replaces autograd's conv / linear weight-gradient kernels for
+ * model/pose_heads.py layers (train.py:169 loss.backward()).
+ * mode 0: A [P,Mc] (lda), B [P,Nc] (ldb).  mode 1: A NHWC [NB,OH,OW,Mc], B NHWC [NB,IH,IW,Nc],
+ * B read at (y+ky-pad_y, x+kx-pad_x) for tap (ky,kx).                                           */
+typedef struct {
+  const void* A;
+  const void* B;
+  int mode, P;
+  long long lda, ldb;
+  int Mc, Nc;
+  int NB, OH, OW, IH, IW;
+  long long a_sw, a_sh, a_sb, b_sw, b_sh, b_sb;
+  int KH, KW, pad_y, pad_x;
+  float* out;
+  long long so_m, so_mo, so_n, so_no, so_t;
+  int m_inner, n_inner;
+  int block_n, splits;
+} dp_wgrad_args;
+int dp_wgrad_bf16(const dp_wgrad_args* a, void* stream);
+
+/* ---------------------------------------------------------------- backbone row-wise kernels */
+
+/* nn.LayerNorm(D, eps) forward (HF modeling_dinov2.py:371,379,477).  x fp32 [rows,D] -> y bf16 and/or
+ * y32 fp32 (either may be NULL).  drop_cls != 0: rows are [B,T] tokens; the CLS row of each image is
+ * dropped and the output is [B*(T-1), D] (reference model/dinov2_pose.py:147,153).  D in {128,384,768,1024}. */
+int dp_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                     long long rows, int D, int T, int drop_cls, float eps, void* stream);
+/* LayerNorm input-gradient (autograd of the above; parameters frozen).  dx = LNbwd(dy) (+ add_in);
+ * optional dx_scaled_bf16 = bf16(dx * ls) feeds the next dgrad GEMM. */
+int dp_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x, const float* gamma, const float* add_in,
+                     float* dx, const float* ls, void* dx_scaled_bf16, long long rows, int D, int T, int drop_cls,
+                     float eps, void* stream);
+/* im2col of the 14x14/stride-14 patch conv (HF:139-149): pixel_values fp32 NCHW -> bf16 [B*gh*gw, Kp]. */
+int dp_patch_im2col(const float* pixel_values, void* out_bf16, int B, int H, int W, int Kp, void* stream);
+/* x[b*T + 0, :] = cls_row (cls_token + position_embeddings[0], HF:108-112). */
+int dp_fill_cls(float* x, const float* cls_row, int B, int T, int D, void* stream);
+/* LoRALayer on the attention output + LayerScale + residual (reference model/lora.py:26-28,57-59; HF:373-376):
+ * x_out = x_in + (y + dropout(y A B) * scaling) * lambda1.  u_save [rows, R] optional. */
+int dp_lora_fwd(const float* y, const float* A, const float* B, const float* lambda1, const float* x_in,
+                float* x_out, float* u_save, long long rows, int D, int R, float scaling, float p_drop,
+                const unsigned long long* seed_dev, void* stream);
+/* gradients of lora_A [D,R] and lora_B [R,D] (accumulated with atomics; caller zeroes them). */
+int dp_lora_bwd(const float* g, const float* y, const float* u_saved, const float* B, const float* lambda1,
+                float* dA, float* dB, long long rows, int D, int R, float scaling, float p_drop,
+                const unsigned long long* seed_dev, void* stream);
+/* Multi-head attention forward (HF:203-234), head dim 64.  qkv bf16 [B*T, 3*heads*64] -> ctx bf16 [B*T, heads*64]. */
+int dp_attention_fwd(const void* qkv_bf16, void* ctx_bf16, int B, int T, int heads, float scale, void* stream);
+
+/* ---------------------------------------------------------------- decode */
+/* Heat-map -> key-points (reference src/model_utils.py:10-51).  heatmaps fp32 [maps, H, W];
+ * idx int32 [maps,2] = (row, col) of the first maximum; xy float64 [maps,2] = refined (x, y) scaled to
+ * (target_w, target_h); conf fp32 [maps] = peak value (may be NULL).  Bit-exact vs the numpy reference. */
+int dp_decode(const float* heatmaps, int maps, int H, int W, double target_w, double target_h, int* idx,
+              double* xy, float* conf, void* stream);
+
+/* ---------------------------------------------------------------- pose-head kernels (NHWC bf16) */
+int dp_im2col(const void* in, void* col, int NB, int IH, int IW, int C, int OH, int OW, int KH, int KW, int stride,
+              int pad, void* stream);
+int dp_col2im(const void* col, const float* bias, void* big, int NB, int SH, int SW, int C, int BH, int BW, int KH,
+              int KW, int stride, int pad, void* stream);
+int dp_dwconv3x3(const void* in, const float* w, const float* bias, const void* add, void* out, int NB, int H, int W,
+                 int C, int flip, void* stream);
+int dp_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, int NB, int H, int W, int C, void* stream);
+/* train-mode BatchNorm2d (eps, momentum as torch): sums fp64 [2*C] must be zero on entry of dp_bn_stats;
+ * dp_bn_finalize re-zeroes it. */
+int dp_bn_stats(const void* raw, double* sums, long long P, int C, void* stream);
+int dp_bn_finalize(double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
+                   float* scale, float* shift, float* mean, float* invstd, int C, double count, float eps,
+                   float momentum, void* stream);
+int dp_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
+                    const float* conv_bias, float* scale, float* shift, int C, float eps, void* stream);
+int dp_bn_apply(const void* raw, const float* scale, const float* shift, const void* add1, const void* add2,
+                void* out, long long P, int C, int relu, int mode, void* stream);
+int dp_bn_bwd_reduce(const void* dout, const void* raw, const void* add1, const float* scale, const float* shift,
+                     const float* mean, const float* invstd, double* sums, long long P, int C, int relu, int mode,
+                     void* stream);
+int dp_bn_bwd_apply(const void* dout, const void* raw, const void* add1, const float* gamma, const float* scale,
+                    const float* shift, const float* mean, const float* invstd, const double* sums, void* draw,
+                    void* dres, float* dgamma, float* dbeta, long long P, int C, int relu, int mode, int eval_mode,
+                    int shuffle_oh, int shuffle_ow, void* stream);
+int dp_avgpool2(const float* in, float* out, long long planes, int OH, int OW, void* stream);
+int dp_hm_grad_to_nhwc(const float* g, void* out_bf16, int NB, int K, int Kp, int OH, int OW, int up, void* stream);
+int dp_mean_tokens(const void* feat_bf16, float* out, int B, int N, int D, void* stream);
+int dp_mean_tokens_bwd(void* dfeat_bf16, const float* dmean, int B, int N, int D, void* stream);
+/* fp32 GEMM for the z-head MLP (M = batch): C[m,n] (+)= sum_k A[m*sa_m + k*sa_k] * B[k*sb_k + n*sb_n]. */
+int dp_sgemm_small(const float* A, long long sa_m, long long sa_k, const float* B, long long sb_k, long long sb_n,
+                   float* C, long long ldc, int M, int N, int K, const float* bias, int relu, const float* mask_ref,
+                   long long ld_ref, float p_drop, const unsigned long long* seed_dev, int accumulate, void* stream);
+int dp_colsum(const void* x, int is_bf16, float* out, long long P, int C, long long ld, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DINOPOSE_H_ */

@@ -45,15 +45,18 @@ class Program:
     def __init__(self):
         self.calls = []       # (fn, args, name)
         self.keep = []        # keep ctypes structs / tensors alive
+        self.meta = []        # per call: kernel family, algorithmic FLOPs / bytes (roofline accounting)
         self.lib = _lib.lib()
 
-    def add(self, name, fn, *args, keep=()):
+    def add(self, name, fn, *args, keep=(), kernel=None, flops=0.0, bytes=0.0):
         self.calls.append((fn, args, name))
+        self.meta.append({"name": name, "kernel": kernel or name, "flops": float(flops), "bytes": float(bytes)})
         self.keep.extend(keep)
 
     def add_callable(self, name, fn):
         """Host-side step (e.g. a torch op on static tensors) recorded in order with the launches."""
         self.calls.append((None, fn, name))
+        self.meta.append({"name": name, "kernel": "host:" + name, "flops": 0.0, "bytes": 0.0})
 
     def __len__(self):
         return sum(1 for fn, _a, _n in self.calls if fn is not None)
@@ -67,6 +70,25 @@ class Program:
             rc = fn(*args, stream)
             if rc != 0:
                 _lib.check(rc, name)
+
+    def run_timed(self):
+        """Replay with a CUDA event pair around every launch (on the launching stream); returns a list of
+        dicts {name, kernel, ms, flops, bytes}.  Used by bench.py for the per-kernel roofline figures."""
+        stream = torch.cuda.current_stream()
+        evs = []
+        for (fn, args, name), meta in zip(self.calls, self.meta):
+            if fn is None:
+                args()
+                continue
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rc = fn(*args, stream.cuda_stream)
+            e1.record(stream)
+            if rc != 0:
+                _lib.check(rc, name)
+            evs.append((meta, e0, e1))
+        torch.cuda.synchronize()
+        return [dict(m, ms=e0.elapsed_time(e1)) for m, e0, e1 in evs]
 
 
 class CudaBackend:
@@ -123,7 +145,7 @@ class CudaBackend:
         a.act = ACT[act]
         a.row_map = ROWMAP[row_map]
         a.n_valid, a.map_a, a.map_b = n_valid, map_a, map_b
-        self.prog.add(name, self.lib.dp_gemm_bf16, C.byref(a),
+        self.prog.add(name, self.lib.dp_gemm_bf16, C.byref(a), kernel="gemm_kmajor_tcgen05", flops=2.0 * M * N * K,
                       keep=(a, A, W, out, bias, scale, ls, residual, aux_out, aux_in))
 
     def wgrad(self, A, B, out, *, Mc, Nc, so_m, so_n, so_t=0, so_mo=0, so_no=0, m_inner=0, n_inner=0, conv=None,
@@ -153,13 +175,16 @@ class CudaBackend:
             a.lda = lda if lda is not None else A.stride(0)
             a.ldb = ldb if ldb is not None else B.stride(0)
             a.KH = a.KW = 1
-        self.prog.add(name, self.lib.dp_wgrad_bf16, C.byref(a), keep=(a, A, B, out))
+        pix = (A.shape[0] * A.shape[1] * A.shape[2]) if conv is not None else P
+        taps = conv["KH"] * conv["KW"] if conv is not None else 1
+        self.prog.add(name, self.lib.dp_wgrad_bf16, C.byref(a), kernel="gemm_wgrad_tcgen05",
+                      flops=2.0 * pix * Mc * Nc * taps, keep=(a, A, B, out))
 
     # ------------------------------------------------------------------ backbone row-wise
     def layernorm_fwd(self, x, gamma, beta, y_bf16, y_f32, *, rows, D, T=0, drop_cls=False, eps=1e-6):
         _chk(x, torch.float32, "ln.x", False)
         self.prog.add("layernorm_fwd", self.lib.dp_layernorm_fwd, _p(x), _p(gamma), _p(beta), _p(y_bf16), _p(y_f32),
-                      rows, D, T, int(drop_cls), eps, keep=(x, gamma, beta, y_bf16, y_f32))
+                      rows, D, T, int(drop_cls), eps, keep=(x, gamma, beta, y_bf16, y_f32), bytes=rows * D * 6.0)
 
     def layernorm_bwd(self, dy, x, gamma, add_in, dx, *, rows, D, T=0, drop_cls=False, eps=1e-6, ls=None,
                       dx_scaled=None):
@@ -184,12 +209,12 @@ class CudaBackend:
 
     def attention_fwd(self, qkv, ctx, *, B, T, heads, scale):
         _chk(qkv, torch.bfloat16, "attention.qkv")
-        self.prog.add("attention_fwd", self.lib.dp_attention_fwd, _p(qkv), _p(ctx), B, T, heads, scale, keep=(qkv, ctx))
+        self.prog.add("attention_fwd", self.lib.dp_attention_fwd, _p(qkv), _p(ctx), B, T, heads, scale, keep=(qkv, ctx), flops=4.0 * B * T * T * heads * 64, bytes=B * T * heads * 64 * 8.0)
 
     def decode(self, hm, idx, xy, conf, *, maps, H, W, target_w, target_h):
         _chk(hm, torch.float32, "decode.heatmaps")
         self.prog.add("decode", self.lib.dp_decode, _p(hm), maps, H, W, float(target_w), float(target_h), _p(idx),
-                      _p(xy), _p(conf), keep=(hm, idx, xy, conf))
+                      _p(xy), _p(conf), keep=(hm, idx, xy, conf), bytes=maps * (H * W * 4.0 + 28.0))
 
     # ------------------------------------------------------------------ heads
     def im2col(self, x, col, *, NB, IH, IW, C, OH, OW, KH, KW, stride, pad):

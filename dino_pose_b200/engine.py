@@ -1,0 +1,767 @@
+"""Host-side engine: lowers the dino_pose forward / backward onto the sm_100a kernels.
+
+The reference executes this path as a chain of ATen calls driven by Python (``train.py:144,169`` ->
+``model/dinov2_pose.py:292-306`` -> HF ``Dinov2Model`` -> ``model/pose_heads.py:395-400``).  Here the same
+chain is described ONCE per plan -- (batch, height, width, training) -- as a recorded program of
+C-ABI launches on statically allocated device buffers (see ``backend.py``); a step replays it.
+
+Data layout in HBM (B images, T = 1 + N tokens, D channels):
+  residual stream x            fp32 [B*T, D]
+  LayerNorm outputs / qkv / ctx / MLP hidden / head activations     bf16, rows = tokens or NHWC pixels
+  weights                      bf16 [N, K] K-major copies of the fp32 nn.Parameters (packed here)
+  gradients of parameters      fp32, one flat buffer, views per parameter
+  heat-maps / z                fp32 [B,K,48,48] / [B,K]
+
+What autograd reaches in the reference: heads, final LayerNorm, MLP branch of the last
+block, LoRA adapter.  The backward program implements exactly that path; everything earlier is frozen
+(``model/dinov2_pose.py:193-194``).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+PATCH = 14
+PATCH_K = 3 * PATCH * PATCH          # 588
+PATCH_KP = 640                       # padded to a multiple of the 64-wide k-block
+LN_EPS = 1e-6
+HM_PAD = 32                          # heat-map gradient channels padded 24 -> 32 (16-byte TMA pitch)
+
+
+def _ceil(a, b):
+    return (a + b - 1) // b
+
+
+class ConvLayer:
+    """One conv(+BN+ReLU) unit of the heads: geometry, parameter names, packed weights, saved tensors."""
+
+    def __init__(self, name, kind, cin, cout, k, ih, iw, oh, ow, bn=None, relu=True, stride=1, pad=0):
+        self.name, self.kind = name, kind
+        self.cin, self.cout, self.k = cin, cout, k
+        self.ih, self.iw, self.oh, self.ow = ih, iw, oh, ow
+        self.bn, self.relu = bn, relu
+        self.stride, self.pad = stride, pad
+        self.t = {}   # tensors
+
+
+class PoseEngine:
+    def __init__(self, params, buffers, cfg, backend, device):
+        """params / buffers: dict reference-state_dict-name -> tensor (fp32 parameters / BN buffers).
+        cfg: dict(D, L, heads, num_keypoints, heatmap_size, lora=None|dict(rank, alpha, dropout),
+                  z_hidden, z_dropout)."""
+        self.P, self.Bufs, self.cfg = params, buffers, cfg
+        self.be = backend
+        self.device = device
+        self.D, self.L, self.heads = cfg["D"], cfg["L"], cfg["heads"]
+        self.K = cfg["num_keypoints"]
+        self.hm_size = cfg["heatmap_size"]
+        self.lora = cfg.get("lora")
+        # storage dtype of activations / packed weights.  The CUDA kernels are bf16-only; fp32 is accepted only by
+        # the torch emulator (tests) to separate logic errors from bf16 rounding.
+        self.adt = cfg.get("act_dtype", BF16)
+        if self.adt != BF16 and getattr(backend, "name", "") == "cuda":
+            raise ValueError("the sm_100a kernels store activations in bf16 only")
+        self.plans = {}
+        self.frozen = None
+        self.seed = None
+        self.step_count = 0
+        last = self.L - 1
+        self.att_prefix = [f"backbone.encoder.layer.{i}.attention." for i in range(self.L)]
+        if self.lora:
+            self.att_prefix[last] = f"backbone.encoder.layer.{last}.attention.original_attention."
+        self.lora_prefix = f"backbone.encoder.layer.{last}.attention.lora_output."
+
+    # ------------------------------------------------------------------ helpers
+    def new(self, shape, dtype, fill=None):
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        if fill is None:
+            t.zero_()
+        else:
+            t.fill_(fill)
+        return t
+
+    def p(self, name):
+        t = self.P.get(name)
+        if t is None:
+            t = self.Bufs[name]
+        return t
+
+    def trainable_names(self):
+        out = []
+        for n, t in self.P.items():
+            if t.requires_grad:
+                out.append(n)
+        return out
+
+    # ------------------------------------------------------------------ frozen weight packing
+    def pack_frozen(self):
+        """bf16 K-major copies of the frozen backbone weights (plain torch layout ops, run once and
+        whenever a frozen parameter's version counter changes)."""
+        D, L = self.D, self.L
+        fz = {}
+        w = self.p("backbone.embeddings.patch_embeddings.projection.weight").detach()
+        wpe = torch.zeros(D, PATCH_KP, dtype=self.adt, device=self.device)
+        wpe[:, :PATCH_K] = w.reshape(D, PATCH_K).to(self.adt)
+        fz["wpe"] = wpe
+        for i in range(L):
+            lp = f"backbone.encoder.layer.{i}."
+            ap = self.att_prefix[i]
+            q, k, v = (self.p(ap + f"attention.{n}.weight").detach() for n in ("query", "key", "value"))
+            fz[f"wqkv{i}"] = torch.cat([q, k, v], 0).to(self.adt).contiguous()
+            fz[f"bqkv{i}"] = torch.cat([self.p(ap + f"attention.{n}.bias").detach() for n in ("query", "key", "value")]).float().contiguous()
+            fz[f"wo{i}"] = self.p(ap + "output.dense.weight").detach().to(self.adt).contiguous()
+            fz[f"bo{i}"] = self.p(ap + "output.dense.bias").detach().float().contiguous()
+            fz[f"w1{i}"] = self.p(lp + "mlp.fc1.weight").detach().to(self.adt).contiguous()
+            fz[f"w2{i}"] = self.p(lp + "mlp.fc2.weight").detach().to(self.adt).contiguous()
+        lp = f"backbone.encoder.layer.{L - 1}."
+        # transposed copies for the last block's MLP input-gradient GEMMs
+        fz["w2T"] = self.p(lp + "mlp.fc2.weight").detach().t().to(self.adt).contiguous()   # [4D, D]
+        fz["w1T"] = self.p(lp + "mlp.fc1.weight").detach().t().to(self.adt).contiguous()   # [D, 4D]
+        self.frozen = fz
+        self.frozen_versions = self._versions(frozen=True)
+        self.pos_cache = {}
+
+    def _versions(self, frozen):
+        return tuple(t._version for n, t in self.P.items() if (not t.requires_grad) == frozen)
+
+    def pos_tables(self, H, W):
+        """Position-embedding table for an HxW input: rows 1.. = bicubic-resized patch position
+        embeddings (HF modeling_dinov2.py:57-95, constant per resolution for frozen parameters) + the
+        patch-conv bias; row 0 = cls_token + position_embeddings[0] (HF:108-112)."""
+        key = (H, W)
+        if key in self.pos_cache:
+            return self.pos_cache[key]
+        pos = self.p("backbone.embeddings.position_embeddings").detach().float()
+        D = self.D
+        gh, gw = H // PATCH, W // PATCH
+        npos = pos.shape[1] - 1
+        s = int(math.sqrt(npos))
+        if gh * gw == npos and gh == gw:
+            patch = pos[0, 1:]
+        else:
+            grid = pos[0, 1:].reshape(1, s, s, D).permute(0, 3, 1, 2)
+            grid = F.interpolate(grid, size=(gh, gw), mode="bicubic", align_corners=False)
+            patch = grid.permute(0, 2, 3, 1).reshape(gh * gw, D)
+        table = torch.empty(1 + gh * gw, D, dtype=F32, device=self.device)
+        bias = self.p("backbone.embeddings.patch_embeddings.projection.bias").detach().float()
+        table[1:] = patch + bias
+        table[0] = self.p("backbone.embeddings.cls_token").detach().float().reshape(D) + pos[0, 0]
+        self.pos_cache[key] = table
+        return table
+
+    # ------------------------------------------------------------------ head layer table
+    def build_head_layers(self, g):
+        """g = side of the token grid (16 at 224^2, 32 at 448^2).  Geometry follows
+        model/pose_heads.py:212-343 with spatial_input_size=16, heatmap_size=48 (dinov2_pose.py:45-54)."""
+        hp = "pose_heads.heatmap_head."
+        fr = hp + "feature_refine."
+        hg = fr + "3."
+        D = self.D
+        g2, g4 = g // 2, g // 4
+        s47 = (g - 1) * 3 - 2 + 4          # ConvT(k4,s3,p1): 16 -> 47, 32 -> 95
+        s48 = s47 + 1                      # ConvT(k4,s1,p1): 47 -> 48, 95 -> 96
+        Ls = {}
+
+        def add(key, *a, **k):
+            Ls[key] = ConvLayer(*a, **k)
+
+        add("fr0", fr + "0", "conv", D, 512, 3, g, g, g, g, bn=fr + "1", pad=1)
+        add("skip", hg + "skip.0", "conv", 512, 512, 1, g, g, g, g, bn=hg + "skip.1")
+        add("dw", hg + "depthwise_conv.0", "dw", 512, 512, 3, g, g, g, g, bn=hg + "depthwise_conv.1", pad=1)
+        add("pw", hg + "depthwise_conv.3", "conv", 512, 512, 1, g, g, g, g, bn=hg + "depthwise_conv.4")
+        add("down1", hg + "down1.0", "conv_s2", 512, 256, 3, g, g, g2, g2, bn=hg + "down1.1", stride=2, pad=1)
+        add("down2", hg + "down2.0", "conv_s2", 256, 128, 3, g2, g2, g4, g4, bn=hg + "down2.1", stride=2, pad=1)
+        add("bt1", hg + "bottleneck.0", "conv", 128, 128, 3, g4, g4, g4, g4, bn=hg + "bottleneck.1", pad=1)
+        add("bt2", hg + "bottleneck.3", "conv", 128, 128, 3, g4, g4, g4, g4, bn=hg + "bottleneck.4", pad=1, relu=False)
+        add("up1", hg + "up1.0", "convT2", 128, 256, 2, g4, g4, g2, g2, bn=hg + "up1.1", stride=2)
+        add("up2", hg + "up2.0", "convT2", 256, 512, 2, g2, g2, g, g, bn=hg + "up2.1", stride=2)
+        add("fr4", fr + "4", "conv", 512, 256, 3, g, g, g, g, bn=fr + "5", pad=1)
+        add("ups0", hp + "upsampling.0.0", "convT", 256, 128, 4, g, g, s47, s47, bn=hp + "upsampling.0.1", stride=3, pad=1)
+        add("ups1", hp + "upsampling.1.0", "convT_s1", 128, 128, 4, s47, s47, s48, s48, bn=hp + "upsampling.1.1", pad=1)
+        add("pred0", hp + "prediction.0", "conv", 128, 64, 3, s48, s48, s48, s48, bn=hp + "prediction.1", pad=1)
+        add("pred3", hp + "prediction.3", "conv", 64, self.K, 1, s48, s48, s48, s48, bn=None, relu=False)
+        return Ls
+
+    # ------------------------------------------------------------------ trainable weight packing (recorded)
+    def record_pack_heads(self, plan):
+        """bf16 GEMM-layout copies of the trainable head weights; re-run every step in training (the
+        optimizer just changed them) and on version change in eval."""
+        Ls = plan["layers"]
+        be = self.be
+
+        def alloc(L):
+            k, ci, co = L.k, L.cin, L.cout
+            kk = k * k
+            if L.kind == "dw":
+                return
+            if L.kind in ("conv", "conv_s2"):
+                L.t["wf"] = self.new((co, kk * ci), self.adt)                 # [Cout, (ky,kx,ci)]
+                L.t["wd"] = self.new((ci, kk * co), self.adt) if L.kind == "conv" else self.new((kk * ci, co), self.adt)
+            elif L.kind in ("convT2", "convT"):
+                L.t["wf"] = self.new((kk * co, ci), self.adt)                 # [(ky,kx,co), ci]
+                L.t["wd"] = self.new((ci, kk * co), self.adt)                 # [ci, (ky,kx,co)]
+            elif L.kind == "convT_s1":
+                L.t["wf"] = self.new((co, kk * ci), self.adt)                 # conv form, flipped taps
+                L.t["wd"] = self.new((ci, kk * co), self.adt)
+            if L.name.endswith("prediction.3"):
+                L.t["wd"] = self.new((ci, HM_PAD), self.adt)                  # [64, 32] zero padded K
+
+        for L in Ls.values():
+            alloc(L)
+
+        def pack():
+            with torch.no_grad():
+                for L in Ls.values():
+                    if L.kind == "dw":
+                        continue
+                    w = self.p(L.name + ".weight").detach()
+                    k, ci, co = L.k, L.cin, L.cout
+                    kk = k * k
+                    if L.kind == "conv":
+                        L.t["wf"].copy_(w.permute(0, 2, 3, 1).reshape(co, kk * ci))
+                        if L.name.endswith("prediction.3"):
+                            L.t["wd"][:, :co].copy_(w.reshape(co, ci).t())
+                        else:
+                            # dgrad: dIn[y,x,ci] = sum dRaw[y+ky'-pad, x+kx'-pad, co] * W[co,ci,k-1-ky',k-1-kx']
+                            L.t["wd"].copy_(w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, kk * co))
+                    elif L.kind == "conv_s2":
+                        wf = w.permute(0, 2, 3, 1).reshape(co, kk * ci)
+                        L.t["wf"].copy_(wf)
+                        L.t["wd"].copy_(wf.t())                           # dcol = dRaw @ Wf  -> B operand [N=(tap,ci), K=co]
+                    elif L.kind in ("convT2", "convT"):
+                        L.t["wf"].copy_(w.permute(2, 3, 1, 0).reshape(kk * co, ci))
+                        L.t["wd"].copy_(w.permute(0, 2, 3, 1).reshape(ci, kk * co))
+                    elif L.kind == "convT_s1":
+                        # out[y,x,co] = sum in[y+ky'-2, x+kx'-2, ci] * Wt[ci,co,3-ky',3-kx']
+                        L.t["wf"].copy_(w.flip(2, 3).permute(1, 2, 3, 0).reshape(co, kk * ci))
+                        # dIn[iy,ix,ci] = sum dOut[iy-1+ky, ix-1+kx, co] * Wt[ci,co,ky,kx]
+                        L.t["wd"].copy_(w.permute(0, 2, 3, 1).reshape(ci, kk * co))
+        plan["pack_heads_fn"] = pack
+        be.host("pack_heads", pack)
+
+    # ------------------------------------------------------------------ plans
+    def get_plan(self, B, H, W, training):
+        key = (B, H, W, bool(training))
+        if key not in self.plans:
+            self.plans[key] = self.build_plan(B, H, W, bool(training))
+        return self.plans[key]
+
+    def build_plan(self, B, H, W, training):
+        if H % PATCH or W % PATCH or H != W:
+            raise ValueError(f"pixel_values must be square with sides a multiple of {PATCH} "
+                             f"(reference model/dinov2_pose.py:151 assumes H = W = sqrt(N)); got {H}x{W}")
+        if self.frozen is None:
+            self.pack_frozen()
+        if self.seed is None:
+            self.seed = torch.zeros(1, dtype=torch.int64, device=self.device)
+        be = self.be
+        D, L, heads = self.D, self.L, self.heads
+        g = H // PATCH
+        N = g * g
+        T = N + 1
+        M = B * T
+        plan = {"B": B, "H": H, "W": W, "training": training, "g": g, "N": N, "T": T, "M": M}
+        fz = self.frozen
+        t = plan["t"] = {}
+        t["px"] = self.new((B, 3, H, W), F32)
+        t["acol"] = self.new((B * N, PATCH_KP), self.adt)
+        t["x"] = self.new((M, D), F32)
+        t["xn"] = self.new((M, D), self.adt)
+        t["qkv"] = self.new((M, 3 * D), self.adt)
+        t["ctx"] = self.new((M, D), self.adt)
+        t["h"] = self.new((M, 4 * D), self.adt)
+        t["feat"] = self.new((B * N, D), self.adt)
+        pos = self.pos_tables(H, W)
+        use_lora = self.lora is not None
+        lora_train = use_lora and training
+        if training:
+            t["x_mid"] = self.new((M, D), F32)     # residual stream after the last block's attention branch
+            t["x_last"] = self.new((M, D), F32)    # residual stream entering the final LayerNorm
+            t["pre"] = self.new((M, 4 * D), self.adt)  # fc1 pre-activation of the last block
+        if lora_train:
+            t["y"] = self.new((M, D), F32)
+            t["u"] = self.new((M, self.lora["rank"]), F32)
+
+        # ---------------- forward program
+        prog_f = be.begin()
+        be.patch_im2col(t["px"], t["acol"], B=B, H=H, W=W, Kp=PATCH_KP)
+        be.fill_cls(t["x"], pos[0], B=B, T=T, D=D)
+        be.gemm(t["acol"], fz["wpe"], t["x"], M=B * N, N=D, K=PATCH_KP, out_dtype="f32", residual=pos,
+                row_map="patch_tokens", map_a=N, map_b=T, name="patch_embed")
+        scale = 1.0 / math.sqrt(D // heads)
+        for i in range(L):
+            lp = f"backbone.encoder.layer.{i}."
+            last = i == L - 1
+            be.layernorm_fwd(t["x"], self.p(lp + "norm1.weight"), self.p(lp + "norm1.bias"), t["xn"], None, rows=M, D=D,
+                             eps=LN_EPS)
+            be.gemm(t["xn"], fz[f"wqkv{i}"], t["qkv"], M=M, N=3 * D, K=D, bias=fz[f"bqkv{i}"], name=f"qkv{i}")
+            be.attention_fwd(t["qkv"], t["ctx"], B=B, T=T, heads=heads, scale=scale)
+            x_in = t["x"]
+            x_att = t["x_mid"] if (last and training) else t["x"]
+            if last and use_lora:
+                if lora_train:
+                    # explicit adapter (dropout + saved activations for the backward)
+                    be.gemm(t["ctx"], fz[f"wo{i}"], t["y"], M=M, N=D, K=D, bias=fz[f"bo{i}"], out_dtype="f32",
+                            name="proj_last")
+                    be.lora_fwd(t["y"], self.p(self.lora_prefix + "lora_A"), self.p(self.lora_prefix + "lora_B"),
+                                self.p(lp + "layer_scale1.lambda1"), x_in, x_att, t["u"], rows=M, D=D,
+                                R=self.lora["rank"], scaling=self.lora["alpha"] / self.lora["rank"],
+                                p_drop=float(self.lora.get("dropout", 0.0)), seed=self.seed)
+                else:
+                    # eval: fold the adapter into the projection, W' = (I + s A B)^T W  (dropout inactive)
+                    t["wo_m"] = self.new((D, D), self.adt)
+                    t["bo_m"] = self.new((D,), F32)
+                    be.host("merge_lora", self._merge_lora_fn(t["wo_m"], t["bo_m"], i))
+                    be.gemm(t["ctx"], t["wo_m"], x_att, M=M, N=D, K=D, bias=t["bo_m"], out_dtype="f32",
+                            ls=self.p(lp + "layer_scale1.lambda1"), residual=x_in, name="proj_last_merged")
+            else:
+                be.gemm(t["ctx"], fz[f"wo{i}"], x_att, M=M, N=D, K=D, bias=fz[f"bo{i}"], out_dtype="f32",
+                        ls=self.p(lp + "layer_scale1.lambda1"), residual=x_in, name=f"proj{i}")
+            be.layernorm_fwd(x_att, self.p(lp + "norm2.weight"), self.p(lp + "norm2.bias"), t["xn"], None, rows=M, D=D,
+                             eps=LN_EPS)
+            be.gemm(t["xn"], fz[f"w1{i}"], t["h"], M=M, N=4 * D, K=D, bias=self.p(lp + "mlp.fc1.bias"), act="gelu",
+                    aux_out=t["pre"] if (last and training) else None, ld_aux=4 * D, name=f"fc1_{i}")
+            x_out = t["x_last"] if (last and training) else t["x"]
+            be.gemm(t["h"], fz[f"w2{i}"], x_out, M=M, N=D, K=4 * D, bias=self.p(lp + "mlp.fc2.bias"), out_dtype="f32",
+                    ls=self.p(lp + "layer_scale2.lambda1"), residual=x_att, name=f"fc2_{i}")
+        x_fin = t["x_last"] if training else t["x"]
+        plan["x_final"] = x_fin
+        be.layernorm_fwd(x_fin, self.p("backbone.layernorm.weight"), self.p("backbone.layernorm.bias"), t["feat"], None,
+                         rows=M, D=D, T=T, drop_cls=True, eps=LN_EPS)
+        self.record_heads_forward(plan)
+        plan["fwd"] = prog_f
+        if training:
+            plan["bwd"] = be.begin()
+            self.record_backward(plan)
+        return plan
+
+    def _merge_lora_fn(self, wo_m, bo_m, i):
+        def fn():
+            with torch.no_grad():
+                A = self.p(self.lora_prefix + "lora_A").detach().float()
+                Bm = self.p(self.lora_prefix + "lora_B").detach().float()
+                s = self.lora["alpha"] / self.lora["rank"]
+                wo = self.p(self.att_prefix[i] + "output.dense.weight").detach().float()
+                bo = self.p(self.att_prefix[i] + "output.dense.bias").detach().float()
+                mix = torch.eye(self.D, device=wo.device) + s * (A @ Bm)      # y' = y @ mix
+                wo_m.copy_(mix.t() @ wo)
+                bo_m.copy_(bo @ mix)
+        return fn
+
+    # ------------------------------------------------------------------ heads forward
+    def _bn_tensors(self, L):
+        c = L.cout
+        for n in ("scale", "shift", "mean", "invstd"):
+            L.t[n] = self.new((c,), F32)
+        L.t["sums"] = self.new((2 * c,), torch.float64)
+
+    def _conv_forward(self, L, x, NB, training, out_override=None):
+        """Records conv (no BN) of layer L on NHWC input x; returns raw (train) or activated (eval) output.
+        x: 4-D NHWC view for implicit convs, 2-D [P, C] otherwise."""
+        be = self.be
+        P_out = NB * L.oh * L.ow
+        fold = (not training) and L.bn is not None
+        if fold:
+            be_scale, be_shift = L.t["scale"], L.t["shift"]
+            act = "relu" if L.relu else "none"
+        bias = self.p(L.name + ".bias")
+        out = out_override if out_override is not None else self.new((P_out, L.cout), self.adt)
+        kk = L.k * L.k
+        if L.kind == "conv" and L.k == 1:
+            be.gemm(x.reshape(-1, L.cin), L.t["wf"], out, M=P_out, N=L.cout, K=L.cin,
+                    bias=be_shift if fold else bias, scale=be_scale if fold else None, act=act if fold else "none",
+                    name=L.name)
+        elif L.kind in ("conv", "convT_s1"):
+            pad = L.pad if L.kind == "conv" else L.k - 1 - L.pad
+            xin = x.view(NB, L.ih, L.iw, L.cin) if x.dim() == 2 else x
+            be.gemm(xin, L.t["wf"], out, M=P_out, N=L.cout, K=kk * L.cin, bias=be_shift if fold else bias,
+                    scale=be_scale if fold else None, act=act if fold else "none",
+                    conv=dict(KH=L.k, KW=L.k, pad=pad, OH=L.oh, OW=L.ow), name=L.name)
+        elif L.kind == "conv_s2":
+            L.t["col"] = self.new((P_out, kk * L.cin), self.adt)
+            be.im2col(x, L.t["col"], NB=NB, IH=L.ih, IW=L.iw, C=L.cin, OH=L.oh, OW=L.ow, KH=L.k, KW=L.k, stride=L.stride,
+                      pad=L.pad)
+            be.gemm(L.t["col"], L.t["wf"], out, M=P_out, N=L.cout, K=kk * L.cin, bias=be_shift if fold else bias,
+                    scale=be_scale if fold else None, act=act if fold else "none", name=L.name)
+        elif L.kind == "convT2":
+            P_in = NB * L.ih * L.iw
+            L.t["bias4"] = self.new((kk * L.cout,), F32)
+            if fold:
+                L.t["scale4"] = self.new((kk * L.cout,), F32)
+            be.host("bias4", self._tile4_fn(L, fold))
+            be.gemm(x.reshape(P_in, L.cin), L.t["wf"], out, M=P_in, N=kk * L.cout, K=L.cin, bias=L.t["bias4"],
+                    scale=L.t["scale4"] if fold else None, act=act if fold else "none", row_map="shuffle2x2",
+                    map_a=L.cout, OH=L.ih, OW=L.iw, NB=NB, ldo=L.cout, name=L.name)
+        elif L.kind == "convT":
+            P_in = NB * L.ih * L.iw
+            L.t["colT"] = self.new((P_in, kk * L.cout), self.adt)
+            be.gemm(x.reshape(P_in, L.cin), L.t["wf"], L.t["colT"], M=P_in, N=kk * L.cout, K=L.cin, name=L.name)
+            raw = self.new((P_out, L.cout), self.adt) if fold else out
+            be.col2im(L.t["colT"], bias, raw, NB=NB, SH=L.ih, SW=L.iw, C=L.cout, BH=L.oh, BW=L.ow, KH=L.k, KW=L.k,
+                      stride=L.stride, pad=L.pad)
+            if fold:
+                L.t["shift_nb"] = self.new((L.cout,), F32)
+                be.host("fold_nobias", self._fold_nobias_fn(L))
+                be.bn_apply(raw, L.t["scale"], L.t["shift_nb"], None, None, out, P=P_out, C=L.cout, relu=L.relu)
+        elif L.kind == "dw":
+            raw = self.new((P_out, L.cout), self.adt) if fold else out
+            be.dwconv3x3(x, self.p(L.name + ".weight"), bias, None, raw, NB=NB, H=L.ih, W=L.iw, C=L.cin)
+            if fold:
+                L.t["shift_nb"] = self.new((L.cout,), F32)
+                be.host("fold_nobias", self._fold_nobias_fn(L))
+                be.bn_apply(raw, L.t["scale"], L.t["shift_nb"], None, None, out, P=P_out, C=L.cout, relu=L.relu)
+        else:
+            raise ValueError(L.kind)
+        return out
+
+    def _tile4_fn(self, L, fold):
+        def fn():
+            with torch.no_grad():
+                kk = L.k * L.k
+                if fold:
+                    L.t["bias4"].copy_(L.t["shift"].repeat(kk))
+                    L.t["scale4"].copy_(L.t["scale"].repeat(kk))
+                else:
+                    L.t["bias4"].copy_(self.p(L.name + ".bias").detach().repeat(kk))
+        return fn
+
+    def _fold_nobias_fn(self, L):
+        # col2im / dwconv already added the conv bias: remove it from the folded shift
+        def fn():
+            with torch.no_grad():
+                L.t["shift_nb"].copy_(L.t["shift"] - self.p(L.name + ".bias").detach() * L.t["scale"])
+        return fn
+
+    def _bn_forward(self, L, raw, NB, add1=None, add2=None, mode=0, out=None):
+        """train-mode BatchNorm (+ReLU, + fused adds) on raw [P, C]."""
+        be = self.be
+        P = NB * L.oh * L.ow
+        bn = L.bn
+        be.bn_stats(raw, L.t["sums"], P=P, C=L.cout)
+        be.bn_finalize(L.t["sums"], self.p(bn + ".weight"), self.p(bn + ".bias"), self.p(bn + ".running_mean"),
+                       self.p(bn + ".running_var"), L.t["scale"], L.t["shift"], L.t["mean"], L.t["invstd"], C=L.cout,
+                       count=P)
+        out = out if out is not None else self.new((P, L.cout), self.adt)
+        be.bn_apply(raw, L.t["scale"], L.t["shift"], add1, add2, out, P=P, C=L.cout, relu=L.relu, mode=mode)
+        return out
+
+    def record_heads_forward(self, plan):
+        be = self.be
+        B, g, training = plan["B"], plan["g"], plan["training"]
+        t = plan["t"]
+        Ls = plan["layers"] = self.build_head_layers(g)
+        self.record_pack_heads(plan)
+        for L in Ls.values():
+            if L.bn is not None:
+                self._bn_tensors(L)
+                if not training:
+                    bn = L.bn
+                    be.bn_fold_eval(self.p(bn + ".weight"), self.p(bn + ".bias"), self.p(bn + ".running_mean"),
+                                    self.p(bn + ".running_var"), self.p(L.name + ".bias"), L.t["scale"], L.t["shift"],
+                                    C=L.cout)
+        feat4 = t["feat"].view(B, g, g, self.D)
+        a = plan["a"] = {}    # activations (bf16 [P, C])
+        r = plan["raw"] = {}  # pre-BN conv outputs (training only)
+
+        def unit(key, x, **kw):
+            L = Ls[key]
+            if training:
+                r[key] = self._conv_forward(L, x, B, True)
+                a[key] = self._bn_forward(L, r[key], B, **kw)
+            else:
+                a[key] = self._conv_forward(L, x, B, False)
+            return a[key]
+
+        a1 = unit("fr0", feat4)
+        a1_4 = a1.view(B, g, g, 512)
+        if training:
+            unit("skip", a1)
+            unit("dw", a1_4)
+            unit("pw", a["dw"])
+            unit("down1", a1_4)
+            unit("down2", a["down1"].view(B, g // 2, g // 2, 256))
+            unit("bt1", a["down2"].view(B, g // 4, g // 4, 128))
+            unit("bt2", a["bt1"].view(B, g // 4, g // 4, 128), add1=a["down2"], mode=1)
+            unit("up1", a["bt2"])
+            # hourglass output = up2 + skip + depthwise branch (pose_heads.py:285), fused into up2's BN apply
+            unit("up2", a["up1"], add1=a["skip"], add2=a["pw"])
+            hgout = a["up2"]
+        else:
+            unit("skip", a1)
+            unit("dw", a1_4)
+            unit("pw", a["dw"])
+            unit("down1", a1_4)
+            unit("down2", a["down1"].view(B, g // 2, g // 2, 256))
+            unit("bt1", a["down2"].view(B, g // 4, g // 4, 128))
+            # bottleneck residual + relu, 3-way sum: small element-wise passes through bn_apply with identity BN
+            L = Ls["bt2"]
+            L.t["one"] = self.new((L.cout,), F32, 1.0)
+            L.t["zero"] = self.new((L.cout,), F32)
+            bt2 = unit("bt2", a["bt1"].view(B, g // 4, g // 4, 128))
+            a["bt2r"] = self.new(tuple(bt2.shape), self.adt)
+            be.bn_apply(bt2, L.t["one"], L.t["zero"], a["down2"], None, a["bt2r"], P=bt2.shape[0], C=L.cout, relu=True, mode=1)
+            unit("up1", a["bt2r"])
+            up2 = unit("up2", a["up1"])
+            L2 = Ls["up2"]
+            L2.t["one"] = self.new((L2.cout,), F32, 1.0)
+            L2.t["zero"] = self.new((L2.cout,), F32)
+            hgout = a["hg"] = self.new(tuple(up2.shape), self.adt)
+            be.bn_apply(up2, L2.t["one"], L2.t["zero"], a["skip"], a["pw"], hgout, P=up2.shape[0], C=L2.cout, relu=False, mode=0)
+        plan["hgout"] = hgout
+        unit("fr4", hgout.view(B, g, g, 512))
+        unit("ups0", a["fr4"])
+        s47, s48 = Ls["ups0"].oh, Ls["ups1"].oh
+        unit("ups1", a["ups0"].view(B, s47, s47, 128))
+        unit("pred0", a["ups1"].view(B, s48, s48, 128))
+        # prediction.3: 1x1 conv 64 -> K with bias, written straight to fp32 NCHW
+        L = Ls["pred3"]
+        K = self.K
+        t["hm_full"] = self.new((B, K, s48, s48), F32)
+        be.gemm(a["pred0"], L.t["wf"], t["hm_full"], M=B * s48 * s48, N=K, K=64, bias=self.p(L.name + ".bias"),
+                out_dtype="f32", row_map="nchw", n_valid=K, map_a=K, OH=s48, OW=s48, NB=B, block_n=32, name="pred3")
+        if s48 == self.hm_size:
+            t["hm"] = t["hm_full"]       # bilinear resize to the same size is the identity (pose_heads.py:353-359)
+        elif s48 == 2 * self.hm_size:
+            t["hm"] = self.new((B, K, self.hm_size, self.hm_size), F32)
+            be.avgpool2(t["hm_full"], t["hm"], planes=B * K, OH=self.hm_size, OW=self.hm_size)
+        else:
+            raise NotImplementedError(f"heat-map resize {s48} -> {self.hm_size} (only 1x and 2x reductions occur "
+                                      "for 224^2 / 448^2 inputs)")
+        # z head: mean over patch tokens -> MLP (pose_heads.py:397-398, :148-159)
+        zh = self.cfg["z_hidden"]
+        dims = [self.D] + list(zh) + [K]
+        t["zin"] = self.new((B, self.D), F32)
+        be.mean_tokens(t["feat"], t["zin"], B=B, N=plan["N"], D=self.D)
+        zp = "pose_heads.z_head.mlp."
+        cur = t["zin"]
+        p_drop = float(self.cfg.get("z_dropout", 0.0)) if training else 0.0
+        t["zact"] = [cur]
+        for j in range(len(dims) - 1):
+            lastl = j == len(dims) - 2
+            out = self.new((B, dims[j + 1]), F32)
+            be.sgemm_small(cur, dims[j], 1, self.p(zp + f"{3 * j}.weight"), 1, dims[j], out, dims[j + 1], M=B,
+                           N=dims[j + 1], K=dims[j], bias=self.p(zp + f"{3 * j}.bias"), relu=not lastl,
+                           p_drop=0.0 if lastl else p_drop, seed=self.seed if (p_drop > 0 and not lastl) else None)
+            cur = out
+            t["zact"].append(cur)
+        t["z"] = cur
+        plan["zdims"] = dims
+        if training:
+            counters = [self.Bufs[L.bn + ".num_batches_tracked"] for L in Ls.values() if L.bn is not None]
+
+            def bump():
+                for c in counters:      # torch BatchNorm bookkeeping (momentum is fixed, value unused)
+                    c.add_(1)
+            be.host("num_batches_tracked", bump)
+
+    # ------------------------------------------------------------------ backward
+    def record_backward(self, plan):
+        be = self.be
+        B, g, N, T, M = plan["B"], plan["g"], plan["N"], plan["T"], plan["M"]
+        D, K = self.D, self.K
+        t, a, r, Ls = plan["t"], plan["a"], plan["raw"], plan["layers"]
+        names = self.trainable_names()
+        total = sum(self.P[n].numel() for n in names)
+        flat = plan["gflat"] = self.new((total,), F32)
+        G = plan["grads"] = {}
+        off = 0
+        for n in names:
+            k = self.P[n].numel()
+            G[n] = flat[off:off + k].view(self.P[n].shape)
+            off += k
+        t["dhm"] = self.new(tuple(t["hm"].shape), F32)
+        t["dz"] = self.new((B, K), F32)
+        be.host("zero_grads", flat.zero_)
+        s47, s48 = Ls["ups0"].oh, Ls["ups1"].oh
+        P48 = B * s48 * s48
+
+        def bn_bwd(key, dact, add1=None, mode=0, dres=None, shuffle=False):
+            L = Ls[key]
+            P = B * L.oh * L.ow
+            bn = L.bn
+            be.bn_bwd_reduce(dact, r[key], add1, L.t["scale"], L.t["shift"], L.t["mean"], L.t["invstd"], L.t["sums"], P=P,
+                             C=L.cout, relu=L.relu, mode=mode)
+            draw = self.new((P, L.cout), self.adt)
+            be.bn_bwd_apply(dact, r[key], add1, self.p(bn + ".weight"), L.t["scale"], L.t["shift"], L.t["mean"],
+                            L.t["invstd"], L.t["sums"], draw, dres, G[bn + ".weight"], G[bn + ".bias"], P=P, C=L.cout,
+                            relu=L.relu, mode=mode, shuffle_oh=L.oh if shuffle else 0, shuffle_ow=L.ow if shuffle else 0)
+            be.host("zero_sums", L.t["sums"].zero_)
+            return draw
+
+        def conv_bwd(key, draw, x_in, want_dx=True, dx_residual=None):
+            """weight gradient of layer `key` (+ input gradient).  x_in = the layer's forward input."""
+            L = Ls[key]
+            k, ci, co = L.k, L.cin, L.cout
+            kk = k * k
+            gw = G[L.name + ".weight"]
+            P_out = B * L.oh * L.ow
+            P_in = B * L.ih * L.iw
+            dx = None
+            if L.kind == "conv" and k == 1:
+                be.wgrad(draw, x_in.reshape(P_in, ci), gw, Mc=co, Nc=ci, so_m=ci, so_n=1, P=P_out, name=L.name + ".wgrad")
+                if want_dx:
+                    dx = self.new((P_in, ci), self.adt)
+                    be.gemm(draw, L.t["wd"], dx, M=P_out, N=ci, K=draw.shape[1], residual=dx_residual,
+                            name=L.name + ".dgrad")
+            elif L.kind == "conv":
+                d4 = draw.view(B, L.oh, L.ow, co)
+                x4 = x_in.view(B, L.ih, L.iw, ci) if x_in.dim() == 2 else x_in
+                be.wgrad(d4, x4, gw, Mc=co, Nc=ci, so_m=ci * kk, so_n=kk, so_t=1, conv=dict(KH=k, KW=k, pad=L.pad),
+                         name=L.name + ".wgrad")
+                if want_dx:
+                    dx = self.new((P_in, ci), self.adt)
+                    be.gemm(d4, L.t["wd"], dx, M=P_in, N=ci, K=kk * co, residual=dx_residual,
+                            conv=dict(KH=k, KW=k, pad=k - 1 - L.pad, OH=L.ih, OW=L.iw), name=L.name + ".dgrad")
+            elif L.kind == "convT_s1":
+                x4 = x_in.view(B, L.ih, L.iw, ci)
+                d4 = draw.view(B, L.oh, L.ow, co)
+                be.wgrad(x4, d4, gw, Mc=ci, Nc=co, so_m=co * kk, so_n=kk, so_t=1, conv=dict(KH=k, KW=k, pad=L.pad),
+                         name=L.name + ".wgrad")
+                if want_dx:
+                    dx = self.new((P_in, ci), self.adt)
+                    be.gemm(d4, L.t["wd"], dx, M=P_in, N=ci, K=kk * co, residual=dx_residual,
+                            conv=dict(KH=k, KW=k, pad=L.pad, OH=L.ih, OW=L.iw), name=L.name + ".dgrad")
+            elif L.kind == "conv_s2":
+                be.wgrad(draw, L.t["col"], gw, Mc=co, Nc=kk * ci, so_m=ci * kk, so_n=kk, so_no=1, n_inner=ci, P=P_out,
+                         name=L.name + ".wgrad")
+                if want_dx:
+                    dcol = self.new((P_out, kk * ci), self.adt)
+                    be.gemm(draw, L.t["wd"], dcol, M=P_out, N=kk * ci, K=co, name=L.name + ".dgrad")
+                    dx = self.new((P_in, ci), self.adt)
+                    be.col2im(dcol, None, dx, NB=B, SH=L.oh, SW=L.ow, C=ci, BH=L.ih, BW=L.iw, KH=k, KW=k, stride=L.stride,
+                              pad=L.pad)
+            elif L.kind == "convT2":
+                # draw arrives in the un-shuffled [P_in, 4*Cout] layout (bn_bwd(..., shuffle=True))
+                dcol = draw.view(P_in, kk * co)
+                be.wgrad(x_in.reshape(P_in, ci), dcol, gw, Mc=ci, Nc=kk * co, so_m=co * kk, so_n=kk, so_no=1, n_inner=co,
+                         P=P_in, name=L.name + ".wgrad")
+                if want_dx:
+                    dx = self.new((P_in, ci), self.adt)
+                    be.gemm(dcol, L.t["wd"], dx, M=P_in, N=ci, K=kk * co, residual=dx_residual, name=L.name + ".dgrad")
+            elif L.kind == "convT":
+                dcol = self.new((P_in, kk * co), self.adt)
+                be.im2col(draw, dcol, NB=B, IH=L.oh, IW=L.ow, C=co, OH=L.ih, OW=L.iw, KH=k, KW=k, stride=L.stride,
+                          pad=L.pad)
+                be.wgrad(x_in.reshape(P_in, ci), dcol, gw, Mc=ci, Nc=kk * co, so_m=co * kk, so_n=kk, so_no=1, n_inner=co,
+                         P=P_in, name=L.name + ".wgrad")
+                if want_dx:
+                    dx = self.new((P_in, ci), self.adt)
+                    be.gemm(dcol, L.t["wd"], dx, M=P_in, N=ci, K=kk * co, residual=dx_residual, name=L.name + ".dgrad")
+            # conv biases feeding train-mode BN have an identically-zero gradient (the batch mean removes any
+            # constant); gflat was zeroed, nothing to write.
+            return dx
+
+        # ---- heat-map head
+        up = s48 // self.hm_size
+        t["ghm"] = self.new((P48, HM_PAD), self.adt)
+        be.hm_grad_to_nhwc(t["dhm"], t["ghm"], NB=B, K=K, Kp=HM_PAD, OH=s48, OW=s48, up=up)
+        L = Ls["pred3"]
+        be.colsum(t["ghm"], G[L.name + ".bias"], P=P48, C=K, ld=HM_PAD)
+        be.wgrad(t["ghm"], a["pred0"], G[L.name + ".weight"], Mc=K, Nc=64, so_m=64, so_n=1, P=P48, block_n=64,
+                 name="pred3.wgrad")
+        d = self.new((P48, 64), self.adt)
+        be.gemm(t["ghm"], L.t["wd"], d, M=P48, N=64, K=HM_PAD, name="pred3.dgrad")
+        d = conv_bwd("pred0", bn_bwd("pred0", d), a["ups1"])
+        d = conv_bwd("ups1", bn_bwd("ups1", d), a["ups0"])
+        d = conv_bwd("ups0", bn_bwd("ups0", d), a["fr4"])
+        d_hg = conv_bwd("fr4", bn_bwd("fr4", d), plan["hgout"])
+        # ---- hourglass (three consumers of d_hg: up2, skip, depthwise branch)
+        d = conv_bwd("up2", bn_bwd("up2", d_hg, shuffle=True), a["up1"])
+        d = conv_bwd("up1", bn_bwd("up1", d, shuffle=True), a["bt2"])
+        P4 = B * (g // 4) ** 2
+        dres = self.new((P4, 128), self.adt)
+        d = conv_bwd("bt2", bn_bwd("bt2", d, add1=a["down2"], mode=1, dres=dres), a["bt1"])
+        d = conv_bwd("bt1", bn_bwd("bt1", d), a["down2"], dx_residual=dres)
+        d = conv_bwd("down2", bn_bwd("down2", d), a["down1"])
+        d_a1 = conv_bwd("down1", bn_bwd("down1", d), a["fr0"])
+        # depthwise branch
+        d = conv_bwd("pw", bn_bwd("pw", d_hg), a["dw"])
+        ddw = bn_bwd("dw", d)
+        Ldw = Ls["dw"]
+        be.dwconv3x3_wgrad(a["fr0"], ddw, G[Ldw.name + ".weight"], NB=B, H=g, W=g, C=512)
+        d_a1b = self.new((B * g * g, 512), self.adt)
+        be.dwconv3x3(ddw, self.p(Ldw.name + ".weight"), None, d_a1, d_a1b, NB=B, H=g, W=g, C=512, flip=True)
+        # skip branch, accumulating into the running gradient of a1
+        d_a1c = conv_bwd("skip", bn_bwd("skip", d_hg), a["fr0"], dx_residual=d_a1b)
+        dfeat = conv_bwd("fr0", bn_bwd("fr0", d_a1c), t["feat"].view(B, g, g, D))
+        # ---- z head
+        dims = plan["zdims"]
+        zp = "pose_heads.z_head.mlp."
+        p_drop = float(self.cfg.get("z_dropout", 0.0))
+        dcur = t["dz"]
+        nl = len(dims) - 1
+        for j in reversed(range(nl)):
+            xin, yout = t["zact"][j], t["zact"][j + 1]
+            if j < nl - 1:
+                # through dropout + relu of layer j: mask by the saved (post-dropout) activation
+                dm = self.new((B, dims[j + 1]), F32)
+                t.setdefault("eyes", {})
+                eye = t["eyes"].setdefault(dims[j + 1], torch.eye(dims[j + 1], dtype=F32, device=self.device))
+                be.sgemm_small(dcur, dims[j + 1], 1, eye, dims[j + 1], 1, dm, dims[j + 1], M=B, N=dims[j + 1],
+                               K=dims[j + 1], mask_ref=yout, ld_ref=dims[j + 1], p_drop=p_drop,
+                               seed=self.seed if p_drop > 0 else None)
+                dcur = dm
+            be.sgemm_small(dcur, 1, dims[j + 1], xin, dims[j], 1, G[zp + f"{3 * j}.weight"], dims[j], M=dims[j + 1],
+                           N=dims[j], K=B)
+            be.colsum(dcur, G[zp + f"{3 * j}.bias"], P=B, C=dims[j + 1], ld=dims[j + 1])
+            dx = self.new((B, dims[j]), F32)
+            be.sgemm_small(dcur, dims[j + 1], 1, self.p(zp + f"{3 * j}.weight"), dims[j], 1, dx, dims[j], M=B, N=dims[j],
+                           K=dims[j + 1])
+            dcur = dx
+        be.mean_tokens_bwd(dfeat, dcur, B=B, N=N, D=D)
+        if not self.lora:
+            return
+        # ---- backbone: final LayerNorm, last block's MLP branch, LoRA adapter
+        lp = f"backbone.encoder.layer.{self.L - 1}."
+        fz = self.frozen
+        t["gx"] = self.new((M, D), F32)
+        t["gxs"] = self.new((M, D), self.adt)
+        be.layernorm_bwd(dfeat, t["x_last"], self.p("backbone.layernorm.weight"), None, t["gx"], rows=M, D=D, T=T,
+                         drop_cls=True, eps=LN_EPS, ls=self.p(lp + "layer_scale2.lambda1"), dx_scaled=t["gxs"])
+        t["dpre"] = self.new((M, 4 * D), self.adt)
+        be.gemm(t["gxs"], fz["w2T"], t["dpre"], M=M, N=4 * D, K=D, aux_in=t["pre"], ld_aux=4 * D, name="fc2.dgrad")
+        t["dxn2"] = self.new((M, D), self.adt)
+        be.gemm(t["dpre"], fz["w1T"], t["dxn2"], M=M, N=D, K=4 * D, name="fc1.dgrad")
+        t["gmid"] = self.new((M, D), F32)
+        be.layernorm_bwd(t["dxn2"], t["x_mid"], self.p(lp + "norm2.weight"), t["gx"], t["gmid"], rows=M, D=D, eps=LN_EPS)
+        be.lora_bwd(t["gmid"], t["y"], t["u"], self.p(self.lora_prefix + "lora_B"), self.p(lp + "layer_scale1.lambda1"),
+                    G[self.lora_prefix + "lora_A"], G[self.lora_prefix + "lora_B"], rows=M, D=D, R=self.lora["rank"],
+                    scaling=self.lora["alpha"] / self.lora["rank"], p_drop=float(self.lora.get("dropout", 0.0)),
+                    seed=self.seed)
+
+    # ------------------------------------------------------------------ running
+    def check_frozen(self):
+        if self.frozen is not None and self._versions(frozen=True) != self.frozen_versions:
+            # frozen parameters were modified (load_state_dict, manual edit): repack and drop plans
+            self.frozen = None
+            self.plans = {}
+
+    def forward(self, pixel_values, training):
+        self.check_frozen()
+        B, C, H, W = pixel_values.shape
+        if C != 3:
+            raise ValueError("Make sure that the channel dimension of the pixel values match with the one set in the "
+                             f"configuration. Expected 3 but got {C}.")   # HF modeling_dinov2.py:143-147
+        plan = self.get_plan(B, H, W, training)
+        plan["t"]["px"].copy_(pixel_values, non_blocking=True)
+        if training:
+            self.seed.add_(1)
+        plan["fwd"].run()
+        return plan
+
+    def backward(self, plan, dhm, dz):
+        t = plan["t"]
+        if dhm is None:
+            t["dhm"].zero_()
+        else:
+            t["dhm"].copy_(dhm)
+        if dz is None:
+            t["dz"].zero_()
+        else:
+            t["dz"].copy_(dz)
+        plan["bwd"].run()
+        return plan["grads"]

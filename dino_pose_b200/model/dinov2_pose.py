@@ -1,0 +1,212 @@
+"""DINOv2 pose models (mirrors reference model/dinov2_pose.py): same constructor arguments, attributes,
+``forward(pixel_values) -> (heatmaps, z_coords)`` and ``state_dict`` keys; compute on the sm_100a engine.
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import Any, Dict
+
+import torch
+import torch.nn.functional as F
+
+from .base_pose import BasePoseModel
+from .dinov2_backbone import Dinov2Model
+from .lora import LoRAAttention
+from .pose_heads import SpatialAwarePoseHeads
+
+_Z_CONFIG = {"hidden_dims": (1024, 512, 256), "dropout_rate": 0.1}   # reference dinov2_pose.py:50-53
+
+
+def _image_processor(name):
+    """``AutoImageProcessor.from_pretrained`` needs the hub; callers only read ``crop_size`` / call it on PIL
+    images (demo.py:171,281).  Use the real one when it is cached locally, else a stub carrying the defaults."""
+    try:
+        from transformers import AutoImageProcessor
+        return AutoImageProcessor.from_pretrained(name, local_files_only=True)
+    except Exception:
+        return SimpleNamespace(crop_size={"height": 224, "width": 224}, size={"shortest_edge": 256},
+                               image_mean=[0.485, 0.456, 0.406], image_std=[0.229, 0.224, 0.225])
+
+
+class _PoseFunction(torch.autograd.Function):
+    """Autograd boundary: one fused forward program, one fused backward program."""
+
+    @staticmethod
+    def forward(ctx, model, pixel_values, *trainable):
+        eng = model._get_engine(pixel_values.device)
+        plan = eng.forward(pixel_values, training=True)
+        ctx.eng, ctx.plan, ctx.names = eng, plan, model._trainable_names
+        ctx.mark_non_differentiable()
+        return plan["t"]["hm"].clone(), plan["t"]["z"].clone()
+
+    @staticmethod
+    def backward(ctx, dhm, dz):
+        grads = ctx.eng.backward(ctx.plan, dhm, dz)
+        return (None, None) + tuple(grads[n].clone() for n in ctx.names)
+
+
+class _Dinov2PoseBase(BasePoseModel):
+    lora_config = None
+
+    def _init_common(self, num_keypoints, backbone, heatmap_size):
+        self.backbone = Dinov2Model.from_pretrained(backbone)
+        self.backbone_name = backbone
+        self.image_processor = _image_processor(backbone)
+        self.heatmap_size, self.num_keypoints = heatmap_size, num_keypoints
+        self._coreml_patch_applied = False
+        for p in self.backbone.parameters():
+            p.requires_grad = False
+
+    def _init_heads(self, num_keypoints, heatmap_size):
+        self.feat_dim = self.backbone.config.hidden_size
+        self.pose_heads = SpatialAwarePoseHeads(feat_channels=self.feat_dim, num_keypoints=num_keypoints,
+                                                heatmap_size=heatmap_size, spatial_input_size=16,
+                                                z_coord_config=dict(_Z_CONFIG))
+        self._engine = None
+        self._backend_factory = None
+
+    # ---- engine plumbing
+    def _get_engine(self, device):
+        if self._engine is not None and self._engine.device == device:
+            return self._engine
+        from ..engine import PoseEngine
+        if self._backend_factory is not None:
+            backend = self._backend_factory()
+        else:
+            if device.type != "cuda":
+                raise RuntimeError("dino_pose_b200 runs on CUDA (sm_100a) only: move the model and the input to a "
+                                   "B200 (`model.cuda()`); there is no CPU execution path")
+            from ..backend import CudaBackend
+            backend = CudaBackend()
+        cfg = self.backbone.config
+        lora = None
+        if self.lora_config is not None:
+            lora = {"rank": self.lora_config["rank"], "alpha": self.lora_config["alpha"],
+                    "dropout": self._lora_layer().dropout.p}
+        zh = self.pose_heads.z_head
+        ecfg = dict(D=cfg.hidden_size, L=cfg.num_hidden_layers, heads=cfg.num_attention_heads,
+                    num_keypoints=self.num_keypoints, heatmap_size=self.heatmap_size, lora=lora,
+                    z_hidden=zh.hidden_dims, z_dropout=zh.mlp[2].p)
+        if getattr(self, "_act_dtype", None) is not None:
+            ecfg["act_dtype"] = self._act_dtype
+        self._engine = PoseEngine(dict(self.named_parameters()), dict(self.named_buffers()), ecfg, backend, device)
+        return self._engine
+
+    def _lora_layer(self):
+        return self.backbone.encoder.layer[-1].attention.lora_output
+
+    def _apply(self, fn, *a, **k):
+        # .to()/.cuda() replace parameter storage: plans built on the old tensors are stale
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def _sync_dropout_config(self):
+        if self._engine is None:
+            return
+        e = self._engine
+        zp = self.pose_heads.z_head.mlp[2].p
+        lp = self._lora_layer().dropout.p if self.lora_config is not None else 0.0
+        if e.cfg.get("z_dropout") != zp or (e.lora is not None and e.lora.get("dropout") != lp):
+            self._engine = None    # probabilities are baked into the recorded programs
+
+    def forward(self, pixel_values):
+        """reference model/dinov2_pose.py:143-157 / :292-306."""
+        self._sync_dropout_config()
+        self._trainable_names = [n for n, p in self.named_parameters() if p.requires_grad]
+        needs_grad = torch.is_grad_enabled() and self.training and bool(self._trainable_names)
+        if not self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            needs_grad = False   # eval-mode forward: inference program, no graph (see DESIGN.md "eval + grad")
+        if needs_grad:
+            params = [p for p in self.parameters() if p.requires_grad]
+            return _PoseFunction.apply(self, pixel_values, *params)
+        eng = self._get_engine(pixel_values.device)
+        plan = eng.forward(pixel_values, training=self.training)
+        return plan["t"]["hm"].clone(), plan["t"]["z"].clone()
+
+    # ---- CoreML export hooks (reference :56-131, :221-278) -- export-time only, not on the CUDA path
+    def apply_coreml_compatibility_patch(self):
+        if self._coreml_patch_applied:
+            print("Core ML patch already applied")
+            return
+        emb = self.backbone.embeddings
+
+        def nearest_pos_encoding(embeddings, width, height):
+            pos = emb.position_embeddings
+            n_pos = pos.shape[1] - 1
+            if embeddings.shape[1] - 1 == n_pos and height == width:
+                return pos
+            d = embeddings.shape[-1]
+            h0, w0 = height // emb.patch_size + 0.1, width // emb.patch_size + 0.1
+            side = int(n_pos ** 0.5)
+            grid = pos[:, 1:].reshape(1, side, side, d).permute(0, 3, 1, 2)
+            grid = F.interpolate(grid, size=(int(h0), int(w0)), mode="nearest")
+            return torch.cat((pos[:, 0].unsqueeze(0), grid.permute(0, 2, 3, 1).view(1, -1, d)), dim=1)
+
+        self._orig_interpolate = emb.interpolate_pos_encoding
+        emb.interpolate_pos_encoding = nearest_pos_encoding
+        self._coreml_patch_applied = True
+        print("Core ML compatibility patch applied (bicubic -> nearest position-embedding resize)")
+
+    def remove_coreml_compatibility_patch(self):
+        if not self._coreml_patch_applied:
+            print("No Core ML patch to remove")
+            return
+        self.backbone.embeddings.interpolate_pos_encoding = self._orig_interpolate
+        self._coreml_patch_applied = False
+        print("Core ML patch removed")
+
+
+class Dinov2PoseModel(_Dinov2PoseBase):
+    """Frozen DINOv2 backbone + trainable pose heads (reference model/dinov2_pose.py:10-174)."""
+
+    def __init__(self, num_keypoints=24, backbone="facebook/dinov2-base", unfreeze_last_n_layers=0, heatmap_size=48):
+        super().__init__()
+        if unfreeze_last_n_layers > 0:
+            raise NotImplementedError(
+                "unfreeze_last_n_layers > 0 needs the attention / QKV backward kernels (SURVEY 8f-4, next row); "
+                "the LoRA fine-tuning path (Dinov2PoseModelLoRA) is the one implemented")
+        self._init_common(num_keypoints, backbone, heatmap_size)
+        self._init_heads(num_keypoints, heatmap_size)
+
+    @classmethod
+    def from_config(cls, model_name: str, config: Dict[str, Any]):
+        return cls(num_keypoints=config["num_keypoints"], backbone=model_name,
+                   unfreeze_last_n_layers=config.get("unfreeze_last_n_layers", 0),
+                   heatmap_size=config["output_heatmap_size"])
+
+
+class Dinov2PoseModelLoRA(_Dinov2PoseBase):
+    """DINOv2 backbone with a LoRA adapter on the LAST block's attention output + trainable heads
+    (reference model/dinov2_pose.py:176-348; adapter placement :197-204)."""
+
+    def __init__(self, num_keypoints=24, backbone="facebook/dinov2-base", heatmap_size=48, lora_rank=8, lora_alpha=16,
+                 lora_dropout=0.1):
+        super().__init__()
+        self._init_common(num_keypoints, backbone, heatmap_size)
+        self.lora_config = {"rank": lora_rank, "alpha": lora_alpha, "dropout": lora_dropout}
+        layers = self.backbone.encoder.layer
+        for i, layer in enumerate(layers):
+            if i >= len(layers) - 1:
+                layer.attention = LoRAAttention(layer.attention, r=lora_rank, alpha=lora_alpha, dropout=lora_dropout)
+        self._init_heads(num_keypoints, heatmap_size)
+
+    @classmethod
+    def from_config(cls, model_name: str, config: Dict[str, Any]):
+        return cls(num_keypoints=config["num_keypoints"], backbone=model_name,
+                   heatmap_size=config["output_heatmap_size"], lora_rank=config.get("lora_rank", 8),
+                   lora_alpha=config.get("lora_alpha", 16), lora_dropout=config.get("lora_dropout", 0.1))
+
+    def apply_loading_fixes(self):
+        """reference :325-348: re-sync alpha / rank / dropout.p with ``lora_config`` and force eval mode."""
+        for _, m in self.named_modules():
+            if hasattr(m, "alpha") and hasattr(m, "rank"):
+                m.alpha, m.rank = self.lora_config["alpha"], self.lora_config["rank"]
+            if hasattr(m, "dropout") and hasattr(m.dropout, "p"):
+                if abs(m.dropout.p - self.lora_config["dropout"]) > 1e-6:
+                    m.dropout.p = self.lora_config["dropout"]
+        self.eval()
+        self._engine = None

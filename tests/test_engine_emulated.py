@@ -1,0 +1,130 @@
+"""Host-logic test (CPU): the engine's op graph, weight packing and index conventions, executed through
+the torch emulator of the C-ABI op vocabulary (tests/emulator.py), against the oracle and the golden
+vectors of the real reference.  bf16 storage is emulated, so tolerances are the bf16 ones."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import pose_oracle
+from oracle.weights import make_inputs, make_state_dict
+from tests.emulator import TorchEmulator
+
+from dino_pose_b200.model import Dinov2PoseModel, Dinov2PoseModelLoRA
+
+
+def relmax(a, b):
+    a, b = torch.as_tensor(a).double(), torch.as_tensor(b).double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def build(arch, lora_rank, seed=0, act_dtype=None):
+    if lora_rank:
+        m = Dinov2PoseModelLoRA(backbone=arch, lora_rank=lora_rank, lora_alpha=16, lora_dropout=0.0)
+    else:
+        m = Dinov2PoseModel(backbone=arch)
+    m.load_state_dict(make_state_dict(arch, seed, lora_rank))
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    m._backend_factory = TorchEmulator
+    m._act_dtype = act_dtype
+    return m
+
+
+@pytest.mark.parametrize("case", ["tiny_frozen_b2_224_eval"])
+def test_eval_forward_matches_reference_golden(golden_dir, case):
+    g = np.load(os.path.join(golden_dir, case + ".npz"))
+    m = build("test/dinov2-tiny", 0).eval()
+    inp = make_inputs(2, 224, 224, 0)
+    with torch.no_grad():
+        hm, z = m(inp["pixel_values"])
+    assert relmax(hm, g["heatmaps"]) < 2e-2      # north_star bf16 tolerance: max|a-b| / max|b|
+    assert relmax(z, g["z"]) < 2e-2
+
+
+def test_eval_forward_lora_merged_matches_oracle():
+    arch = "test/dinov2-tiny"
+    m = build(arch, 8).eval()
+    inp = make_inputs(2, 224, 224, 1)
+    with torch.no_grad():
+        hm, z = m(inp["pixel_values"])
+        sd = make_state_dict(arch, 0, 8)
+        rhm, rz = pose_oracle.model_forward(sd, inp["pixel_values"], arch, {"rank": 8, "alpha": 16}, False)
+    assert relmax(hm, rhm) < 2e-2
+    assert relmax(z, rz) < 2e-2
+
+
+def _train_grads(golden_dir, act_dtype):
+    g = np.load(os.path.join(golden_dir, "tiny_lora_b3_224_train.npz"))
+    arch = "test/dinov2-tiny"
+    m = build(arch, 8, act_dtype=act_dtype).train()
+    inp = make_inputs(3, 224, 224, 0)
+    hm, z = m(inp["pixel_values"])
+    tol = 2e-2 if act_dtype is None else 1e-4
+    assert relmax(hm.detach(), g["heatmaps"]) < tol
+    assert relmax(z.detach(), g["z"]) < tol
+    conf = inp["keypoints"][..., 2]
+    kp = pose_oracle.keypoint_loss(hm, inp["heatmaps"], conf)
+    zl = pose_oracle.z_loss(z, inp["z"], conf)
+    w = pose_oracle.DynamicLossWeighting()
+    w.update(kp.item(), zl.item())
+    w.balanced(kp, zl).backward()
+    from oracle.make_golden import subsample
+    stats = {}
+    for name, p in m.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None
+            continue
+        assert p.grad is not None, name
+        gn = float(g["gradnorm." + name])
+        if gn < 1e-6:
+            assert float(p.grad.norm()) < 1e-6, name
+            continue
+        ref = g["grad." + name]
+        sub = subsample(p.grad)
+        rel = np.linalg.norm(sub - ref) / (np.linalg.norm(ref) + 1e-30)
+        cos = float(np.dot(sub, ref) / (np.linalg.norm(sub) * np.linalg.norm(ref) + 1e-30))
+        stats[name] = (rel, cos)
+    for k in g.files:   # BatchNorm running statistics were updated like torch does
+        if k.startswith("buf."):
+            cur = dict(m.named_buffers())[k[4:]]
+            assert relmax(subsample(cur), g[k]) < tol, k
+    return stats
+
+
+def test_train_step_logic_exact_in_fp32_storage(golden_dir):
+    """fp32 storage through the same op graph: every gradient of the real reference is reproduced
+    (cosine 1.0000) -- the op graph, packing layouts and tap conventions are right."""
+    stats = _train_grads(golden_dir, torch.float32)
+    assert len(stats) >= 50
+    bad = {n: v for n, v in stats.items() if v[0] > 1e-2 or v[1] < 0.9999}
+    assert not bad, bad
+
+
+def test_train_step_bf16_storage_vs_reference(golden_dir):
+    """bf16 storage: gradients upstream of train-mode BatchNorm are cancelling sums (fp32 itself deviates
+    5e-4 from fp64, see tests/test_oracle_golden.py) and the L1 z-loss gradient flips sign on near-zero
+    residuals, so bf16 forward rounding moves them by up to ~25% relative L2 while staying aligned."""
+    stats = _train_grads(golden_dir, None)
+    bad = {n: v for n, v in stats.items() if v[0] > 0.35 or v[1] < 0.95}
+    assert not bad, bad
+
+
+def test_448_eval_matches_oracle():
+    arch = "test/dinov2-tiny"
+    m = build(arch, 0).eval()
+    inp = make_inputs(1, 448, 448, 2)
+    with torch.no_grad():
+        hm, z = m(inp["pixel_values"])
+        rhm, rz = pose_oracle.model_forward(make_state_dict(arch, 0, 0), inp["pixel_values"], arch, None, False)
+    assert hm.shape == (1, 24, 48, 48)
+    assert relmax(hm, rhm) < 2e-2
+    assert relmax(z, rz) < 2e-2
+
+
+def test_cpu_without_backend_raises():
+    m = Dinov2PoseModel(backbone="test/dinov2-tiny").eval()
+    with pytest.raises(RuntimeError, match="no CPU execution path"):
+        m(torch.zeros(1, 3, 224, 224))

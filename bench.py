@@ -214,10 +214,25 @@ def run_ours(args):
         launches = len(plan["fwd"]) + len(plan["bwd"])
         agg = {}
         reps = 3
+        per_launch = {}
         for _ in range(reps):
-            for rec in plan["fwd"].run_timed() + plan["bwd"].run_timed():
+            recs = plan["fwd"].run_timed() + plan["bwd"].run_timed()
+            for i, rec in enumerate(recs):
+                pl = per_launch.setdefault(i, dict(rec, ms=0.0))
+                pl["ms"] += rec["ms"] / reps
+            for rec in recs:
                 a = agg.setdefault(rec["kernel"], {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "n": 0})
                 a["ms"] += rec["ms"]; a["flops"] += rec["flops"]; a["bytes"] += rec["bytes"]; a["n"] += 1
+        dump = os.environ.get("DP_BENCH_DUMP")
+        if dump:
+            with open(dump, "w") as f:
+                f.write("idx,name,kernel,ms,gflop,tflops,mbytes,gbs\n")
+                for i in sorted(per_launch):
+                    r = per_launch[i]
+                    tf = r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] > 0 else 0
+                    gb = r["bytes"] / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 else 0
+                    f.write(f'{i},{r["name"]},{r["kernel"]},{r["ms"]:.5f},{r["flops"] / 1e9:.3f},{tf:.1f},'
+                            f'{r["bytes"] / 1e6:.2f},{gb:.0f}\n')
         peaks = load_peaks()
         top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         name, a = top

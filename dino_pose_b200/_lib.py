@@ -78,26 +78,27 @@ SIGNATURES = {
     "dp_patch_im2col": [c_vp, c_vp, i, i, i, i, c_vp],
     "dp_fill_cls": [c_vp, c_vp, i, i, i, c_vp],
     "dp_lora_fwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, f, f, c_vp, c_vp],
-    "dp_lora_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, f, f, c_vp, c_vp],
+    "dp_lora_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, f, f, c_vp, c_vp],
     "dp_attention_fwd": [c_vp, c_vp, i, i, i, f, c_vp],
     "dp_decode": [c_vp, i, i, i, d, d, c_vp, c_vp, c_vp, c_vp],
     "dp_im2col": [c_vp, c_vp, i, i, i, i, i, i, i, i, i, i, c_vp],
-    "dp_col2im": [c_vp, c_vp, c_vp, i, i, i, i, i, i, i, i, i, i, c_vp],
-    "dp_dwconv3x3": [c_vp, c_vp, c_vp, c_vp, c_vp, i, i, i, i, i, c_vp],
+    "dp_col2im": [c_vp, c_vp, c_vp, i, i, i, i, i, i, i, i, i, i, i, c_vp],
+    "dp_dwconv3x3": [c_vp, c_vp, c_vp, c_vp, c_vp, i, i, i, i, i, i, c_vp],
     "dp_dwconv3x3_wgrad": [c_vp, c_vp, c_vp, i, i, i, i, c_vp],
-    "dp_bn_stats": [c_vp, c_vp, c_ll, i, c_vp],
+    "dp_bn_stats": [c_vp, i, c_vp, c_ll, i, c_vp],
     "dp_bn_finalize": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, d, f, f, c_vp],
     "dp_bn_fold_eval": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, f, c_vp],
-    "dp_bn_apply": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, c_vp],
-    "dp_bn_bwd_reduce": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, c_vp],
-    "dp_bn_bwd_apply": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, i,
-                        i, i, c_vp],
+    "dp_bn_apply": [c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, c_vp],
+    "dp_bn_bwd_reduce": [c_vp, c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, c_vp],
+    "dp_bn_bwd_apply": [c_vp, c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i,
+                        i, i, i, c_vp],
     "dp_avgpool2": [c_vp, c_vp, c_ll, i, i, c_vp],
     "dp_hm_grad_to_nhwc": [c_vp, c_vp, i, i, i, i, i, i, c_vp],
     "dp_mean_tokens": [c_vp, c_vp, i, i, i, c_vp],
     "dp_mean_tokens_bwd": [c_vp, c_vp, i, i, i, c_vp],
     "dp_sgemm_small": [c_vp, c_ll, c_ll, c_vp, c_ll, c_ll, c_vp, c_ll, i, i, i, c_vp, i, c_vp, c_ll, f, c_vp, i, c_vp],
     "dp_colsum": [c_vp, i, c_vp, c_ll, i, c_ll, c_vp],
+    "dp_relu_mask": [c_vp, c_vp, c_vp, c_ll, f, c_vp],
 }
 _RESTYPES = {"dp_last_error": C.c_char_p}
 

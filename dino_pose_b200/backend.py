@@ -132,6 +132,8 @@ class CudaBackend:
             a.lda = lda if lda is not None else A.stride(0)
             a.OH, a.OW, a.NB = OH, OW, NB
         a.ldo = ldo if ldo is not None else (out.stride(0) if out.dim() == 2 else 0)
+        if out.dtype == torch.float32:
+            out_dtype = "f32"        # the output tensor decides (pre-BN conv outputs are fp32 in training)
         a.out_dtype = 0 if out_dtype == "bf16" else 1
         _chk(out, torch.bfloat16 if out_dtype == "bf16" else torch.float32, name + ".out", contiguous=False)
         for t, nm in ((bias, "bias"), (scale, "scale"), (ls, "ls")):
@@ -203,9 +205,10 @@ class CudaBackend:
         self.prog.add("lora_fwd", self.lib.dp_lora_fwd, _p(y), _p(A), _p(Bm), _p(lambda1), _p(x_in), _p(x_out),
                       _p(u_save), rows, D, R, scaling, p_drop, _p(seed), keep=(y, A, Bm, lambda1, x_in, x_out, u_save, seed))
 
-    def lora_bwd(self, g, y, u_saved, Bm, lambda1, dA, dB, *, rows, D, R, scaling, p_drop, seed):
+    def lora_bwd(self, g, y, u_saved, Bm, lambda1, dA, dB, gu_ws, *, rows, D, R, scaling, p_drop, seed):
         self.prog.add("lora_bwd", self.lib.dp_lora_bwd, _p(g), _p(y), _p(u_saved), _p(Bm), _p(lambda1), _p(dA), _p(dB),
-                      rows, D, R, scaling, p_drop, _p(seed), keep=(g, y, u_saved, Bm, lambda1, dA, dB, seed))
+                      _p(gu_ws), rows, D, R, scaling, p_drop, _p(seed),
+                      keep=(g, y, u_saved, Bm, lambda1, dA, dB, gu_ws, seed))
 
     def attention_fwd(self, qkv, ctx, *, B, T, heads, scale):
         _chk(qkv, torch.bfloat16, "attention.qkv")
@@ -222,19 +225,20 @@ class CudaBackend:
                       keep=(x, col))
 
     def col2im(self, col, bias, big, *, NB, SH, SW, C, BH, BW, KH, KW, stride, pad):
-        self.prog.add("col2im", self.lib.dp_col2im, _p(col), _p(bias), _p(big), NB, SH, SW, C, BH, BW, KH, KW, stride,
-                      pad, keep=(col, bias, big))
+        self.prog.add("col2im", self.lib.dp_col2im, _p(col), _p(bias), _p(big), int(big.dtype == torch.float32), NB, SH,
+                      SW, C, BH, BW, KH, KW, stride, pad, keep=(col, bias, big))
 
     def dwconv3x3(self, x, w, bias, add, out, *, NB, H, W, C, flip=False):
-        self.prog.add("dwconv3x3", self.lib.dp_dwconv3x3, _p(x), _p(w), _p(bias), _p(add), _p(out), NB, H, W, C,
-                      int(flip), keep=(x, w, bias, add, out))
+        self.prog.add("dwconv3x3", self.lib.dp_dwconv3x3, _p(x), _p(w), _p(bias), _p(add), _p(out),
+                      int(out.dtype == torch.float32), NB, H, W, C, int(flip), keep=(x, w, bias, add, out))
 
     def dwconv3x3_wgrad(self, x, dout, dw, *, NB, H, W, C):
         self.prog.add("dwconv3x3_wgrad", self.lib.dp_dwconv3x3_wgrad, _p(x), _p(dout), _p(dw), NB, H, W, C,
                       keep=(x, dout, dw))
 
     def bn_stats(self, raw, sums, *, P, C):
-        self.prog.add("bn_stats", self.lib.dp_bn_stats, _p(raw), _p(sums), P, C, keep=(raw, sums))
+        self.prog.add("bn_stats", self.lib.dp_bn_stats, _p(raw), int(raw.dtype == torch.float32), _p(sums), P, C,
+                      keep=(raw, sums))
 
     def bn_finalize(self, sums, gamma, beta, rm, rv, scale, shift, mean, invstd, *, C, count, eps=1e-5, momentum=0.1):
         self.prog.add("bn_finalize", self.lib.dp_bn_finalize, _p(sums), _p(gamma), _p(beta), _p(rm), _p(rv), _p(scale),
@@ -246,17 +250,19 @@ class CudaBackend:
                       _p(scale), _p(shift), C, eps, keep=(gamma, beta, rm, rv, conv_bias, scale, shift))
 
     def bn_apply(self, raw, scale, shift, add1, add2, out, *, P, C, relu=True, mode=0):
-        self.prog.add("bn_apply", self.lib.dp_bn_apply, _p(raw), _p(scale), _p(shift), _p(add1), _p(add2), _p(out), P,
-                      C, int(relu), mode, keep=(raw, scale, shift, add1, add2, out))
+        self.prog.add("bn_apply", self.lib.dp_bn_apply, _p(raw), int(raw.dtype == torch.float32), _p(scale), _p(shift),
+                      _p(add1), _p(add2), _p(out), P, C, int(relu), mode, keep=(raw, scale, shift, add1, add2, out))
 
     def bn_bwd_reduce(self, dout, raw, add1, scale, shift, mean, invstd, sums, *, P, C, relu=True, mode=0):
-        self.prog.add("bn_bwd_reduce", self.lib.dp_bn_bwd_reduce, _p(dout), _p(raw), _p(add1), _p(scale), _p(shift),
+        self.prog.add("bn_bwd_reduce", self.lib.dp_bn_bwd_reduce, _p(dout), _p(raw), int(raw.dtype == torch.float32),
+                      _p(add1), _p(scale), _p(shift),
                       _p(mean), _p(invstd), _p(sums), P, C, int(relu), mode,
                       keep=(dout, raw, add1, scale, shift, mean, invstd, sums))
 
     def bn_bwd_apply(self, dout, raw, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta, *, P, C,
                      relu=True, mode=0, eval_mode=False, shuffle_oh=0, shuffle_ow=0):
-        self.prog.add("bn_bwd_apply", self.lib.dp_bn_bwd_apply, _p(dout), _p(raw), _p(add1), _p(gamma), _p(scale),
+        self.prog.add("bn_bwd_apply", self.lib.dp_bn_bwd_apply, _p(dout), _p(raw), int(raw.dtype == torch.float32),
+                      _p(add1), _p(gamma), _p(scale),
                       _p(shift), _p(mean), _p(invstd), _p(sums), _p(draw), _p(dres), _p(dgamma), _p(dbeta), P, C,
                       int(relu), mode, int(eval_mode), shuffle_oh, shuffle_ow,
                       keep=(dout, raw, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta))
@@ -280,6 +286,9 @@ class CudaBackend:
         self.prog.add("sgemm_small", self.lib.dp_sgemm_small, _p(A), sa_m, sa_k, _p(Bm), sb_k, sb_n, _p(Cm), ldc, M, N, K,
                       _p(bias), int(relu), _p(mask_ref), ld_ref, p_drop, _p(seed), int(accumulate),
                       keep=(A, Bm, Cm, bias, mask_ref, seed))
+
+    def relu_mask(self, d, ref, out, *, n, keep_scale=1.0):
+        self.prog.add("relu_mask", self.lib.dp_relu_mask, _p(d), _p(ref), _p(out), n, float(keep_scale), keep=(d, ref, out))
 
     def colsum(self, x, out, *, P, C, ld):
         self.prog.add("colsum", self.lib.dp_colsum, _p(x), int(x.dtype == torch.bfloat16), _p(out), P, C, ld,

@@ -17,24 +17,24 @@ cudaError_t launch_patch_im2col(const float*, __nv_bfloat16*, int, int, int, int
 cudaError_t launch_fill_cls(float*, const float*, int, int, int, cudaStream_t);
 cudaError_t launch_lora_fwd(const float*, const float*, const float*, const float*, const float*, float*, float*, long long,
                             int, int, float, float, const unsigned long long*, int, cudaStream_t);
-cudaError_t launch_lora_bwd(const float*, const float*, const float*, const float*, const float*, float*, float*, long long,
-                            int, int, float, float, const unsigned long long*, int, cudaStream_t);
+cudaError_t launch_lora_bwd(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
+                            long long, int, int, float, float, const unsigned long long*, int, cudaStream_t);
 cudaError_t launch_attention_fwd(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, float, cudaStream_t);
 cudaError_t launch_decode(const float*, int, int, int, double, double, int*, double*, float*, cudaStream_t);
 cudaError_t launch_im2col(const void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
-cudaError_t launch_col2im(const void*, const float*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
-cudaError_t launch_dwconv3x3(const void*, const float*, const float*, const void*, void*, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_col2im(const void*, const float*, void*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
+cudaError_t launch_dwconv3x3(const void*, const float*, const float*, const void*, void*, int, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_dwconv3x3_wgrad(const void*, const void*, float*, int, int, int, int, cudaStream_t);
-cudaError_t launch_bn_stats(const void*, double*, long long, int, cudaStream_t);
+cudaError_t launch_bn_stats(const void*, int, double*, long long, int, cudaStream_t);
 cudaError_t launch_bn_finalize(double*, const float*, const float*, float*, float*, float*, float*, float*, float*, int,
                                double, float, float, cudaStream_t);
 cudaError_t launch_bn_fold_eval(const float*, const float*, const float*, const float*, const float*, float*, float*, int,
                                 float, cudaStream_t);
-cudaError_t launch_bn_apply(const void*, const float*, const float*, const void*, const void*, void*, long long, int, int,
-                            int, cudaStream_t);
-cudaError_t launch_bn_bwd_reduce(const void*, const void*, const void*, const float*, const float*, const float*,
+cudaError_t launch_bn_apply(const void*, int, const float*, const float*, const void*, const void*, void*, long long, int,
+                            int, int, cudaStream_t);
+cudaError_t launch_bn_bwd_reduce(const void*, const void*, int, const void*, const float*, const float*, const float*,
                                  const float*, double*, long long, int, int, int, cudaStream_t);
-cudaError_t launch_bn_bwd_apply(const void*, const void*, const void*, const float*, const float*, const float*,
+cudaError_t launch_bn_bwd_apply(const void*, const void*, int, const void*, const float*, const float*, const float*,
                                 const float*, const float*, const double*, void*, void*, float*, float*, long long, int, int,
                                 int, int, int, int, cudaStream_t);
 cudaError_t launch_avgpool2(const float*, float*, long long, int, int, cudaStream_t);
@@ -45,6 +45,7 @@ cudaError_t launch_sgemm_small(const float*, long long, long long, const float*,
                                int, int, int, const float*, int, const float*, long long, float, const unsigned long long*, int,
                                cudaStream_t);
 cudaError_t launch_colsum(const void*, int, float*, long long, int, long long, cudaStream_t);
+cudaError_t launch_relu_mask(const float*, const float*, float*, long long, float, cudaStream_t);
 }  // namespace dp
 
 using namespace dp;
@@ -88,11 +89,11 @@ extern "C" int dp_lora_fwd(const float* y, const float* A, const float* B, const
                     "dp_lora_fwd");
 }
 extern "C" int dp_lora_bwd(const float* g, const float* y, const float* u_saved, const float* B, const float* lambda1,
-                           float* dA, float* dB, long long rows, int D, int R, float scaling, float p_drop,
+                           float* dA, float* dB, float* gu_ws, long long rows, int D, int R, float scaling, float p_drop,
                            const unsigned long long* seed, void* stream) {
-  if (!g || !y || !u_saved || !B || !lambda1 || !dA || !dB) return set_error(-1, "dp_lora_bwd: null pointer");
+  if (!g || !y || !u_saved || !B || !lambda1 || !dA || !dB || !gu_ws) return set_error(-1, "dp_lora_bwd: null pointer");
   if (R != 4 && R != 8 && R != 16) return set_error(-2, "dp_lora_bwd: rank %d not in {4,8,16}", R);
-  return cuda_error(launch_lora_bwd(g, y, u_saved, B, lambda1, dA, dB, rows, D, R, scaling, p_drop, seed, sm_count(), ST),
+  return cuda_error(launch_lora_bwd(g, y, u_saved, B, lambda1, dA, dB, gu_ws, rows, D, R, scaling, p_drop, seed, sm_count(), ST),
                     "dp_lora_bwd");
 }
 extern "C" int dp_attention_fwd(const void* qkv, void* ctx, int B, int T, int heads, float scale, void* stream) {
@@ -114,23 +115,23 @@ extern "C" int dp_im2col(const void* in, void* col, int NB, int IH, int IW, int 
   if (!in || !col || C % 8) return set_error(-1, "dp_im2col: bad args");
   return cuda_error(launch_im2col(in, col, NB, IH, IW, C, OH, OW, KH, KW, stride, pad, ST), "dp_im2col");
 }
-extern "C" int dp_col2im(const void* col, const float* bias, void* big, int NB, int SH, int SW, int C, int BH, int BW,
-                         int KH, int KW, int stride, int pad, void* stream) {
+extern "C" int dp_col2im(const void* col, const float* bias, void* big, int big_f32, int NB, int SH, int SW, int C, int BH,
+                         int BW, int KH, int KW, int stride, int pad, void* stream) {
   if (!col || !big || C % 8) return set_error(-1, "dp_col2im: bad args");
-  return cuda_error(launch_col2im(col, bias, big, NB, SH, SW, C, BH, BW, KH, KW, stride, pad, ST), "dp_col2im");
+  return cuda_error(launch_col2im(col, bias, big, big_f32, NB, SH, SW, C, BH, BW, KH, KW, stride, pad, ST), "dp_col2im");
 }
-extern "C" int dp_dwconv3x3(const void* in, const float* w, const float* bias, const void* add, void* out, int NB, int H,
-                            int W, int C, int flip, void* stream) {
+extern "C" int dp_dwconv3x3(const void* in, const float* w, const float* bias, const void* add, void* out, int out_f32,
+                            int NB, int H, int W, int C, int flip, void* stream) {
   if (!in || !w || !out || C % 8) return set_error(-1, "dp_dwconv3x3: bad args");
-  return cuda_error(launch_dwconv3x3(in, w, bias, add, out, NB, H, W, C, flip, ST), "dp_dwconv3x3");
+  return cuda_error(launch_dwconv3x3(in, w, bias, add, out, out_f32, NB, H, W, C, flip, ST), "dp_dwconv3x3");
 }
 extern "C" int dp_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, int NB, int H, int W, int C, void* stream) {
   if (!in || !dout || !dw) return set_error(-1, "dp_dwconv3x3_wgrad: bad args");
   return cuda_error(launch_dwconv3x3_wgrad(in, dout, dw, NB, H, W, C, ST), "dp_dwconv3x3_wgrad");
 }
-extern "C" int dp_bn_stats(const void* raw, double* sums, long long P, int C, void* stream) {
-  if (!raw || !sums || C % 2) return set_error(-1, "dp_bn_stats: bad args");
-  return cuda_error(launch_bn_stats(raw, sums, P, C, ST), "dp_bn_stats");
+extern "C" int dp_bn_stats(const void* raw, int raw_f32, double* sums, long long P, int C, void* stream) {
+  if (!raw || !sums || C % 8) return set_error(-1, "dp_bn_stats: bad args");
+  return cuda_error(launch_bn_stats(raw, raw_f32, sums, P, C, ST), "dp_bn_stats");
 }
 extern "C" int dp_bn_finalize(double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,
                               float* shift, float* mean, float* invstd, int C, double count, float eps, float momentum,
@@ -144,25 +145,26 @@ extern "C" int dp_bn_fold_eval(const float* gamma, const float* beta, const floa
   if (!gamma || !beta || !rm || !rv || !scale || !shift) return set_error(-1, "dp_bn_fold_eval: bad args");
   return cuda_error(launch_bn_fold_eval(gamma, beta, rm, rv, conv_bias, scale, shift, C, eps, ST), "dp_bn_fold_eval");
 }
-extern "C" int dp_bn_apply(const void* raw, const float* scale, const float* shift, const void* add1, const void* add2,
-                           void* out, long long P, int C, int relu, int mode, void* stream) {
+extern "C" int dp_bn_apply(const void* raw, int raw_f32, const float* scale, const float* shift, const void* add1,
+                           const void* add2, void* out, long long P, int C, int relu, int mode, void* stream) {
   if (!raw || !scale || !shift || !out || C % 8) return set_error(-1, "dp_bn_apply: bad args");
   if (mode == 1 && !add1) return set_error(-2, "dp_bn_apply: mode 1 needs add1");
-  return cuda_error(launch_bn_apply(raw, scale, shift, add1, add2, out, P, C, relu, mode, ST), "dp_bn_apply");
+  return cuda_error(launch_bn_apply(raw, raw_f32, scale, shift, add1, add2, out, P, C, relu, mode, ST), "dp_bn_apply");
 }
-extern "C" int dp_bn_bwd_reduce(const void* dout, const void* raw, const void* add1, const float* scale,
+extern "C" int dp_bn_bwd_reduce(const void* dout, const void* raw, int raw_f32, const void* add1, const float* scale,
                                 const float* shift, const float* mean, const float* invstd, double* sums, long long P,
                                 int C, int relu, int mode, void* stream) {
   if (!dout || !raw || !scale || !shift || !mean || !invstd || !sums || C % 2) return set_error(-1, "dp_bn_bwd_reduce: bad args");
-  return cuda_error(launch_bn_bwd_reduce(dout, raw, add1, scale, shift, mean, invstd, sums, P, C, relu, mode, ST),
+  return cuda_error(launch_bn_bwd_reduce(dout, raw, raw_f32, add1, scale, shift, mean, invstd, sums, P, C, relu, mode, ST),
                     "dp_bn_bwd_reduce");
 }
-extern "C" int dp_bn_bwd_apply(const void* dout, const void* raw, const void* add1, const float* gamma, const float* scale,
+extern "C" int dp_bn_bwd_apply(const void* dout, const void* raw, int raw_f32, const void* add1, const float* gamma,
+                               const float* scale,
                                const float* shift, const float* mean, const float* invstd, const double* sums, void* draw,
                                void* dres, float* dgamma, float* dbeta, long long P, int C, int relu, int mode,
                                int eval_mode, int shuffle_oh, int shuffle_ow, void* stream) {
   if (!dout || !raw || !scale || !shift || !draw || C % 8) return set_error(-1, "dp_bn_bwd_apply: bad args");
-  return cuda_error(launch_bn_bwd_apply(dout, raw, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta,
+  return cuda_error(launch_bn_bwd_apply(dout, raw, raw_f32, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta,
                                         P, C, relu, mode, eval_mode, shuffle_oh, shuffle_ow, ST),
                     "dp_bn_bwd_apply");
 }
@@ -194,4 +196,8 @@ extern "C" int dp_sgemm_small(const float* A, long long sa_m, long long sa_k, co
 extern "C" int dp_colsum(const void* x, int is_bf16, float* out, long long P, int C, long long ld, void* stream) {
   if (!x || !out) return set_error(-1, "dp_colsum: bad args");
   return cuda_error(launch_colsum(x, is_bf16, out, P, C, ld, ST), "dp_colsum");
+}
+extern "C" int dp_relu_mask(const float* d, const float* ref, float* out, long long n, float keep_scale, void* stream) {
+  if (!d || !ref || !out) return set_error(-1, "dp_relu_mask: bad args");
+  return cuda_error(launch_relu_mask(d, ref, out, n, keep_scale, ST), "dp_relu_mask");
 }

@@ -29,6 +29,8 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   t.w = pack_bf16x2(f[6], f[7]);
   return t;
 }
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]);
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]);
 inline unsigned grid_for(long long n, int block, int max_blocks = 148 * 16) {
   long long g = (n + block - 1) / block;
   if (g > max_blocks) g = max_blocks;
@@ -59,8 +61,9 @@ __global__ void __launch_bounds__(256) im2col_kernel(const uint4* __restrict__ i
 // col2im (gather form): big[b,y,x,c] = bias[c] + sum_{ky,kx} col[(b,sy,sx), (ky*KW+kx)*C + c]
 // over taps with y = sy*stride - pad + ky, x = sx*stride - pad + kx, (sy,sx) inside the small SHxSW grid.
 // Forward of ConvTranspose2d (small = input grid) and input-gradient of a strided Conv2d (small = output grid).
+template <typename OutT>
 __global__ void __launch_bounds__(256) col2im_kernel(const uint4* __restrict__ col, const float* __restrict__ bias,
-                                                     uint4* __restrict__ big, int NB, int SH, int SW, int C8, int BH, int BW,
+                                                     OutT* __restrict__ big, int NB, int SH, int SW, int C8, int BH, int BW,
                                                      int KH, int KW, int stride, int pad) {
   const long long total = (long long)NB * BH * BW * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -89,15 +92,16 @@ __global__ void __launch_bounds__(256) col2im_kernel(const uint4* __restrict__ c
         for (int j = 0; j < 8; ++j) acc[j] += f[j];
       }
     }
-    big[i] = pack8(acc);
+    store8(big + i * 8, acc);
   }
 }
 
 // depthwise 3x3, pad 1 (HourglassModule.depthwise_conv[0], pose_heads.py:219).  w fp32 [C,1,3,3].
 // flip = 1 gives the input-gradient (correlation with the flipped kernel).
+template <typename OutT>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const uint4* __restrict__ in, const float* __restrict__ w,
                                                         const float* __restrict__ bias, const uint4* __restrict__ add,
-                                                        uint4* __restrict__ out, int NB, int H, int W, int C8, int flip) {
+                                                        OutT* __restrict__ out, int NB, int H, int W, int C8, int flip) {
   const long long total = (long long)NB * H * W * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = int(i % C8);
@@ -130,7 +134,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const uint4* __restrict_
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += f[j];
     }
-    out[i] = pack8(acc);
+    store8(out + i * 8, acc);
   }
 }
 
@@ -180,25 +184,71 @@ __global__ void __launch_bounds__(256) dwconv3x3_wgrad_kernel(const __nv_bfloat1
 }
 
 // ------------------------------------------------------------------------------------------------
-// BatchNorm statistics: per-channel sum and sum of squares of raw bf16 [P, C] (fp32 partials per block,
-// fp64 atomics across blocks).  blockDim.x = C/2 (one bf16 pair per thread).
-__global__ void bn_stats_kernel(const __nv_bfloat162* __restrict__ raw, double* __restrict__ sums, long long P, int C2,
-                                int rows_per_block) {
-  const int c = threadIdx.x + blockIdx.y * blockDim.x;
-  if (c >= C2) return;
-  const long long p0 = (long long)blockIdx.x * rows_per_block;
-  const long long p1 = min(p0 + rows_per_block, P);
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  for (long long p = p0; p < p1; ++p) {
-    const __nv_bfloat162 v = raw[p * C2 + c];
-    const float a = __low2float(v), b = __high2float(v);
-    s0 += a; s1 += b;
-    q0 += a * a; q1 += b * b;
+// Train-mode BatchNorm over channels-last [P, C] tensors.  The pre-BN conv output ("raw") may be stored
+// in fp32 (training: bf16 rounding of raw is amplified by |mean|/std through the normalisation) or bf16.
+// Thread mapping for all four kernels: a thread owns ONE group of 8 consecutive channels for the whole
+// kernel (per-channel parameters live in registers) and strides over rows; 16/32-byte vector accesses.
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&f)[8]);
+template <> __device__ __forceinline__ void load8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  unpack8(__ldg(reinterpret_cast<const uint4*>(p)), f);
+}
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+__device__ __forceinline__ void store8(__nv_bfloat16* p, const float (&f)[8]) { *reinterpret_cast<uint4*>(p) = pack8(f); }
+__device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
+  reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
+  reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
+}
+
+constexpr int kBnThreads = 256;
+
+// block-level reduction of per-thread partial sums that share a channel group, then fp64 atomics
+__device__ __forceinline__ void bn_block_reduce_atomic(float (&s)[8], float (&q)[8], int c8, int C8, int C,
+                                                       double* __restrict__ sums) {
+  __shared__ float red[kBnThreads][17];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[tid][j] = s[j];
+    red[tid][8 + j] = q[j];
   }
-  atomicAdd(sums + 2 * c, double(s0));
-  atomicAdd(sums + 2 * c + 1, double(s1));
-  atomicAdd(sums + 2 * C2 + 2 * c, double(q0));
-  atomicAdd(sums + 2 * C2 + 2 * c + 1, double(q1));
+  __syncthreads();
+  if (tid < C8) {
+    float ts[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) ts[j] = 0.f;
+    for (int t = tid; t < kBnThreads; t += C8)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) ts[j] += red[t][j];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      atomicAdd(sums + c8 * 8 + j, double(ts[j]));
+      atomicAdd(sums + C + c8 * 8 + j, double(ts[8 + j]));
+    }
+  }
+}
+
+template <typename RawT>
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const RawT* __restrict__ raw, double* __restrict__ sums,
+                                                              long long P, int C8) {
+  const int C = C8 * 8;
+  const int c8 = threadIdx.x % C8;
+  const int rpb = kBnThreads / C8;
+  float s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
+  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C8; row < P; row += (long long)gridDim.x * rpb) {
+    float f[8];
+    load8(raw + row * C + c8 * 8, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      s[j] += f[j];
+      q[j] += f[j] * f[j];
+    }
+  }
+  bn_block_reduce_atomic(s, q, c8, C8, C, sums);
 }
 
 // finalize: batch mean / biased var -> scale, shift (y = raw*scale + shift), saved mean / invstd,
@@ -241,19 +291,30 @@ __global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float
 
 // apply: y = raw*scale + shift;  mode 0: out = relu?(y) + add1 + add2      (HourglassModule 3-way sum, :285)
 //                                 mode 1: out = relu(y + add1)              (bottleneck residual, :277-278)
-__global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__ raw, const float* __restrict__ scale,
-                                                       const float* __restrict__ shift, const uint4* __restrict__ add1,
-                                                       const uint4* __restrict__ add2, uint4* __restrict__ out,
-                                                       long long P, int C8, int relu, int mode) {
-  const long long total = P * C8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = int(i % C8) * 8;
-    float f[8], a[8];
-    unpack8(__ldg(raw + i), f);
+template <typename RawT>
+__global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const RawT* __restrict__ raw, const float* __restrict__ scale,
+                                                              const float* __restrict__ shift,
+                                                              const __nv_bfloat16* __restrict__ add1,
+                                                              const __nv_bfloat16* __restrict__ add2,
+                                                              __nv_bfloat16* __restrict__ out, long long P, int C8, int relu,
+                                                              int mode) {
+  const int C = C8 * 8;
+  const int c8 = threadIdx.x % C8;
+  const int rpb = kBnThreads / C8;
+  float sc[8], sh[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = f[j] * __ldg(scale + c + j) + __ldg(shift + c + j);
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale + c8 * 8 + j);
+    sh[j] = __ldg(shift + c8 * 8 + j);
+  }
+  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C8; row < P; row += (long long)gridDim.x * rpb) {
+    const long long o = row * C + c8 * 8;
+    float f[8], a[8];
+    load8(raw + o, f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = f[j] * sc[j] + sh[j];
     if (mode == 1) {
-      unpack8(__ldg(add1 + i), a);
+      load8(add1 + o, a);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j] + a[j], 0.f);
     } else {
@@ -262,108 +323,115 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const uint4* __restrict__
         for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
       }
       if (add1 != nullptr) {
-        unpack8(__ldg(add1 + i), a);
+        load8(add1 + o, a);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] += a[j];
       }
       if (add2 != nullptr) {
-        unpack8(__ldg(add2 + i), a);
+        load8(add2 + o, a);
 #pragma unroll
         for (int j = 0; j < 8; ++j) f[j] += a[j];
       }
     }
-    out[i] = pack8(f);
+    store8(out + o, f);
   }
 }
 
 // BatchNorm backward, pass 1: with y = raw*scale+shift, xhat = (raw-mean)*invstd,
 //   dy = dout * [y > 0]            (mode 0, relu)      | dy = dout * [y + add1 > 0]   (mode 1)
 //   sums[c] += dy ; sums[C + c] += dy * xhat
-// blockDim.x = C/2.
-__global__ void bn_bwd_reduce_kernel(const __nv_bfloat162* __restrict__ dout, const __nv_bfloat162* __restrict__ raw,
-                                     const __nv_bfloat162* __restrict__ add1, const float* __restrict__ scale,
-                                     const float* __restrict__ shift, const float* __restrict__ mean,
-                                     const float* __restrict__ invstd, double* __restrict__ sums, long long P, int C2,
-                                     int rows_per_block, int relu, int mode) {
-  const int c = threadIdx.x + blockIdx.y * blockDim.x;
-  if (c >= C2) return;
-  const float sc0 = scale[2 * c], sc1 = scale[2 * c + 1], sh0 = shift[2 * c], sh1 = shift[2 * c + 1];
-  const float m0 = mean[2 * c], m1 = mean[2 * c + 1], i0 = invstd[2 * c], i1 = invstd[2 * c + 1];
-  const long long p0 = (long long)blockIdx.x * rows_per_block;
-  const long long p1 = min(p0 + rows_per_block, P);
-  float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
-  for (long long p = p0; p < p1; ++p) {
-    const __nv_bfloat162 r = raw[p * C2 + c];
-    const __nv_bfloat162 g = dout[p * C2 + c];
-    const float ra = __low2float(r), rb = __high2float(r);
-    float ga = __low2float(g), gb = __high2float(g);
-    float ya = ra * sc0 + sh0, yb = rb * sc1 + sh1;
-    if (mode == 1) {
-      const __nv_bfloat162 a = add1[p * C2 + c];
-      ya += __low2float(a);
-      yb += __high2float(a);
-    }
-    if (relu || mode == 1) {
-      ga = ya > 0.f ? ga : 0.f;
-      gb = yb > 0.f ? gb : 0.f;
-    }
-    s0 += ga; s1 += gb;
-    q0 += ga * (ra - m0) * i0;
-    q1 += gb * (rb - m1) * i1;
+template <typename RawT>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
+    const __nv_bfloat16* __restrict__ dout, const RawT* __restrict__ raw, const __nv_bfloat16* __restrict__ add1,
+    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
+    const float* __restrict__ invstd, double* __restrict__ sums, long long P, int C8, int relu, int mode) {
+  const int C = C8 * 8;
+  const int c8 = threadIdx.x % C8;
+  const int rpb = kBnThreads / C8;
+  float sc[8], sh[8], mu[8], is[8], s[8], q[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = __ldg(scale + c8 * 8 + j);
+    sh[j] = __ldg(shift + c8 * 8 + j);
+    mu[j] = __ldg(mean + c8 * 8 + j);
+    is[j] = __ldg(invstd + c8 * 8 + j);
+    s[j] = q[j] = 0.f;
   }
-  atomicAdd(sums + 2 * c, double(s0));
-  atomicAdd(sums + 2 * c + 1, double(s1));
-  atomicAdd(sums + 2 * C2 + 2 * c, double(q0));
-  atomicAdd(sums + 2 * C2 + 2 * c + 1, double(q1));
+  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C8; row < P; row += (long long)gridDim.x * rpb) {
+    const long long o = row * C + c8 * 8;
+    float r[8], g[8], a[8];
+    load8(raw + o, r);
+    load8(dout + o, g);
+    if (mode == 1) load8(add1 + o, a);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float y = r[j] * sc[j] + sh[j];
+      if (mode == 1) y += a[j];
+      const float gj = ((relu || mode == 1) && !(y > 0.f)) ? 0.f : g[j];
+      s[j] += gj;
+      q[j] += gj * (r[j] - mu[j]) * is[j];
+    }
+  }
+  bn_block_reduce_atomic(s, q, c8, C8, C, sums);
 }
 
 // pass 2: draw = gamma*invstd * (dy - S1/P - xhat*S2/P)  (train)   |   draw = dy * scale (eval_mode)
 // Also emits dgamma = S2, dbeta = S1 (block 0) and, for mode 1, the masked gradient of the residual branch.
-// shuffle_cout > 0: write draw in the un-shuffled [P/4, 4*Cout] "col" layout of a k2 s2 transposed conv
+// shuffle_oh > 0: write draw in the un-shuffled [P/4, 4*Cout] "col" layout of a k2 s2 transposed conv
 // (row = input pixel, column = tap*Cout + co), the operand layout of its weight / input gradients.
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const uint4* __restrict__ dout, const uint4* __restrict__ raw,
-                                                           const uint4* __restrict__ add1, const float* __restrict__ gamma,
-                                                           const float* __restrict__ scale, const float* __restrict__ shift,
-                                                           const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                           const double* __restrict__ sums, uint4* __restrict__ draw,
-                                                           uint4* __restrict__ dres, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, long long P, int C8, int relu,
-                                                           int mode, int eval_mode, int shuffle_oh, int shuffle_ow) {
+template <typename RawT>
+__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
+    const __nv_bfloat16* __restrict__ dout, const RawT* __restrict__ raw, const __nv_bfloat16* __restrict__ add1,
+    const float* __restrict__ gamma, const float* __restrict__ scale, const float* __restrict__ shift,
+    const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ sums,
+    __nv_bfloat16* __restrict__ draw, __nv_bfloat16* __restrict__ dres, float* __restrict__ dgamma,
+    float* __restrict__ dbeta, long long P, int C8, int relu, int mode, int eval_mode, int shuffle_oh, int shuffle_ow) {
   const int C = C8 * 8;
-  const long long total = P * C8;
+  const int c8 = threadIdx.x % C8;
+  const int rpb = kBnThreads / C8;
   const float invP = 1.0f / float(P);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = int(i % C8) * 8;
-    float r[8], g[8], a[8], o[8];
-    unpack8(__ldg(raw + i), r);
-    unpack8(__ldg(dout + i), g);
-    if (mode == 1) unpack8(__ldg(add1 + i), a);
+  float sc[8], sh[8], mu[8], is[8], gi[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = c8 * 8 + j;
+    sc[j] = __ldg(scale + c);
+    sh[j] = __ldg(shift + c);
+    if (!eval_mode) {
+      mu[j] = __ldg(mean + c);
+      is[j] = __ldg(invstd + c);
+      gi[j] = __ldg(gamma + c) * is[j];
+      s1[j] = float(sums[c]) * invP;
+      s2[j] = float(sums[C + c]) * invP;
+    } else {
+      mu[j] = is[j] = gi[j] = s1[j] = s2[j] = 0.f;
+    }
+  }
+  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C8; row < P; row += (long long)gridDim.x * rpb) {
+    const long long o = row * C + c8 * 8;
+    float r[8], g[8], a[8], ov[8];
+    load8(raw + o, r);
+    load8(dout + o, g);
+    if (mode == 1) load8(add1 + o, a);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float y = r[j] * __ldg(scale + c + j) + __ldg(shift + c + j);
+      float y = r[j] * sc[j] + sh[j];
       if (mode == 1) y += a[j];
       if ((relu || mode == 1) && !(y > 0.f)) g[j] = 0.f;
-      if (eval_mode) {
-        o[j] = g[j] * __ldg(scale + c + j);
-      } else {
-        const float xhat = (r[j] - __ldg(mean + c + j)) * __ldg(invstd + c + j);
-        const float s1 = float(sums[c + j]) * invP, s2 = float(sums[C + c + j]) * invP;
-        o[j] = __ldg(gamma + c + j) * __ldg(invstd + c + j) * (g[j] - s1 - xhat * s2);
-      }
+      ov[j] = eval_mode ? g[j] * sc[j] : gi[j] * (g[j] - s1[j] - (r[j] - mu[j]) * is[j] * s2[j]);
     }
-    long long oi = i;
+    long long oo = o;
     if (shuffle_oh > 0) {
-      // i indexes the shuffled NHWC output [NB, 2*ih, 2*iw, C]; destination is [NB*ih*iw, 4*C]
-      long long p = i / C8;
+      // row indexes the shuffled NHWC output [NB, 2*ih, 2*iw, C]; destination is [NB*ih*iw, 4*C]
+      long long p = row;
       const int x = int(p % shuffle_ow); p /= shuffle_ow;
       const int y = int(p % shuffle_oh);
       const long long b = p / shuffle_oh;
       const int ih = shuffle_oh / 2, iw = shuffle_ow / 2;
       const int tap = (y & 1) * 2 + (x & 1);
-      oi = (((b * ih + (y >> 1)) * iw + (x >> 1)) * 4 + tap) * C8 + (i % C8);
+      oo = ((((b * ih + (y >> 1)) * iw + (x >> 1)) * 4 + tap) * C8 + c8) * 8;
     }
-    draw[oi] = pack8(o);
-    if (dres != nullptr) dres[i] = pack8(g);
+    store8(draw + oo, ov);
+    if (dres != nullptr) store8(dres + o, g);
   }
   if (blockIdx.x == 0 && dgamma != nullptr) {
     for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -443,50 +511,61 @@ __device__ __forceinline__ uint32_t mix32h(uint64_t z) {
   return uint32_t((z ^ (z >> 31)) >> 16);
 }
 
-__global__ void __launch_bounds__(256) sgemm_small_kernel(const float* __restrict__ A, long long sa_m, long long sa_k,
+__global__ void __launch_bounds__(128) sgemm_small_kernel(const float* __restrict__ A, long long sa_m, long long sa_k,
                                                           const float* __restrict__ Bm, long long sb_k, long long sb_n,
                                                           float* __restrict__ Cc, long long ldc, int M, int N, int K,
                                                           const float* __restrict__ bias, int relu,
                                                           const float* __restrict__ mask_ref, long long ld_ref,
-                                                          float p_drop, const unsigned long long* __restrict__ seed_ptr, int accumulate) {
+                                                          float p_drop, const unsigned long long* __restrict__ seed_ptr,
+                                                          int accumulate) {
+  // 32x32 output tile, 32-deep k-steps, 128 threads x (2 rows x 4 cols); loads are coalesced along whichever
+  // operand dimension has unit stride
   const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
-  __shared__ float As[16][64 + 1];
-  __shared__ float Bs[16][64 + 1];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
-  float acc[4][4];
+  __shared__ float As[32][33];
+  __shared__ float Bs[32][33];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  float acc[2][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += 16) {
-    for (int i = threadIdx.x; i < 16 * 64; i += 256) {
-      const int kk = i & 15, mm = i >> 4;
-      const int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < M && k < K) ? A[m * sa_m + k * sa_k] : 0.f;
-      const int n = n0 + mm;
-      Bs[kk][mm] = (n < N && k < K) ? Bm[k * sb_k + n * sb_n] : 0.f;
+  const bool a_kfast = (sa_k == 1), b_kfast = (sb_k == 1);
+  for (int k0 = 0; k0 < K; k0 += 32) {
+#pragma unroll
+    for (int i = threadIdx.x; i < 32 * 32; i += 128) {
+      const int lo = i & 31, hi = i >> 5;
+      {
+        const int kk = a_kfast ? lo : hi, mm = a_kfast ? hi : lo;
+        const int m = m0 + mm, k = k0 + kk;
+        As[kk][mm] = (m < M && k < K) ? __ldg(A + m * sa_m + k * sa_k) : 0.f;
+      }
+      {
+        const int kk = b_kfast ? lo : hi, nn = b_kfast ? hi : lo;
+        const int n = n0 + nn, k = k0 + kk;
+        Bs[kk][nn] = (n < N && k < K) ? __ldg(Bm + k * sb_k + n * sb_n) : 0.f;
+      }
     }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < 16; ++kk) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+    for (int kk = 0; kk < 32; ++kk) {
+      const float a0 = As[kk][ty * 2], a1 = As[kk][ty * 2 + 1];
+      float b[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] += a[i] * b[j];
+      for (int j = 0; j < 4; ++j) {
+        acc[0][j] += a0 * b[j];
+        acc[1][j] += a1 * b[j];
+      }
     }
     __syncthreads();
   }
   const uint32_t thresh = p_drop > 0.f ? uint32_t(fminf(p_drop, 0.999999f) * 4294967296.0f) : 0u;
   const float keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + ty * 2 + i;
     if (m >= M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -501,6 +580,13 @@ __global__ void __launch_bounds__(256) sgemm_small_kernel(const float* __restric
       Cc[m * ldc + n] = v;
     }
   }
+}
+
+// out = (ref > 0) ? d * keep_scale : 0      (gradient through ReLU [+ inverted dropout] given the saved output)
+__global__ void relu_mask_kernel(const float* __restrict__ d, const float* __restrict__ ref, float* __restrict__ out,
+                                 long long n, float keep_scale) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = ref[i] > 0.f ? d[i] * keep_scale : 0.f;
 }
 
 // column sums: out[c] (+)= sum_p x[p, c]   (bias gradients).  x fp32 or bf16.
@@ -529,20 +615,31 @@ cudaError_t launch_im2col(const void* in, void* col, int NB, int IH, int IW, int
                                                      IH, IW, C / 8, OH, OW, KH, KW, stride, pad);
   return cudaGetLastError();
 }
-cudaError_t launch_col2im(const void* col, const float* bias, void* big, int NB, int SH, int SW, int C, int BH, int BW,
-                          int KH, int KW, int stride, int pad, cudaStream_t s) {
+cudaError_t launch_col2im(const void* col, const float* bias, void* big, int big_f32, int NB, int SH, int SW, int C, int BH,
+                          int BW, int KH, int KW, int stride, int pad, cudaStream_t s) {
   const long long total = (long long)NB * BH * BW * (C / 8);
-  col2im_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(col), bias,
-                                                     reinterpret_cast<uint4*>(big), NB, SH, SW, C / 8, BH, BW, KH, KW,
-                                                     stride, pad);
+  if (big_f32)
+    col2im_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(col), bias,
+                                                              reinterpret_cast<float*>(big), NB, SH, SW, C / 8, BH, BW, KH,
+                                                              KW, stride, pad);
+  else
+    col2im_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(col), bias,
+                                                                      reinterpret_cast<__nv_bfloat16*>(big), NB, SH, SW,
+                                                                      C / 8, BH, BW, KH, KW, stride, pad);
   return cudaGetLastError();
 }
-cudaError_t launch_dwconv3x3(const void* in, const float* w, const float* bias, const void* add, void* out, int NB, int H,
-                             int W, int C, int flip, cudaStream_t s) {
+cudaError_t launch_dwconv3x3(const void* in, const float* w, const float* bias, const void* add, void* out, int out_f32,
+                             int NB, int H, int W, int C, int flip, cudaStream_t s) {
   const long long total = (long long)NB * H * W * (C / 8);
-  dwconv3x3_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), w, bias,
-                                                        reinterpret_cast<const uint4*>(add),
-                                                        reinterpret_cast<uint4*>(out), NB, H, W, C / 8, flip);
+  if (out_f32)
+    dwconv3x3_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), w, bias,
+                                                                 reinterpret_cast<const uint4*>(add),
+                                                                 reinterpret_cast<float*>(out), NB, H, W, C / 8, flip);
+  else
+    dwconv3x3_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), w, bias,
+                                                                         reinterpret_cast<const uint4*>(add),
+                                                                         reinterpret_cast<__nv_bfloat16*>(out), NB, H, W,
+                                                                         C / 8, flip);
   return cudaGetLastError();
 }
 cudaError_t launch_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, int NB, int H, int W, int C,
@@ -555,19 +652,21 @@ cudaError_t launch_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, 
                                               reinterpret_cast<const __nv_bfloat16*>(dout), dw, NB, H, W, C, rpb);
   return cudaGetLastError();
 }
-static void stats_grid(long long P, int C2, dim3* grid, int* block, int* rpb) {
-  *block = C2 > 256 ? 256 : C2;
-  const int gy = (C2 + *block - 1) / *block;
-  int r = int((P + 591) / 592);
-  if (r < 16) r = 16;
-  *rpb = r;
-  *grid = dim3(unsigned((P + r - 1) / r), unsigned(gy));
+static unsigned bn_grid(long long P, int C8) {
+  const int rpb = kBnThreads / C8;
+  long long g = (P + rpb - 1) / rpb;
+  const long long cap = 148 * 4;
+  if (g > cap) g = cap;
+  return unsigned(g < 1 ? 1 : g);
 }
-cudaError_t launch_bn_stats(const void* raw, double* sums, long long P, int C, cudaStream_t s) {
-  dim3 grid;
-  int block, rpb;
-  stats_grid(P, C / 2, &grid, &block, &rpb);
-  bn_stats_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat162*>(raw), sums, P, C / 2, rpb);
+static bool bn_c_ok(int C) { return C % 8 == 0 && kBnThreads % (C / 8) == 0 && C / 8 <= kBnThreads; }
+
+cudaError_t launch_bn_stats(const void* raw, int raw_f32, double* sums, long long P, int C, cudaStream_t s) {
+  if (!bn_c_ok(C)) return cudaErrorInvalidValue;
+  if (raw_f32)
+    bn_stats_kernel<float><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(reinterpret_cast<const float*>(raw), sums, P, C / 8);
+  else
+    bn_stats_kernel<__nv_bfloat16><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(raw), sums, P, C / 8);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_finalize(double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,
@@ -582,33 +681,43 @@ cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const flo
   bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, rm, rv, conv_bias, scale, shift, C, eps);
   return cudaGetLastError();
 }
-cudaError_t launch_bn_apply(const void* raw, const float* scale, const float* shift, const void* add1, const void* add2,
-                            void* out, long long P, int C, int relu, int mode, cudaStream_t s) {
-  bn_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, s>>>(
-      reinterpret_cast<const uint4*>(raw), scale, shift, reinterpret_cast<const uint4*>(add1),
-      reinterpret_cast<const uint4*>(add2), reinterpret_cast<uint4*>(out), P, C / 8, relu, mode);
+cudaError_t launch_bn_apply(const void* raw, int raw_f32, const float* scale, const float* shift, const void* add1,
+                            const void* add2, void* out, long long P, int C, int relu, int mode, cudaStream_t s) {
+  if (!bn_c_ok(C)) return cudaErrorInvalidValue;
+  auto a1 = reinterpret_cast<const __nv_bfloat16*>(add1);
+  auto a2 = reinterpret_cast<const __nv_bfloat16*>(add2);
+  auto o = reinterpret_cast<__nv_bfloat16*>(out);
+  if (raw_f32)
+    bn_apply_kernel<float><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(reinterpret_cast<const float*>(raw), scale, shift, a1, a2, o, P, C / 8, relu, mode);
+  else
+    bn_apply_kernel<__nv_bfloat16><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(raw), scale, shift, a1, a2, o, P, C / 8, relu, mode);
   return cudaGetLastError();
 }
-cudaError_t launch_bn_bwd_reduce(const void* dout, const void* raw, const void* add1, const float* scale,
+cudaError_t launch_bn_bwd_reduce(const void* dout, const void* raw, int raw_f32, const void* add1, const float* scale,
                                  const float* shift, const float* mean, const float* invstd, double* sums, long long P,
                                  int C, int relu, int mode, cudaStream_t s) {
-  dim3 grid;
-  int block, rpb;
-  stats_grid(P, C / 2, &grid, &block, &rpb);
-  bn_bwd_reduce_kernel<<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat162*>(dout),
-                                              reinterpret_cast<const __nv_bfloat162*>(raw),
-                                              reinterpret_cast<const __nv_bfloat162*>(add1), scale, shift, mean, invstd,
-                                              sums, P, C / 2, rpb, relu, mode);
+  if (!bn_c_ok(C)) return cudaErrorInvalidValue;
+  auto d = reinterpret_cast<const __nv_bfloat16*>(dout);
+  auto a1 = reinterpret_cast<const __nv_bfloat16*>(add1);
+  if (raw_f32)
+    bn_bwd_reduce_kernel<float><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(d, reinterpret_cast<const float*>(raw), a1, scale, shift, mean, invstd, sums, P, C / 8, relu, mode);
+  else
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, mean, invstd, sums, P, C / 8, relu, mode);
   return cudaGetLastError();
 }
-cudaError_t launch_bn_bwd_apply(const void* dout, const void* raw, const void* add1, const float* gamma,
+cudaError_t launch_bn_bwd_apply(const void* dout, const void* raw, int raw_f32, const void* add1, const float* gamma,
                                 const float* scale, const float* shift, const float* mean, const float* invstd,
                                 const double* sums, void* draw, void* dres, float* dgamma, float* dbeta, long long P, int C,
                                 int relu, int mode, int eval_mode, int shuffle_oh, int shuffle_ow, cudaStream_t s) {
-  bn_bwd_apply_kernel<<<grid_for(P * (C / 8), 256), 256, 0, s>>>(
-      reinterpret_cast<const uint4*>(dout), reinterpret_cast<const uint4*>(raw), reinterpret_cast<const uint4*>(add1),
-      gamma, scale, shift, mean, invstd, sums, reinterpret_cast<uint4*>(draw), reinterpret_cast<uint4*>(dres), dgamma,
-      dbeta, P, C / 8, relu, mode, eval_mode, shuffle_oh, shuffle_ow);
+  if (!bn_c_ok(C)) return cudaErrorInvalidValue;
+  auto d = reinterpret_cast<const __nv_bfloat16*>(dout);
+  auto a1 = reinterpret_cast<const __nv_bfloat16*>(add1);
+  auto dr = reinterpret_cast<__nv_bfloat16*>(draw);
+  auto ds = reinterpret_cast<__nv_bfloat16*>(dres);
+  if (raw_f32)
+    bn_bwd_apply_kernel<float><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(d, reinterpret_cast<const float*>(raw), a1, gamma, scale, shift, mean, invstd, sums, dr, ds, dgamma, dbeta, P, C / 8, relu, mode, eval_mode, shuffle_oh, shuffle_ow);
+  else
+    bn_bwd_apply_kernel<__nv_bfloat16><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, gamma, scale, shift, mean, invstd, sums, dr, ds, dgamma, dbeta, P, C / 8, relu, mode, eval_mode, shuffle_oh, shuffle_ow);
   return cudaGetLastError();
 }
 cudaError_t launch_zero_f64(double* p, int n, cudaStream_t s) {
@@ -639,9 +748,13 @@ cudaError_t launch_sgemm_small(const float* A, long long sa_m, long long sa_k, c
                                long long sb_n, float* C, long long ldc, int M, int N, int K, const float* bias, int relu,
                                const float* mask_ref, long long ld_ref, float p_drop, const unsigned long long* seed,
                                int accumulate, cudaStream_t s) {
-  dim3 grid((N + 63) / 64, (M + 63) / 64);
-  sgemm_small_kernel<<<grid, 256, 0, s>>>(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, bias, relu, mask_ref, ld_ref,
+  dim3 grid((N + 31) / 32, (M + 31) / 32);
+  sgemm_small_kernel<<<grid, 128, 0, s>>>(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, bias, relu, mask_ref, ld_ref,
                                           p_drop, seed, accumulate);
+  return cudaGetLastError();
+}
+cudaError_t launch_relu_mask(const float* d, const float* ref, float* out, long long n, float keep_scale, cudaStream_t s) {
+  relu_mask_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(d, ref, out, n, keep_scale);
   return cudaGetLastError();
 }
 cudaError_t launch_colsum(const void* x, int is_bf16, float* out, long long P, int C, long long ld, cudaStream_t s) {

@@ -316,62 +316,78 @@ __global__ void __launch_bounds__(256) lora_fwd_kernel(const float* __restrict__
 }
 
 // LoRA backward.  g = dL/dx_out [rows, D] fp32 (gradient of the residual stream after the attention
-// branch).  With gy = g * lambda1 (gradient wrt y + v*s):
-//   gv = gy * s * mask/(1-p)          [rows, D]
-//   dB[r, d] += u[row, r] * gv[row, d]
-//   gu[r]    = sum_d gv[d] * B[r, d]
-//   dA[d, r] += y[row, d] * gu[r]
+// branch).  With gv = g * lambda1 * s * mask/(1-p) (gradient wrt u B):
+//   gu[row, r] = sum_d gv[row, d] * B[r, d]                     (kernel 1, warp per row)
+//   dB[r, d]  += sum_rows u[row, r] * gv[row, d]                 (kernel 2, thread per column d)
+//   dA[d, r]  += sum_rows y[row, d] * gu[row, r]
 // (no gradient flows further: y is produced by frozen parameters from a frozen input.)
-// Each block accumulates its rows into shared-memory partials, then one atomicAdd per element.
 template <int R>
-__global__ void __launch_bounds__(256) lora_bwd_kernel(const float* __restrict__ g, const float* __restrict__ y,
-                                                       const float* __restrict__ u_saved, const float* __restrict__ Bm,
-                                                       const float* __restrict__ lambda1, float* __restrict__ dA,
-                                                       float* __restrict__ dB, long long rows, int D, float scaling,
-                                                       float p_drop, const unsigned long long* __restrict__ seed_ptr) {
+__global__ void __launch_bounds__(256) lora_bwd_gu_kernel(const float* __restrict__ g, const float* __restrict__ Bm,
+                                                          const float* __restrict__ lambda1, float* __restrict__ gu_out,
+                                                          long long rows, int D, float scaling, float p_drop,
+                                                          const unsigned long long* __restrict__ seed_ptr) {
   const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
   extern __shared__ float sm[];
-  float* sB = sm;               // [R][D]
-  float* pA = sm + R * D;       // [D][R] partial dA
-  float* pB = pA + R * D;       // [R][D] partial dB
-  for (int i = threadIdx.x; i < D * R; i += blockDim.x) {
-    sB[i] = Bm[i];
-    pA[i] = 0.f;
-    pB[i] = 0.f;
-  }
+  float* sB = sm;  // [R][D]
+  for (int i = threadIdx.x; i < D * R; i += blockDim.x) sB[i] = Bm[i];
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const uint32_t thresh = p_drop > 0.f ? uint32_t(fminf(p_drop, 0.999999f) * 4294967296.0f) : 0u;
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
-    float u[R], gu[R];
+    float gu[R];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      u[r] = u_saved[row * R + r];
-      gu[r] = 0.f;
-    }
+    for (int r = 0; r < R; ++r) gu[r] = 0.f;
     for (int d = lane; d < D; d += 32) {
       float gv = g[row * D + d] * lambda1[d] * scaling;
       if (p_drop > 0.f) gv = dropout_keep(seed, uint64_t(row) * D + d, thresh) ? gv * keep_scale : 0.f;
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        atomicAdd(&pB[r * D + d], u[r] * gv);
-        gu[r] += gv * sB[r * D + d];
-      }
+      for (int r = 0; r < R; ++r) gu[r] += gv * sB[r * D + d];
     }
 #pragma unroll
     for (int r = 0; r < R; ++r) gu[r] = warp_sum(gu[r]);
-    for (int d = lane; d < D; d += 32) {
-      const float yv = y[row * D + d];
+    if (lane < R) {
+      float mine = 0.f;
 #pragma unroll
-      for (int r = 0; r < R; ++r) atomicAdd(&pA[d * R + r], yv * gu[r]);
+      for (int r = 0; r < R; ++r) mine = (lane == r) ? gu[r] : mine;
+      gu_out[row * R + lane] = mine;
     }
   }
-  __syncthreads();
-  for (int i = threadIdx.x; i < D * R; i += blockDim.x) {
-    atomicAdd(&dA[i], pA[i]);
-    atomicAdd(&dB[i], pB[i]);
+}
+
+template <int R>
+__global__ void __launch_bounds__(256) lora_bwd_acc_kernel(const float* __restrict__ g, const float* __restrict__ y,
+                                                           const float* __restrict__ u_saved, const float* __restrict__ gu,
+                                                           const float* __restrict__ lambda1, float* __restrict__ dA,
+                                                           float* __restrict__ dB, long long rows, int D, float scaling,
+                                                           float p_drop, const unsigned long long* __restrict__ seed_ptr,
+                                                           int rows_per_block) {
+  const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
+  const int d = blockIdx.y * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const uint32_t thresh = p_drop > 0.f ? uint32_t(fminf(p_drop, 0.999999f) * 4294967296.0f) : 0u;
+  const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const float ld = lambda1[d] * scaling;
+  const long long r0 = (long long)blockIdx.x * rows_per_block;
+  const long long r1 = min(r0 + rows_per_block, rows);
+  float aB[R], aA[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) aB[r] = aA[r] = 0.f;
+  for (long long row = r0; row < r1; ++row) {
+    float gv = g[row * D + d] * ld;
+    if (p_drop > 0.f) gv = dropout_keep(seed, uint64_t(row) * D + d, thresh) ? gv * keep_scale : 0.f;
+    const float yv = y[row * D + d];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      aB[r] += __ldg(u_saved + row * R + r) * gv;
+      aA[r] += yv * __ldg(gu + row * R + r);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    atomicAdd(dB + (long long)r * D + d, aB[r]);
+    atomicAdd(dA + (long long)d * R + r, aA[r]);
   }
 }
 
@@ -395,24 +411,31 @@ cudaError_t launch_lora_fwd(const float* y, const float* A, const float* Bm, con
   return cudaGetLastError();
 }
 
-cudaError_t launch_lora_bwd(const float* g, const float* y, const float* u_saved, const float* Bm, const float* lambda1,
-                            float* dA, float* dB, long long rows, int D, int R, float scaling, float p_drop,
-                            const unsigned long long* seed, int sms, cudaStream_t s) {
-  const size_t smem = size_t(3) * D * R * sizeof(float);
-  const int grid = sms;
-  if (R == 8) {
-    cudaFuncSetAttribute(lora_bwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    lora_bwd_kernel<8><<<grid, 256, smem, s>>>(g, y, u_saved, Bm, lambda1, dA, dB, rows, D, scaling, p_drop, seed);
-  } else if (R == 4) {
-    cudaFuncSetAttribute(lora_bwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    lora_bwd_kernel<4><<<grid, 256, smem, s>>>(g, y, u_saved, Bm, lambda1, dA, dB, rows, D, scaling, p_drop, seed);
-  } else if (R == 16) {
-    cudaFuncSetAttribute(lora_bwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    lora_bwd_kernel<16><<<grid, 256, smem, s>>>(g, y, u_saved, Bm, lambda1, dA, dB, rows, D, scaling, p_drop, seed);
-  } else {
-    return cudaErrorInvalidValue;
-  }
+template <int R>
+static cudaError_t lora_bwd_t(const float* g, const float* y, const float* u_saved, const float* Bm, const float* lambda1,
+                              float* dA, float* dB, float* gu_ws, long long rows, int D, float scaling, float p_drop,
+                              const unsigned long long* seed, int sms, cudaStream_t s) {
+  const size_t smem = size_t(D) * R * sizeof(float);
+  cudaFuncSetAttribute(lora_bwd_gu_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  lora_bwd_gu_kernel<R><<<sms * 2, 256, smem, s>>>(g, Bm, lambda1, gu_ws, rows, D, scaling, p_drop, seed);
+  const int bx = 128;
+  const int gy = (D + bx - 1) / bx;
+  int gx = (sms * 4) / gy;
+  if (gx < 1) gx = 1;
+  int rpb = int((rows + gx - 1) / gx);
+  if (rpb < 8) rpb = 8;
+  gx = int((rows + rpb - 1) / rpb);
+  lora_bwd_acc_kernel<R><<<dim3(gx, gy), bx, 0, s>>>(g, y, u_saved, gu_ws, lambda1, dA, dB, rows, D, scaling, p_drop, seed, rpb);
   return cudaGetLastError();
+}
+
+cudaError_t launch_lora_bwd(const float* g, const float* y, const float* u_saved, const float* Bm, const float* lambda1,
+                            float* dA, float* dB, float* gu_ws, long long rows, int D, int R, float scaling, float p_drop,
+                            const unsigned long long* seed, int sms, cudaStream_t s) {
+  if (R == 8) return lora_bwd_t<8>(g, y, u_saved, Bm, lambda1, dA, dB, gu_ws, rows, D, scaling, p_drop, seed, sms, s);
+  if (R == 4) return lora_bwd_t<4>(g, y, u_saved, Bm, lambda1, dA, dB, gu_ws, rows, D, scaling, p_drop, seed, sms, s);
+  if (R == 16) return lora_bwd_t<16>(g, y, u_saved, Bm, lambda1, dA, dB, gu_ws, rows, D, scaling, p_drop, seed, sms, s);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace dp

@@ -65,6 +65,8 @@ class PoseEngine:
         self.adt = cfg.get("act_dtype", BF16)
         if self.adt != BF16 and getattr(backend, "name", "") == "cuda":
             raise ValueError("the sm_100a kernels store activations in bf16 only")
+        # storage dtype of pre-BatchNorm conv outputs in training ("raw")
+        self.rdt = cfg.get("raw_dtype", F32)
         self.plans = {}
         self.frozen = None
         self.seed = None
@@ -369,7 +371,7 @@ class PoseEngine:
             be_scale, be_shift = L.t["scale"], L.t["shift"]
             act = "relu" if L.relu else "none"
         bias = self.p(L.name + ".bias")
-        out = out_override if out_override is not None else self.new((P_out, L.cout), self.adt)
+        out = out_override if out_override is not None else self.new((P_out, L.cout), self.rdt if (training and L.bn is not None) else self.adt)
         kk = L.k * L.k
         if L.kind == "conv" and L.k == 1:
             be.gemm(x.reshape(-1, L.cin), L.t["wf"], out, M=P_out, N=L.cout, K=L.cin,
@@ -699,11 +701,7 @@ class PoseEngine:
             if j < nl - 1:
                 # through dropout + relu of layer j: mask by the saved (post-dropout) activation
                 dm = self.new((B, dims[j + 1]), F32)
-                t.setdefault("eyes", {})
-                eye = t["eyes"].setdefault(dims[j + 1], torch.eye(dims[j + 1], dtype=F32, device=self.device))
-                be.sgemm_small(dcur, dims[j + 1], 1, eye, dims[j + 1], 1, dm, dims[j + 1], M=B, N=dims[j + 1],
-                               K=dims[j + 1], mask_ref=yout, ld_ref=dims[j + 1], p_drop=p_drop,
-                               seed=self.seed if p_drop > 0 else None)
+                be.relu_mask(dcur, yout, dm, n=B * dims[j + 1], keep_scale=1.0 / (1.0 - p_drop) if p_drop > 0 else 1.0)
                 dcur = dm
             be.sgemm_small(dcur, 1, dims[j + 1], xin, dims[j], 1, G[zp + f"{3 * j}.weight"], dims[j], M=dims[j + 1],
                            N=dims[j], K=B)
@@ -728,8 +726,9 @@ class PoseEngine:
         be.gemm(t["dpre"], fz["w1T"], t["dxn2"], M=M, N=D, K=4 * D, name="fc1.dgrad")
         t["gmid"] = self.new((M, D), F32)
         be.layernorm_bwd(t["dxn2"], t["x_mid"], self.p(lp + "norm2.weight"), t["gx"], t["gmid"], rows=M, D=D, eps=LN_EPS)
+        t["gu"] = self.new((M, self.lora["rank"]), F32)
         be.lora_bwd(t["gmid"], t["y"], t["u"], self.p(self.lora_prefix + "lora_B"), self.p(lp + "layer_scale1.lambda1"),
-                    G[self.lora_prefix + "lora_A"], G[self.lora_prefix + "lora_B"], rows=M, D=D, R=self.lora["rank"],
+                    G[self.lora_prefix + "lora_A"], G[self.lora_prefix + "lora_B"], t["gu"], rows=M, D=D, R=self.lora["rank"],
                     scaling=self.lora["alpha"] / self.lora["rank"], p_drop=float(self.lora.get("dropout", 0.0)),
                     seed=self.seed)
 

@@ -89,6 +89,8 @@ class _Dinov2PoseBase(BasePoseModel):
                     z_hidden=zh.hidden_dims, z_dropout=zh.mlp[2].p)
         if getattr(self, "_act_dtype", None) is not None:
             ecfg["act_dtype"] = self._act_dtype
+        if getattr(self, "_raw_dtype", None) is not None:
+            ecfg["raw_dtype"] = self._raw_dtype
         self._engine = PoseEngine(dict(self.named_parameters()), dict(self.named_buffers()), ecfg, backend, device)
         return self._engine
 

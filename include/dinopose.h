@@ -115,7 +115,7 @@ int dp_lora_fwd(const float* y, const float* A, const float* B, const float* lam
                 const unsigned long long* seed_dev, void* stream);
 /* gradients of lora_A [D,R] and lora_B [R,D] (accumulated with atomics; caller zeroes them). */
 int dp_lora_bwd(const float* g, const float* y, const float* u_saved, const float* B, const float* lambda1,
-                float* dA, float* dB, long long rows, int D, int R, float scaling, float p_drop,
+                float* dA, float* dB, float* gu_workspace /* [rows,R] */, long long rows, int D, int R, float scaling, float p_drop,
                 const unsigned long long* seed_dev, void* stream);
 /* Multi-head attention forward (HF:203-234), head dim 64.  qkv bf16 [B*T, 3*heads*64] -> ctx bf16 [B*T, heads*64]. */
 int dp_attention_fwd(const void* qkv_bf16, void* ctx_bf16, int B, int T, int heads, float scale, void* stream);
@@ -130,25 +130,25 @@ int dp_decode(const float* heatmaps, int maps, int H, int W, double target_w, do
 /* ---------------------------------------------------------------- pose-head kernels (NHWC bf16) */
 int dp_im2col(const void* in, void* col, int NB, int IH, int IW, int C, int OH, int OW, int KH, int KW, int stride,
               int pad, void* stream);
-int dp_col2im(const void* col, const float* bias, void* big, int NB, int SH, int SW, int C, int BH, int BW, int KH,
-              int KW, int stride, int pad, void* stream);
-int dp_dwconv3x3(const void* in, const float* w, const float* bias, const void* add, void* out, int NB, int H, int W,
-                 int C, int flip, void* stream);
+int dp_col2im(const void* col, const float* bias, void* big, int big_is_f32, int NB, int SH, int SW, int C, int BH, int BW,
+              int KH, int KW, int stride, int pad, void* stream);
+int dp_dwconv3x3(const void* in, const float* w, const float* bias, const void* add, void* out, int out_is_f32, int NB,
+                 int H, int W, int C, int flip, void* stream);
 int dp_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, int NB, int H, int W, int C, void* stream);
 /* train-mode BatchNorm2d (eps, momentum as torch): sums fp64 [2*C] must be zero on entry of dp_bn_stats;
- * dp_bn_finalize re-zeroes it. */
-int dp_bn_stats(const void* raw, double* sums, long long P, int C, void* stream);
+ * dp_bn_finalize re-zeroes it.  `raw` (pre-BN conv output, [P,C]) is bf16 or fp32 (raw_is_f32). */
+int dp_bn_stats(const void* raw, int raw_is_f32, double* sums, long long P, int C, void* stream);
 int dp_bn_finalize(double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                    float* scale, float* shift, float* mean, float* invstd, int C, double count, float eps,
                    float momentum, void* stream);
 int dp_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
                     const float* conv_bias, float* scale, float* shift, int C, float eps, void* stream);
-int dp_bn_apply(const void* raw, const float* scale, const float* shift, const void* add1, const void* add2,
-                void* out, long long P, int C, int relu, int mode, void* stream);
-int dp_bn_bwd_reduce(const void* dout, const void* raw, const void* add1, const float* scale, const float* shift,
+int dp_bn_apply(const void* raw, int raw_is_f32, const float* scale, const float* shift, const void* add1,
+                const void* add2, void* out, long long P, int C, int relu, int mode, void* stream);
+int dp_bn_bwd_reduce(const void* dout, const void* raw, int raw_is_f32, const void* add1, const float* scale, const float* shift,
                      const float* mean, const float* invstd, double* sums, long long P, int C, int relu, int mode,
                      void* stream);
-int dp_bn_bwd_apply(const void* dout, const void* raw, const void* add1, const float* gamma, const float* scale,
+int dp_bn_bwd_apply(const void* dout, const void* raw, int raw_is_f32, const void* add1, const float* gamma, const float* scale,
                     const float* shift, const float* mean, const float* invstd, const double* sums, void* draw,
                     void* dres, float* dgamma, float* dbeta, long long P, int C, int relu, int mode, int eval_mode,
                     int shuffle_oh, int shuffle_ow, void* stream);
@@ -161,6 +161,8 @@ int dp_sgemm_small(const float* A, long long sa_m, long long sa_k, const float* 
                    float* C, long long ldc, int M, int N, int K, const float* bias, int relu, const float* mask_ref,
                    long long ld_ref, float p_drop, const unsigned long long* seed_dev, int accumulate, void* stream);
 int dp_colsum(const void* x, int is_bf16, float* out, long long P, int C, long long ld, void* stream);
+/* out = ref > 0 ? d * keep_scale : 0  (gradient through ReLU + inverted dropout given the saved output) */
+int dp_relu_mask(const float* d, const float* ref, float* out, long long n, float keep_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -171,7 +171,7 @@ class TorchEmulator:
             x_out.copy_(x_in + (y + (u @ Bm.detach()) * scaling) * lambda1.detach())
         self.prog.calls.append(fn)
 
-    def lora_bwd(self, g, y, u_saved, Bm, lambda1, dA, dB, *, rows, D, R, scaling, p_drop, seed):
+    def lora_bwd(self, g, y, u_saved, Bm, lambda1, dA, dB, gu_ws, *, rows, D, R, scaling, p_drop, seed):
         def fn():
             gv = g * lambda1.detach() * scaling
             dB.add_(u_saved.t() @ gv)
@@ -362,6 +362,11 @@ class TorchEmulator:
                 c.add_(v)
             else:
                 c.copy_(v)
+        self.prog.calls.append(fn)
+
+    def relu_mask(self, d, ref, out, *, n, keep_scale=1.0):
+        def fn():
+            out.copy_(torch.where(ref > 0, d * keep_scale, torch.zeros_like(d)))
         self.prog.calls.append(fn)
 
     def colsum(self, x, out, *, P, C, ld):

@@ -260,7 +260,8 @@ def test_lora_fwd_bwd():
     g = rnd(rows, D, seed=5)
     ref.backward(g)
     dA, dB = torch.zeros_like(A), torch.zeros_like(Bm)
-    run(lambda b: b.lora_bwd(g, y, u, Bm, lam, dA, dB, rows=rows, D=D, R=R, scaling=s, p_drop=0.0, seed=None))
+    gu = torch.zeros(rows, R, device=dev())
+    run(lambda b: b.lora_bwd(g, y, u, Bm, lam, dA, dB, gu, rows=rows, D=D, R=R, scaling=s, p_drop=0.0, seed=None))
     assert rel(dA, Ar.grad) < 1e-4
     assert rel(dB, Br.grad) < 1e-4
     # dropout: statistically ~10% dropped, kept values scaled by 1/(1-p)
@@ -376,10 +377,10 @@ def test_dwconv_and_wgrad():
     assert rel(dw, wr.grad) < 1e-3
 
 
-@pytest.mark.parametrize("mode", [0, 1])
-def test_batchnorm_train_fwd_bwd(mode):
-    P, C = 3 * 16 * 16, 128
-    raw = (rnd(P, C) * 1.5 + 0.2).to(BF)
+@pytest.mark.parametrize("mode,rawdt,C", [(0, BF, 128), (1, BF, 128), (0, torch.float32, 512), (1, torch.float32, 64)])
+def test_batchnorm_train_fwd_bwd(mode, rawdt, C):
+    P = 3 * 16 * 16
+    raw = (rnd(P, C) * 1.5 + 0.2).to(rawdt)
     gamma, beta = rnd(C, seed=1) * 0.1 + 1, rnd(C, seed=2) * 0.1
     rm, rv = rnd(C, seed=3) * 0.1, rnd(C, seed=4).abs() + 0.5
     add1 = rnd(P, C, seed=5, dtype=BF)
@@ -464,9 +465,9 @@ def test_sgemm_small():
     # backward forms: dX = (dY*mask) W ; dW = (dY*mask)^T X
     dy = rnd(M, N, seed=3)
     dpre = torch.zeros(M, N, device=dev())
-    eye = torch.eye(N, device=dev())
-    run(lambda b: b.sgemm_small(dy, N, 1, eye, N, 1, dpre, N, M=M, N=N, K=N, mask_ref=y, ld_ref=N))
-    assert rel(dpre, dy * (ref > 0)) < 1e-6
+    run(lambda b: b.relu_mask(dy, y, dpre, n=M * N, keep_scale=1.25))
+    assert rel(dpre, 1.25 * dy * (ref > 0)) < 1e-6
+    run(lambda b: b.relu_mask(dy, y, dpre, n=M * N))
     dx = torch.zeros(M, K, device=dev())
     run(lambda b: b.sgemm_small(dpre, N, 1, w, K, 1, dx, K, M=M, N=K, K=N))
     assert rel(dx, dpre @ w) < 1e-5

@@ -154,7 +154,7 @@ def run_ours(args):
 
     from dino_pose_b200.model import Dinov2PoseModelLoRA
     from dino_pose_b200.train import PoseTrainer
-    from oracle.weights import make_inputs   # synthetic batch generator only (no oracle compute on this arm)
+    from dino_pose_b200.synthetic import make_inputs
 
     B = args.batch
     torch.manual_seed(0)                      # identical random-init replica on every rank

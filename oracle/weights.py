@@ -181,15 +181,4 @@ def make_state_dict(arch="facebook/dinov2-small", seed=0, lora_rank=0, num_keypo
     return sd
 
 
-def make_inputs(batch, height=224, width=224, seed=0, num_keypoints=24, heatmap_size=48):
-    """Synthetic batch per SURVEY.md section 8(d): N(0,1) pixels, U(0,1) target maps,
-    visibility in {0,1,2} (the loss mask is ``> 1``, reference train.py:94,114)."""
-    g = torch.Generator(device="cpu")
-    g.manual_seed(1000 + seed)
-    px = torch.randn(batch, 3, height, width, generator=g)
-    hm = torch.rand(batch, num_keypoints, heatmap_size, heatmap_size, generator=g)
-    xy = torch.rand(batch, num_keypoints, 2, generator=g) * height
-    vis = torch.randint(0, 3, (batch, num_keypoints, 1), generator=g).float()
-    kps = torch.cat([xy, vis], dim=-1)
-    z = torch.randn(batch, num_keypoints, generator=g)
-    return {"pixel_values": px, "heatmaps": hm, "keypoints": kps, "z": z}
+from dino_pose_b200.synthetic import make_inputs  # noqa: E402,F401  (one generator for tests, bench and tools)

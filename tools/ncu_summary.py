@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""Summarise ncu output for profiles/ (run in the CPU container on files brought back in gpurun_out/).
+
+    python tools/ncu_summary.py full   gpurun_out/X.ncu-rep          > profiles/X_full.md
+    python tools/ncu_summary.py launch gpurun_out/X_ncu_launches.csv > profiles/X_launches.md
+"""
+import collections
+import csv
+import io
+import re
+import subprocess
+import sys
+
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "smsp__inst_executed.sum", "sm__cycles_elapsed.max",
+        "l1tex__data_pipe_lsu_wavefronts.sum", "lts__t_sector_hit_rate.pct"]
+
+
+def short(name):
+    name = re.sub(r"void |dp::|<unnamed>::|at::native::|at::", "", name)
+    return re.sub(r"\(.*", "", name)[:80]
+
+
+def full(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    print(f"# ncu --set full summary of `{path}`\n")
+    print("| # | kernel | grid | " + " | ".join(k for k in KEYS if k in idx) + " |")
+    print("|---|---|---|" + "---|" * sum(k in idx for k in KEYS))
+    for n, r in enumerate(rows[2:]):
+        vals = [f"{r[idx[k]]} {units[idx[k]]}" for k in KEYS if k in idx]
+        print(f"| {n} | `{short(r[idx['Kernel Name']])}` | {r[idx['Grid Size']]} | " + " | ".join(vals) + " |")
+
+
+def launch(path):
+    txt = open(path).read().splitlines()
+    i = [k for k, l in enumerate(txt) if l.startswith('"ID"')][0]
+    rows = list(csv.DictReader(io.StringIO("\n".join(txt[i:]))))
+    agg = collections.OrderedDict()
+    for r in rows:
+        a = agg.setdefault(short(r["Kernel Name"]), [0, 0.0])
+        a[0] += 1
+        a[1] += float(r["Metric Value"]) / 1e3
+    tot = sum(v[1] for v in agg.values())
+    print(f"# ncu launch list `{path}`: {len(rows)} launches, {tot:.1f} us total (cold-cache, serialised)\n")
+    print("| kernel | launches | total us | share |")
+    print("|---|---|---|---|")
+    for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+        print(f"| `{n}` | {c} | {t:.1f} | {100 * t / tot:.1f}% |")
+
+
+if __name__ == "__main__":
+    {"full": full, "launch": launch}[sys.argv[1]](sys.argv[2])

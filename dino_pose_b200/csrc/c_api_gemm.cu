@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/dinopose.h"
@@ -113,7 +114,7 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   memset(&p, 0, sizeof(p));
   int bn = a->block_n;
   if (bn == 0) bn = a->N >= 128 ? 128 : (a->N > 32 ? 64 : 32);
-  if (bn != 32 && bn != 64 && bn != 128 && bn != 256) return set_error(-3, "dp_gemm_bf16: block_n %d", bn);
+  if (bn != 32 && bn != 64 && bn != 128 && bn != 192 && bn != 256) return set_error(-3, "dp_gemm_bf16: block_n %d", bn);
   p.N = a->N;
   p.n_tiles = (a->N + bn - 1) / bn;
   p.a_mode = a->a_mode;
@@ -134,6 +135,8 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
     if (a->K != a->KH * a->KW * a->C) return set_error(-5, "dp_gemm_bf16: K != KH*KW*C");
     if (a->M != a->NB * a->OH * a->OW) return set_error(-5, "dp_gemm_bf16: M != NB*OH*OW");
     choose_box(a->OW, a->OH, 128, &p.bw, &p.bh, &p.bb);
+    p.bw_log2 = __builtin_ctz(p.bw);
+    p.bh_log2 = __builtin_ctz(p.bh);
     p.OW = a->OW; p.OH = a->OH; p.NB = a->NB;
     p.tiles_x = (a->OW + p.bw - 1) / p.bw;
     p.tiles_y = (a->OH + p.bh - 1) / p.bh;
@@ -162,6 +165,15 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   e.n_valid = a->n_valid > 0 ? a->n_valid : a->N;
   e.map_a = a->map_a; e.map_b = a->map_b;
   if (e.n_valid > a->N) return set_error(-6, "dp_gemm_bf16: n_valid > N");
+  if (e.row_map != DP_ROWMAP_NCHW && (e.n_valid % 4)) return set_error(-6, "dp_gemm_bf16: n_valid %% 4 != 0");
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* v = getenv("DP_GEMM_DEBUG"); dbg = v ? atoi(v) : 0; }
+    e.debug = dbg;
+  }
+  e.stats = a->stats;
+  e.stats_c = a->stats_c > 0 ? a->stats_c : e.n_valid;
+  if (e.stats && e.row_map == DP_ROWMAP_NCHW) return set_error(-6, "dp_gemm_bf16: stats with NCHW row map");
   if (e.row_map == DP_ROWMAP_IDENTITY || e.row_map == DP_ROWMAP_PATCH_TOKENS) {
     const long long align = (e.out_dtype == DP_OUT_BF16) ? 8 : 4;
     if (e.ldo % align) return set_error(-7, "dp_gemm_bf16: ldo %lld must be a multiple of %lld", e.ldo, align);
@@ -170,6 +182,14 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
     return set_error(-8, "dp_gemm_bf16: shuffle map needs Cout %% 32 == 0");
   if ((e.row_map == DP_ROWMAP_NCHW || e.row_map == DP_ROWMAP_SHUFFLE2X2) && (a->OH <= 0 || a->OW <= 0))
     return set_error(-8, "dp_gemm_bf16: row map needs OH/OW");
+  if (e.row_map != DP_ROWMAP_NCHW) {
+    // the epilogue addresses rows with 32-bit element offsets
+    const long long out_rows = (e.row_map == DP_ROWMAP_SHUFFLE2X2) ? 4LL * a->M
+                               : (e.row_map == DP_ROWMAP_PATCH_TOKENS) ? (long long)(a->M / e.map_a + 1) * e.map_b : a->M;
+    if (out_rows * e.ldo + a->N >= 0xffffffffLL || (e.residual && (long long)a->M * e.ldr + a->N >= 0xffffffffLL) ||
+        ((e.aux_out || e.aux_in) && (long long)a->M * e.ld_aux + a->N >= 0xffffffffLL))
+      return set_error(-9, "dp_gemm_bf16: tensor too large for 32-bit epilogue offsets");
+  }
   const int tiles = p.m_tiles * p.n_tiles;
   const int grid = tiles < sm_count() ? tiles : sm_count();
   return cuda_error(launch_gemm(p, bn, grid, static_cast<cudaStream_t>(stream)), "dp_gemm_bf16 launch");

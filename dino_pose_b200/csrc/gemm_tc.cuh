@@ -24,12 +24,15 @@ struct Epilogue {
   const float* residual;
   void* aux_out;
   const void* aux_in;
+  double* stats;    // optional fused BatchNorm statistics: stats[c] += sum_rows v, stats[stats_c + c] += sum_rows v^2
   long long ldo, ldr, ld_aux;
   int out_dtype;
   int act;
   int row_map;
   int res_is_bf16;  // residual tensor dtype (0 fp32, 1 bf16)
   int n_valid;      // number of valid output columns (<= N)
+  int stats_c;      // number of channels of `stats`
+  int debug;        // tuning knobs (DP_GEMM_DEBUG env): 1 skip stores, 2 skip residual/aux loads, 4 skip phase 2, 8 skip TMEM loads
   int map_a, map_b; // ROWMAP_PATCH_TOKENS: (patches per image, tokens per image); NCHW: (channels K, 0);
                     // SHUFFLE2X2: (Cout, 0)
 };
@@ -42,7 +45,8 @@ struct alignas(64) GemmParams {
   int m_tiles, n_tiles;
   int a_mode;               // 0 plain, 1 implicit conv
   int kw, pad_x, pad_y, cin_blocks;
-  int bw, bh, bb;           // pixel box of one 128-row tile
+  int bw, bh, bb;           // pixel box of one 128-row tile (powers of two)
+  int bw_log2, bh_log2;
   int OW, OH, NB;           // output extents (conv) -- also used by the row maps
   int tiles_x, tiles_y;
 };

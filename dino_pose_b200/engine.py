@@ -371,24 +371,27 @@ class PoseEngine:
             be_scale, be_shift = L.t["scale"], L.t["shift"]
             act = "relu" if L.relu else "none"
         bias = self.p(L.name + ".bias")
+        # train-mode BatchNorm statistics are accumulated by the producing GEMM's epilogue (no separate pass)
+        st = dict(stats=L.t["sums"], stats_c=L.cout) if (training and L.bn is not None and L.kind not in ("convT", "dw")) else {}
+        L.t["stats_fused"] = bool(st)
         out = out_override if out_override is not None else self.new((P_out, L.cout), self.rdt if (training and L.bn is not None) else self.adt)
         kk = L.k * L.k
         if L.kind == "conv" and L.k == 1:
             be.gemm(x.reshape(-1, L.cin), L.t["wf"], out, M=P_out, N=L.cout, K=L.cin,
                     bias=be_shift if fold else bias, scale=be_scale if fold else None, act=act if fold else "none",
-                    name=L.name)
+                    name=L.name, **st)
         elif L.kind in ("conv", "convT_s1"):
             pad = L.pad if L.kind == "conv" else L.k - 1 - L.pad
             xin = x.view(NB, L.ih, L.iw, L.cin) if x.dim() == 2 else x
             be.gemm(xin, L.t["wf"], out, M=P_out, N=L.cout, K=kk * L.cin, bias=be_shift if fold else bias,
                     scale=be_scale if fold else None, act=act if fold else "none",
-                    conv=dict(KH=L.k, KW=L.k, pad=pad, OH=L.oh, OW=L.ow), name=L.name)
+                    conv=dict(KH=L.k, KW=L.k, pad=pad, OH=L.oh, OW=L.ow), name=L.name, **st)
         elif L.kind == "conv_s2":
             L.t["col"] = self.new((P_out, kk * L.cin), self.adt)
             be.im2col(x, L.t["col"], NB=NB, IH=L.ih, IW=L.iw, C=L.cin, OH=L.oh, OW=L.ow, KH=L.k, KW=L.k, stride=L.stride,
                       pad=L.pad)
             be.gemm(L.t["col"], L.t["wf"], out, M=P_out, N=L.cout, K=kk * L.cin, bias=be_shift if fold else bias,
-                    scale=be_scale if fold else None, act=act if fold else "none", name=L.name)
+                    scale=be_scale if fold else None, act=act if fold else "none", name=L.name, **st)
         elif L.kind == "convT2":
             P_in = NB * L.ih * L.iw
             L.t["bias4"] = self.new((kk * L.cout,), F32)
@@ -397,7 +400,7 @@ class PoseEngine:
             be.host("bias4", self._tile4_fn(L, fold))
             be.gemm(x.reshape(P_in, L.cin), L.t["wf"], out, M=P_in, N=kk * L.cout, K=L.cin, bias=L.t["bias4"],
                     scale=L.t["scale4"] if fold else None, act=act if fold else "none", row_map="shuffle2x2",
-                    map_a=L.cout, OH=L.ih, OW=L.iw, NB=NB, ldo=L.cout, name=L.name)
+                    map_a=L.cout, OH=L.ih, OW=L.iw, NB=NB, ldo=L.cout, name=L.name, **st)
         elif L.kind == "convT":
             P_in = NB * L.ih * L.iw
             L.t["colT"] = self.new((P_in, kk * L.cout), self.adt)
@@ -443,7 +446,8 @@ class PoseEngine:
         be = self.be
         P = NB * L.oh * L.ow
         bn = L.bn
-        be.bn_stats(raw, L.t["sums"], P=P, C=L.cout)
+        if not L.t.get("stats_fused"):
+            be.bn_stats(raw, L.t["sums"], P=P, C=L.cout)
         be.bn_finalize(L.t["sums"], self.p(bn + ".weight"), self.p(bn + ".bias"), self.p(bn + ".running_mean"),
                        self.p(bn + ".running_var"), L.t["scale"], L.t["shift"], L.t["mean"], L.t["invstd"], C=L.cout,
                        count=P)

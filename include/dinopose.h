@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 1
+#define DP_ABI_VERSION 2
 
 const char* dp_last_error(void);
 int dp_abi_version(void);
@@ -49,7 +49,7 @@ typedef struct {
   const void* W;          /* bf16 [N, K] row-major, row pitch ldw */
   long long lda, ldw;     /* elements */
   int M, N, K;
-  int block_n;            /* 32 / 64 / 128 / 256, 0 = auto */
+  int block_n;            /* 32 / 64 / 128 / 192 / 256, 0 = auto */
   int a_mode;             /* 0: A is [M,K]; 1: A is NHWC [NB,IH,IW,C], K = KH*KW*C, M = NB*OH*OW */
   int C, IW, IH, NB;
   long long a_stride_w, a_stride_h, a_stride_b; /* elements */
@@ -68,6 +68,11 @@ typedef struct {
   const void* aux_in;
   long long ld_aux;
   int row_map, n_valid, map_a, map_b;
+  double* stats;          /* optional fused train-mode BatchNorm statistics of v (before act): fp64 [2*stats_c],
+                             stats[c] += sum over rows, stats[stats_c + c] += sum of squares (same contract as
+                             dp_bn_stats: zero on entry, dp_bn_finalize re-zeroes).  With DP_ROWMAP_SHUFFLE2X2
+                             the channel of column j is j % map_a. */
+  int stats_c;
 } dp_gemm_args;
 int dp_gemm_bf16(const dp_gemm_args* a, void* stream);
 

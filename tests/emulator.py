@@ -42,7 +42,7 @@ class TorchEmulator:
     # ------------------------------------------------------------------ GEMM family
     def gemm(self, A, W, out, *, M, N, K, lda=None, ldw=None, ldo=None, out_dtype="bf16", bias=None, scale=None,
              ls=None, residual=None, ldr=None, aux_out=None, aux_in=None, ld_aux=0, act="none", row_map="identity",
-             n_valid=0, map_a=0, map_b=0, conv=None, OH=0, OW=0, NB=0, block_n=0, name="gemm"):
+             n_valid=0, map_a=0, map_b=0, conv=None, OH=0, OW=0, NB=0, block_n=0, stats=None, stats_c=0, name="gemm"):
         def fn():
             Wf = W.float()[:N, :K]
             if conv is not None:
@@ -60,6 +60,13 @@ class TorchEmulator:
                 v = v * scale[:nv]
             if bias is not None:
                 v = v + bias[:nv]
+            if stats is not None:
+                sc = stats_c if stats_c > 0 else nv
+                s1, s2 = v.double().sum(0), (v.double() ** 2).sum(0)
+                if row_map == "shuffle2x2":
+                    s1, s2 = s1.view(-1, map_a).sum(0), s2.view(-1, map_a).sum(0)
+                stats[:sc] += s1
+                stats[sc:2 * sc] += s2
             if aux_out is not None:
                 aux_out.view(-1, ld_aux)[:M, :nv] = v.to(aux_out.dtype)
             if act == "relu":

@@ -43,7 +43,9 @@ def rnd(*shape, scale=1.0, seed=0, dtype=torch.float32):
 # ---------------------------------------------------------------------------------- GEMM
 @pytest.mark.parametrize("M,N,K,bn", [(128, 128, 64, 128), (257, 384, 384, 128), (1000, 1152, 384, 128),
                                       (300, 1536, 384, 256), (515, 384, 1536, 128), (200, 64, 128, 64),
-                                      (130, 24, 64, 32), (512, 384, 640, 128), (16448, 384, 384, 128)])
+                                      (130, 24, 64, 32), (512, 384, 640, 128), (16448, 384, 384, 128),
+                                      (1000, 1152, 384, 192), (16448, 1536, 384, 192), (16448, 1152, 384, 256),
+                                      (777, 768, 768, 192), (300, 104, 192, 128), (4096, 512, 512, 256)])
 def test_gemm_plain(M, N, K, bn):
     A = rnd(M, K, dtype=BF)
     W = rnd(N, K, scale=0.05, seed=1, dtype=BF)
@@ -83,6 +85,36 @@ def test_gemm_epilogues():
     x = pre.float().requires_grad_(True)
     F.gelu(x).sum().backward()
     assert rel(out4.float(), (A.float() @ W.float().t()) * x.grad) < 1e-2
+
+
+@pytest.mark.parametrize("M,N,bn", [(5000, 128, 128), (40000, 512, 256), (3000, 384, 192), (129, 64, 64)])
+def test_gemm_fused_bn_statistics(M, N, bn):
+    """Per-column sum / sum-of-squares of the pre-activation value (train-mode BatchNorm statistics fused into the
+    producing GEMM's epilogue), fp64 accumulators, same contract as dp_bn_stats."""
+    K = 128
+    A = rnd(M, K, dtype=BF)
+    W = rnd(N, K, scale=0.05, seed=1, dtype=BF)
+    bias = rnd(N, seed=2)
+    out = torch.zeros(M, N, device=dev())
+    sums = torch.zeros(2 * N, device=dev(), dtype=torch.float64)
+    run(lambda b: b.gemm(A, W, out, M=M, N=N, K=K, bias=bias, out_dtype="f32", block_n=bn, stats=sums, stats_c=N))
+    ref = (A.float() @ W.float().t() + bias).double()
+    assert rel(out, ref) < 2e-3
+    assert rel(sums[:N], ref.sum(0)) < 1e-4
+    assert rel(sums[N:], (ref * ref).sum(0)) < 1e-4
+
+
+def test_gemm_fused_bn_statistics_shuffle2x2():
+    NB, H, Wd, Cin, Cout = 3, 8, 8, 128, 256
+    x = rnd(NB * H * Wd, Cin, dtype=BF)
+    Wm = rnd(4 * Cout, Cin, scale=0.05, seed=1, dtype=BF)
+    bias4 = rnd(Cout, seed=2).repeat(4).contiguous()
+    out = torch.zeros(NB * 2 * H * 2 * Wd, Cout, device=dev())
+    sums = torch.zeros(2 * Cout, device=dev(), dtype=torch.float64)
+    run(lambda b: b.gemm(x, Wm, out, M=NB * H * Wd, N=4 * Cout, K=Cin, bias=bias4, out_dtype="f32", row_map="shuffle2x2",
+                         map_a=Cout, OH=H, OW=Wd, NB=NB, stats=sums, stats_c=Cout))
+    assert rel(sums[:Cout], out.double().sum(0)) < 1e-4
+    assert rel(sums[Cout:], (out.double() ** 2).sum(0)) < 1e-4
 
 
 def test_gemm_patch_rowmap_and_nchw():

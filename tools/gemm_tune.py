@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Micro-benchmark of dp_gemm_bf16 on the backbone / head shapes of BASELINE configs[1] (CUDA events, L2 flushed
+between repetitions by cycling through enough distinct buffers).  Tuning aid, not a reported number."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from dino_pose_b200.backend import CudaBackend  # noqa: E402
+
+BF = torch.bfloat16
+dev = torch.device("cuda:0")
+M = 16448
+SHAPES = {
+    # name: (M, N, K, epilogue)
+    "qkv": (M, 1152, 384, "bias_bf16"),
+    "proj": (M, 384, 384, "res_f32"),
+    "fc1": (M, 1536, 384, "gelu_bf16"),
+    "fc2": (M, 384, 1536, "res_f32"),
+    "fc1_B": (M, 3072, 768, "gelu_bf16"),
+    "fc2_B": (M, 768, 3072, "res_f32"),
+}
+
+
+def bench(name, bn, reps=20, nbuf=6):
+    m, n, k, epi = SHAPES[name]
+    be = CudaBackend()
+    progs = []
+    for i in range(nbuf):
+        A = torch.randn(m, k, device=dev).to(BF)
+        W = (torch.randn(n, k, device=dev) * 0.05).to(BF)
+        bias = torch.randn(n, device=dev)
+        prog = be.begin()
+        if epi == "bias_bf16":
+            out = torch.empty(m, n, device=dev, dtype=BF)
+            be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, block_n=bn)
+        elif epi == "gelu_bf16":
+            out = torch.empty(m, n, device=dev, dtype=BF)
+            be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, act="gelu", block_n=bn)
+        else:
+            out = torch.empty(m, n, device=dev)
+            res = torch.randn(m, n, device=dev)
+            ls = torch.ones(n, device=dev)
+            be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, ls=ls, residual=res, out_dtype="f32", block_n=bn)
+        progs.append(prog)
+    for p in progs:
+        p.run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for r in range(reps):
+        progs[r % nbuf].run()
+    e1.record()
+    torch.cuda.synchronize()
+    us = e0.elapsed_time(e1) / reps * 1e3
+    tf = 2.0 * m * n * k / us / 1e6
+    return us, tf
+
+
+if __name__ == "__main__":
+    names = sys.argv[1].split(",") if len(sys.argv) > 1 else list(SHAPES)
+    bns = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [128, 192, 256]
+    dbg = os.environ.get("DP_GEMM_DEBUG", "0")
+    for nm in names:
+        for bn in bns:
+            us, tf = bench(nm, bn)
+            print(f"debug={dbg} {nm:6s} bn={bn:3d}  {us:8.1f} us  {tf:7.1f} TFLOP/s", flush=True)

@@ -185,17 +185,27 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   const bool has_aux_out = (OPT & OP_AUX_OUT) && e.aux_out != nullptr;
   const bool has_aux_in = (OPT & OP_AUX_IN) && e.aux_in != nullptr && !(e.debug & 2);
   const bool has_stats = (OPT & OP_STATS) && e.stats != nullptr;
+  (void)has_ls;
 
   const int rr = lane >> 3, cg = lane & 7;
   constexpr uint32_t kFull = 0xffffffffu;
 #pragma unroll 1
   for (int c = half; c < BN / 32; c += 2) {
     if (e.debug & 8) continue;
+    const int col0 = n_blk * BN + c * 32;
+    if (col0 >= e.n_valid) continue;  // warp-uniform
+    // per-column parameters first: their global-load latency overlaps the TMEM load and the transpose
+    const int ccol = col0 + cg * 4;
+    const bool cvalid = ccol < e.n_valid;  // n_valid % 4 == 0 (checked by the launcher)
+    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f), lsv = sc;
+    if (cvalid) {
+      if (has_scale) sc = ldg4(e.scale + ccol);
+      if (e.bias != nullptr) bi = ldg4(e.bias + ccol);
+      if (has_ls) lsv = ldg4(e.ls + ccol);
+    }
     uint32_t v[32];
     tmem_ld_32x32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
     tmem_ld_wait();
-    const int col0 = n_blk * BN + c * 32;
-    if (col0 >= e.n_valid) continue;  // warp-uniform
     {
       float4* srow = reinterpret_cast<float4*>(stg + lane * 32);
 #pragma unroll
@@ -205,14 +215,6 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     }
     __syncwarp();
     if (e.debug & 4) continue;
-    const int ccol = col0 + cg * 4;
-    const bool cvalid = ccol < e.n_valid;  // n_valid % 4 == 0 (checked by the launcher)
-    float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f), lsv = sc;
-    if (cvalid) {
-      if (has_scale) sc = ldg4(e.scale + ccol);
-      if (e.bias != nullptr) bi = ldg4(e.bias + ccol);
-      if (has_ls) lsv = ldg4(e.ls + ccol);
-    }
     uint32_t ocol = uint32_t(ccol), tap_off = 0;
     if (map == EM_SHUFFLE) {
       const int tap = col0 / e.map_a;
@@ -258,34 +260,40 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       }
       xs[it] = *reinterpret_cast<const float4*>(stg + row * 32 + ((cg ^ (row & 7)) << 2));
     }
-    // pass B: math + stores
+    // pass B: branch-free math for all 8 rows (the compiler interleaves the rows), predicated stores only
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const float4 x = xs[it];
-      if (o_off[it] != kInvalidRow && cvalid) {
-        float f[4];
-        if constexpr ((OPT & OP_SCALE) != 0) {
-          f[0] = fmaf(x.x, sc.x, bi.x); f[1] = fmaf(x.y, sc.y, bi.y); f[2] = fmaf(x.z, sc.z, bi.z); f[3] = fmaf(x.w, sc.w, bi.w);
-        } else {
-          f[0] = x.x + bi.x; f[1] = x.y + bi.y; f[2] = x.z + bi.z; f[3] = x.w + bi.w;
-        }
-        if constexpr ((OPT & OP_STATS) != 0) {
-          if (has_stats) {
+      const bool ok = o_off[it] != kInvalidRow && cvalid;
+      float f[4];
+      if constexpr ((OPT & OP_SCALE) != 0) {
+        f[0] = fmaf(x.x, sc.x, bi.x); f[1] = fmaf(x.y, sc.y, bi.y); f[2] = fmaf(x.z, sc.z, bi.z); f[3] = fmaf(x.w, sc.w, bi.w);
+      } else {
+        f[0] = x.x + bi.x; f[1] = x.y + bi.y; f[2] = x.z + bi.z; f[3] = x.w + bi.w;
+      }
+      if constexpr ((OPT & OP_STATS) != 0) {
+        const float m = ok ? 1.f : 0.f;   // rows / columns outside the problem do not count
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              s1[k] += f[k];
-              s2[k] = fmaf(f[k], f[k], s2[k]);
-            }
-          }
+        for (int k = 0; k < 4; ++k) {
+          s1[k] = fmaf(f[k], m, s1[k]);
+          s2[k] = fmaf(f[k] * m, f[k], s2[k]);
         }
-        if constexpr ((OPT & OP_AUX_OUT) != 0) {
-          if (has_aux_out) {
-            uint2 t;
-            t.x = pack_bf16x2(f[0], f[1]);
-            t.y = pack_bf16x2(f[2], f[3]);
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux_out) + a_off[it] + ccol) = t;
-          }
+      }
+      if constexpr ((OPT & OP_AUX_OUT) != 0) {
+        if (has_aux_out && ok) {
+          uint2 t;
+          t.x = pack_bf16x2(f[0], f[1]);
+          t.y = pack_bf16x2(f[2], f[3]);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux_out) + a_off[it] + ccol) = t;
         }
+      }
+      if constexpr (ACT == EA_RELU) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], 0.f);
+      } else if constexpr (ACT == EA_GELU) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = gelu_fast(f[k]);
+      } else if constexpr (ACT == EA_RUNTIME) {
         if (act == ACT_RELU) {
 #pragma unroll
           for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], 0.f);
@@ -293,28 +301,28 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 #pragma unroll
           for (int k = 0; k < 4; ++k) f[k] = gelu_fast(f[k]);
         }
-        if constexpr ((OPT & OP_AUX_IN) != 0) {
-          if (has_aux_in) {
-            float t[4];
-            unpack_bf16x4(auxin[it], t);
+      }
+      if constexpr ((OPT & OP_AUX_IN) != 0) {
+        float t[4];
+        unpack_bf16x4(auxin[it], t);
+        if (has_aux_in) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) f[k] *= gelu_fast_grad(t[k]);
-          }
+          for (int k = 0; k < 4; ++k) f[k] *= gelu_fast_grad(t[k]);
         }
-        if constexpr ((OPT & OP_LSRES) != 0) {
-          if (has_ls) { f[0] *= lsv.x; f[1] *= lsv.y; f[2] *= lsv.z; f[3] *= lsv.w; }
-          f[0] += res32[it].x; f[1] += res32[it].y; f[2] += res32[it].z; f[3] += res32[it].w;
-        }
-        if constexpr ((OPT & OP_RES_BF16) != 0) {
-          float t[4];
-          unpack_bf16x4(res16[it], t);
+      }
+      if constexpr ((OPT & OP_LSRES) != 0) {
+        f[0] = fmaf(f[0], lsv.x, res32[it].x); f[1] = fmaf(f[1], lsv.y, res32[it].y);
+        f[2] = fmaf(f[2], lsv.z, res32[it].z); f[3] = fmaf(f[3], lsv.w, res32[it].w);
+      }
+      if constexpr ((OPT & OP_RES_BF16) != 0) {
+        float t[4];
+        unpack_bf16x4(res16[it], t);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) f[k] += t[k];
-        }
-        const uint32_t off = o_off[it] + tap_off + ocol;
-        if (e.debug & 1) {
-          if (f[0] + f[1] + f[2] + f[3] == 1.2345e30f) reinterpret_cast<float*>(e.out)[0] = 0.f;  // keep the math alive
-        } else if (out_f32) {
+        for (int k = 0; k < 4; ++k) f[k] += t[k];
+      }
+      const uint32_t off = o_off[it] + tap_off + ocol;
+      if (ok) {
+        if (out_f32) {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off) = make_float4(f[0], f[1], f[2], f[3]);
         } else {
           uint2 t;

@@ -326,7 +326,8 @@ class PoseEngine:
             be.layernorm_fwd(x_att, self.p(lp + "norm2.weight"), self.p(lp + "norm2.bias"), t["xn"], None, rows=M, D=D,
                              eps=LN_EPS)
             be.gemm(t["xn"], fz[f"w1{i}"], t["h"], M=M, N=4 * D, K=D, bias=self.p(lp + "mlp.fc1.bias"), act="gelu",
-                    aux_out=t["pre"] if (last and training) else None, ld_aux=4 * D, name=f"fc1_{i}")
+                    aux_out=t["pre"] if (last and training) else None, ld_aux=4 * D, name=f"fc1_{i}",
+                    block_n=192 if (4 * D) % 192 == 0 else 0)   # 192-wide tiles: fewer waves for N = 1536 / 3072 (tools/gemm_tune.py)
             x_out = t["x_last"] if (last and training) else t["x"]
             be.gemm(t["h"], fz[f"w2{i}"], x_out, M=M, N=D, K=4 * D, bias=self.p(lp + "mlp.fc2.bias"), out_dtype="f32",
                     ls=self.p(lp + "layer_scale2.lambda1"), residual=x_att, name=f"fc2_{i}")

@@ -47,10 +47,20 @@ def bench(name, bn, reps=20, nbuf=6):
     for p in progs:
         p.run()
     torch.cuda.synchronize()
+    # one CUDA graph of `reps` launches: no CPU launch cost between kernels
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for r in range(reps):
+                progs[r % nbuf].run()
+    torch.cuda.current_stream().wait_stream(side)
+    g.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for r in range(reps):
-        progs[r % nbuf].run()
+    g.replay()
     e1.record()
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3

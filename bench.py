@@ -169,9 +169,9 @@ def run_ours(args):
         return trainer.step(devb["pixel_values"], devb["heatmaps"], devb["keypoints"], devb["z"])
 
     def step_e2e():
-        b = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+        b = host                   # pinned host tensors: PoseTrainer.step copies them H2D into its static buffers
         loss, _, _ = trainer.step(b["pixel_values"], b["heatmaps"], b["keypoints"], b["z"])
-        return loss.cpu()          # device -> host read of the step's result
+        return loss.cpu()          # device -> host read of the step's result (a 4-byte D2H copy + sync)
 
     def barrier():
         if world > 1:
@@ -209,14 +209,15 @@ def run_ours(args):
     roof = None
     launches = 0
     if rank == 0:
-        eng = model._get_engine(dev)
-        plan = eng.get_plan(B, 224, 224, True)
-        launches = len(plan["fwd"]) + len(plan["bwd"])
+        st = trainer._steps[(B, 224, 224)]
+        plan = st["plan"]
+        progs = [plan["fwd"], st["loss"], plan["bwd"], st["opt"]]
+        launches = sum(len(p) for p in progs)
         agg = {}
         reps = 3
         per_launch = {}
         for _ in range(reps):
-            recs = plan["fwd"].run_timed() + plan["bwd"].run_timed()
+            recs = [r for p in progs for r in p.run_timed()]
             for i, rec in enumerate(recs):
                 pl = per_launch.setdefault(i, dict(rec, ms=0.0))
                 pl["ms"] += rec["ms"] / reps
@@ -266,7 +267,8 @@ def run_ours(args):
                        "global_batch": total_b, "parallelism": f"dp{world}",
                        "l2": "per-step working set (activations + saved tensors > 1 GB) exceeds the 126 MB L2; "
                              "no explicit flush",
-                       "step": "fwd + reference losses + bwd (heads, final LN, last-block MLP, LoRA) + AdamW"},
+                       "step": "fwd + reference losses + bwd (heads, final LN, last-block MLP, LoRA) + AdamW, replayed as "
+                               "one CUDA graph" if trainer.use_graph else "fwd + losses + bwd + AdamW (eager launches)"},
             "per_gpu": B / (ms_step * 1e-3),
             "e2e": {"value": total_b / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},

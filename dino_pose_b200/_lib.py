@@ -100,6 +100,8 @@ SIGNATURES = {
     "dp_sgemm_small": [c_vp, c_ll, c_ll, c_vp, c_ll, c_ll, c_vp, c_ll, i, i, i, c_vp, i, c_vp, c_ll, f, c_vp, i, c_vp],
     "dp_colsum": [c_vp, i, c_vp, c_ll, i, c_ll, c_vp],
     "dp_relu_mask": [c_vp, c_vp, c_vp, c_ll, f, c_vp],
+    "dp_pose_loss": [c_vp, c_vp, c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, i, i, f, f, c_vp],
+    "dp_adamw": [c_vp, c_vp, c_vp, c_vp, c_ll, f, f, f, f, f, f, c_vp, c_vp],
 }
 _RESTYPES = {"dp_last_error": C.c_char_p}
 

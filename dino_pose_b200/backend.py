@@ -48,9 +48,10 @@ class Program:
         self.meta = []        # per call: kernel family, algorithmic FLOPs / bytes (roofline accounting)
         self.lib = _lib.lib()
 
-    def add(self, name, fn, *args, keep=(), kernel=None, flops=0.0, bytes=0.0):
+    def add(self, name, fn, *args, keep=(), kernel=None, flops=0.0, bytes=0.0, launches=1):
         self.calls.append((fn, args, name))
-        self.meta.append({"name": name, "kernel": kernel or name, "flops": float(flops), "bytes": float(bytes)})
+        self.meta.append({"name": name, "kernel": kernel or name, "flops": float(flops), "bytes": float(bytes),
+                          "launches": launches})
         self.keep.extend(keep)
 
     def add_callable(self, name, fn):
@@ -58,14 +59,25 @@ class Program:
         self.calls.append((None, fn, name))
         self.meta.append({"name": name, "kernel": "host:" + name, "flops": 0.0, "bytes": 0.0})
 
-    def __len__(self):
-        return sum(1 for fn, _a, _n in self.calls if fn is not None)
+    def add_mark(self, tag):
+        """A named point in the program (e.g. "gradients up to offset N are final"); ``run(on_mark=f)`` calls
+        ``f(tag)`` there -- the trainer uses it to start bucketed all-reduces while the backward continues."""
+        self.calls.append((None, tag, "mark"))
+        self.meta.append({"name": "mark", "kernel": "host:mark", "flops": 0.0, "bytes": 0.0})
 
-    def run(self):
+    def __len__(self):
+        """number of kernel launches of this library per run"""
+        return sum(m.get("launches", 1) for (fn, _a, _n), m in zip(self.calls, self.meta) if fn is not None)
+
+    def run(self, on_mark=None):
         stream = torch.cuda.current_stream().cuda_stream
         for fn, args, name in self.calls:
             if fn is None:
-                args()
+                if name == "mark":
+                    if on_mark is not None:
+                        on_mark(args)
+                else:
+                    args()
                 continue
             rc = fn(*args, stream)
             if rc != 0:
@@ -78,7 +90,8 @@ class Program:
         evs = []
         for (fn, args, name), meta in zip(self.calls, self.meta):
             if fn is None:
-                args()
+                if name != "mark":
+                    args()
                 continue
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -295,6 +308,24 @@ class CudaBackend:
     def colsum(self, x, out, *, P, C, ld):
         self.prog.add("colsum", self.lib.dp_colsum, _p(x), int(x.dtype == torch.bfloat16), _p(out), P, C, ld,
                       keep=(x, out))
+
+    # ------------------------------------------------------------------ training step around the model
+    def pose_loss(self, hm, thm, kps, z, tz, sums, state, out, scales, dhm, dz, *, B, K, HW, momentum=0.9, rate=0.1):
+        for t, nm in ((hm, "heatmaps"), (thm, "target_heatmaps"), (kps, "keypoints"), (z, "z"), (tz, "target_z"),
+                      (dhm, "d_heatmaps"), (dz, "d_z")):
+            _chk(t, torch.float32, "pose_loss." + nm)
+        self.prog.add("pose_loss", self.lib.dp_pose_loss, _p(hm), _p(thm), _p(kps), kps.shape[-1], _p(z), _p(tz), _p(sums),
+                      _p(state), _p(out), _p(scales), _p(dhm), _p(dz), B, K, HW, momentum, rate,
+                      keep=(hm, thm, kps, z, tz, sums, state, out, scales, dhm, dz), bytes=B * K * HW * 4.0 * 5, launches=3)
+
+    def adamw(self, p, g, m, v, step_dev, *, n, lr, beta1, beta2, eps, weight_decay, grad_scale):
+        for t, nm in ((p, "params"), (g, "grads"), (m, "exp_avg"), (v, "exp_avg_sq")):
+            _chk(t, torch.float32, "adamw." + nm)
+        self.prog.add("adamw", self.lib.dp_adamw, _p(p), _p(g), _p(m), _p(v), n, lr, beta1, beta2, eps, weight_decay,
+                      grad_scale, _p(step_dev), keep=(p, g, m, v, step_dev), bytes=n * 4.0 * 7, launches=2)
+
+    def mark(self, tag):
+        self.prog.add_mark(tag)
 
     # ------------------------------------------------------------------ host-side steps on static tensors
     def host(self, name, fn):

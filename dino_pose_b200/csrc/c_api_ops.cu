@@ -201,3 +201,26 @@ extern "C" int dp_relu_mask(const float* d, const float* ref, float* out, long l
   if (!d || !ref || !out) return set_error(-1, "dp_relu_mask: bad args");
   return cuda_error(launch_relu_mask(d, ref, out, n, keep_scale, ST), "dp_relu_mask");
 }
+
+namespace dp {
+cudaError_t launch_pose_loss(const float*, const float*, const float*, int, const float*, const float*, double*, float*, float*,
+                             float*, float*, float*, int, int, int, float, float, int, cudaStream_t);
+cudaError_t launch_adamw(float*, const float*, float*, float*, long long, float, float, float, float, float, float, long long*,
+                         int, cudaStream_t);
+}  // namespace dp
+extern "C" int dp_pose_loss(const float* heatmaps, const float* target_heatmaps, const float* keypoints, int kp_stride,
+                            const float* z, const float* target_z, double* sums, float* state, float* out, float* scales,
+                            float* d_heatmaps, float* d_z, int B, int K, int HW, float momentum, float rate, void* stream) {
+  if (!heatmaps || !target_heatmaps || !keypoints || !z || !target_z || !sums || !state || !out || !scales || !d_heatmaps || !d_z)
+    return set_error(-1, "dp_pose_loss: null pointer");
+  if (B <= 0 || K <= 0 || HW <= 0 || (HW % 4) || kp_stride < 3) return set_error(-2, "dp_pose_loss: bad shape");
+  return cuda_error(launch_pose_loss(heatmaps, target_heatmaps, keypoints, kp_stride, z, target_z, sums, state, out, scales,
+                                     d_heatmaps, d_z, B, K, HW, momentum, rate, sm_count(), ST), "dp_pose_loss");
+}
+extern "C" int dp_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                        float beta2, float eps, float weight_decay, float grad_scale, long long* step_dev, void* stream) {
+  if (!params || !grads || !exp_avg || !exp_avg_sq || !step_dev) return set_error(-1, "dp_adamw: null pointer");
+  if (n <= 0 || (n % 4)) return set_error(-2, "dp_adamw: n must be a positive multiple of 4");
+  return cuda_error(launch_adamw(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_scale,
+                                 step_dev, sm_count(), ST), "dp_adamw");
+}

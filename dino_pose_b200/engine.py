@@ -99,6 +99,45 @@ class PoseEngine:
                 out.append(n)
         return out
 
+    # ------------------------------------------------------------------ flat gradient / parameter layout
+    BWD_LAYER_ORDER = ("pred3", "pred0", "ups1", "ups0", "fr4", "up2", "up1", "bt2", "bt1", "down2", "down1", "pw", "dw",
+                       "skip", "fr0")
+    GRAD_ALIGN = 64   # elements (256 B): every parameter's slice can be used as a 16-byte vector / TMA base
+
+    def layout(self):
+        """Order and offsets of the trainable parameters in the flat gradient buffer (and in the trainer's flat
+        parameter / AdamW-state buffers): the order in which the backward program FINISHES them, so that a prefix
+        of the buffer is final at every ``mark`` and can be all-reduced while the rest is still being computed."""
+        if getattr(self, "_layout", None) is not None:
+            return self._layout
+        trainable = set(self.trainable_names())
+        Ls = self.build_head_layers(16)
+        order = []
+        for key in self.BWD_LAYER_ORDER:
+            L = Ls[key]
+            group = ([L.bn + ".weight", L.bn + ".bias"] if L.bn else []) + [L.name + ".weight", L.name + ".bias"]
+            order.append((key, [n for n in group if n in trainable]))
+        nz = len(self.cfg["z_hidden"]) + 1
+        zg = []
+        for j in reversed(range(nz)):
+            zg += [f"pose_heads.z_head.mlp.{3 * j}.weight", f"pose_heads.z_head.mlp.{3 * j}.bias"]
+        order.append(("z_head", [n for n in zg if n in trainable]))
+        lg = [self.lora_prefix + "lora_A", self.lora_prefix + "lora_B"] if self.lora else []
+        order.append(("lora", [n for n in lg if n in trainable]))
+        seen = {n for _k, g in order for n in g}
+        rest = [n for n in self.trainable_names() if n not in seen]
+        if rest:
+            order.append(("other", rest))
+        offsets, ends, off = {}, {}, 0
+        for key, group in order:
+            for n in group:
+                k = self.P[n].numel()
+                offsets[n] = (off, k)
+                off += _ceil(k, self.GRAD_ALIGN) * self.GRAD_ALIGN
+            ends[key] = off
+        self._layout = {"names": [n for _k, g in order for n in g], "offsets": offsets, "group_end": ends, "total": off}
+        return self._layout
+
     # ------------------------------------------------------------------ frozen weight packing
     def pack_frozen(self):
         """bf16 K-major copies of the frozen backbone weights (plain torch layout ops, run once and
@@ -571,15 +610,16 @@ class PoseEngine:
         B, g, N, T, M = plan["B"], plan["g"], plan["N"], plan["T"], plan["M"]
         D, K = self.D, self.K
         t, a, r, Ls = plan["t"], plan["a"], plan["raw"], plan["layers"]
-        names = self.trainable_names()
-        total = sum(self.P[n].numel() for n in names)
-        flat = plan["gflat"] = self.new((total,), F32)
+        lay = self.layout()
+        flat = plan["gflat"] = self.new((lay["total"],), F32)
         G = plan["grads"] = {}
-        off = 0
-        for n in names:
-            k = self.P[n].numel()
+        for n in lay["names"]:
+            off, k = lay["offsets"][n]
             G[n] = flat[off:off + k].view(self.P[n].shape)
-            off += k
+
+        def done(key):
+            # every gradient in flat[:group_end[key]] is final from here on
+            be.mark(("grads_final", lay["group_end"][key]))
         t["dhm"] = self.new(tuple(t["hm"].shape), F32)
         t["dz"] = self.new((B, K), F32)
         be.host("zero_grads", flat.zero_)
@@ -676,6 +716,7 @@ class PoseEngine:
         d = conv_bwd("ups1", bn_bwd("ups1", d), a["ups0"])
         d = conv_bwd("ups0", bn_bwd("ups0", d), a["fr4"])
         d_hg = conv_bwd("fr4", bn_bwd("fr4", d), plan["hgout"])
+        done("fr4")
         # ---- hourglass (three consumers of d_hg: up2, skip, depthwise branch)
         d = conv_bwd("up2", bn_bwd("up2", d_hg, shuffle=True), a["up1"])
         d = conv_bwd("up1", bn_bwd("up1", d, shuffle=True), a["bt2"])
@@ -685,6 +726,7 @@ class PoseEngine:
         d = conv_bwd("bt1", bn_bwd("bt1", d), a["down2"], dx_residual=dres)
         d = conv_bwd("down2", bn_bwd("down2", d), a["down1"])
         d_a1 = conv_bwd("down1", bn_bwd("down1", d), a["fr0"])
+        done("down1")
         # depthwise branch
         d = conv_bwd("pw", bn_bwd("pw", d_hg), a["dw"])
         ddw = bn_bwd("dw", d)
@@ -695,6 +737,7 @@ class PoseEngine:
         # skip branch, accumulating into the running gradient of a1
         d_a1c = conv_bwd("skip", bn_bwd("skip", d_hg), a["fr0"], dx_residual=d_a1b)
         dfeat = conv_bwd("fr0", bn_bwd("fr0", d_a1c), t["feat"].view(B, g, g, D))
+        done("fr0")
         # ---- z head
         dims = plan["zdims"]
         zp = "pose_heads.z_head.mlp."
@@ -716,6 +759,7 @@ class PoseEngine:
                            K=dims[j + 1])
             dcur = dx
         be.mean_tokens_bwd(dfeat, dcur, B=B, N=N, D=D)
+        done("z_head")
         if not self.lora:
             return
         # ---- backbone: final LayerNorm, last block's MLP branch, LoRA adapter
@@ -736,6 +780,7 @@ class PoseEngine:
                     G[self.lora_prefix + "lora_A"], G[self.lora_prefix + "lora_B"], t["gu"], rows=M, D=D, R=self.lora["rank"],
                     scaling=self.lora["alpha"] / self.lora["rank"], p_drop=float(self.lora.get("dropout", 0.0)),
                     seed=self.seed)
+        be.mark(("grads_final", lay["total"]))
 
     # ------------------------------------------------------------------ running
     def check_frozen(self):
@@ -757,15 +802,19 @@ class PoseEngine:
         plan["fwd"].run()
         return plan
 
-    def backward(self, plan, dhm, dz):
+    def backward(self, plan, dhm, dz, on_mark=None):
+        """dhm / dz: gradients w.r.t. the outputs (copied into the plan's static seed buffers), or the strings
+        "static" when a kernel (dp_pose_loss) already wrote plan["t"]["dhm"] / ["dz"] in place."""
         t = plan["t"]
-        if dhm is None:
-            t["dhm"].zero_()
-        else:
-            t["dhm"].copy_(dhm)
-        if dz is None:
-            t["dz"].zero_()
-        else:
-            t["dz"].copy_(dz)
-        plan["bwd"].run()
+        if not isinstance(dhm, str):
+            if dhm is None:
+                t["dhm"].zero_()
+            else:
+                t["dhm"].copy_(dhm)
+        if not isinstance(dz, str):
+            if dz is None:
+                t["dz"].zero_()
+            else:
+                t["dz"].copy_(dz)
+        plan["bwd"].run(on_mark=on_mark)
         return plan["grads"]

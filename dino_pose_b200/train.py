@@ -4,11 +4,16 @@ One ``PoseTrainer.step`` = ``optimizer.zero_grad`` -> ``model(pixel_values)`` ->
 (``keypoint_loss`` train.py:89-102, ``z_loss`` :109-120, ``DynamicLossWeighting`` :17-69) -> backward ->
 gradient all-reduce (world_size > 1) -> AdamW(lr 3e-5, wd 1e-6; train.py:280-284).
 
-Differences from the reference loop, all deliberate:
-  * the loss-weight EMA state lives on the device -- the reference's 7 ``.item()`` host syncs per step
-    (train.py:155-156,173-178) would cap multi-GPU scaling; the arithmetic is unchanged;
-  * gradients of all trainable parameters live in ONE flat fp32 buffer written by the backward program, so
-    the data-parallel exchange is a single bucketed NCCL all-reduce over NVLink of 31 MB (ViT-S);
+How it differs from the reference loop, all deliberate:
+  * the whole step is ONE CUDA graph: forward program, ``dp_pose_loss`` (loss + backward seed, loss-weight EMA
+    state on the device -- the reference's 7 ``.item()`` host syncs per step, train.py:155-156,173-178, would cap
+    multi-GPU scaling), backward program, bucketed NCCL all-reduce, ``dp_adamw``.  The arithmetic is the reference's;
+  * the trainable parameters (heads + LoRA) are re-homed as views into ONE flat fp32 buffer, laid out in the order
+    the backward program finishes their gradients (``PoseEngine.layout``); gradients and AdamW moments use the same
+    layout, so the optimizer is one element-wise kernel and a gradient bucket is a contiguous slice;
+  * data parallelism: one process per GPU, the batch dimension is sharded, only these ~31 MB (ViT-S) of fp32
+    gradients cross NVLink; every bucket's all-reduce is launched on a side stream as soon as the backward has
+    finished that prefix of the flat buffer and overlaps the rest of the backward;
   * BatchNorm uses per-replica batch statistics (torch DDP default); running statistics are per rank.
 """
 from __future__ import annotations
@@ -17,32 +22,8 @@ import torch
 import torch.distributed as dist
 
 
-class DeviceLossWeighting:
-    """``DynamicLossWeighting`` (reference train.py:17-87) with tensor state (no host round trips)."""
-
-    def __init__(self, device, initial_weight=0.1, adjustment_rate=0.1, momentum=0.9):
-        self.weight = torch.tensor(float(initial_weight), device=device)
-        self.kp_avg = torch.zeros((), device=device)
-        self.z_avg = torch.zeros((), device=device)
-        self.started = torch.zeros((), device=device)
-        self.rate, self.momentum = adjustment_rate, momentum
-
-    @torch.no_grad()
-    def update(self, kp, z):
-        m = self.momentum
-        first = 1.0 - self.started
-        self.kp_avg.copy_(first * kp + self.started * (m * self.kp_avg + (1 - m) * kp))
-        self.z_avg.copy_(first * z + self.started * (m * self.z_avg + (1 - m) * z))
-        self.started.fill_(1.0)
-        target = (kp + 1e-8) / (z + 1e-8)
-        self.weight.copy_(((1 - self.rate) * self.weight + self.rate * target).clamp(1e-3, 10.0))
-
-    def balanced(self, kp_loss, z_loss):
-        return kp_loss / (self.kp_avg + 1e-8) + z_loss / (self.z_avg + 1e-8)
-
-
 def keypoint_loss(pred, target, conf):
-    """reference train.py:89-102."""
+    """reference train.py:89-102 (torch form, used by tests and by callers that own their loop)."""
     mask = (conf > 1).to(pred.dtype)[:, :, None, None]
     diff = (pred - target) ** 2
     return (torch.exp(-diff.detach()) * diff * mask).mean()
@@ -55,52 +36,158 @@ def z_loss(pred_z, target_z, conf):
 
 
 class PoseTrainer:
-    def __init__(self, model, lr=3e-5, weight_decay=1e-6, bucket_mb=8.0):
+    """AdamW fine-tuning of a ``Dinov2PoseModelLoRA`` / ``Dinov2PoseModel`` on this rank's shard of the batch.
+
+    ``step(pixel_values, target_heatmaps, keypoints, target_z)`` returns ``(loss, kp_loss, z_loss)`` as device
+    scalars (views of a static 3-float buffer: read them before the next step, or ``.clone()``)."""
+
+    def __init__(self, model, lr=3e-5, weight_decay=1e-6, betas=(0.9, 0.999), eps=1e-8, bucket_mb=8.0, use_graph=True,
+                 process_group=None):
         self.model = model
         self.device = next(model.parameters()).device
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
-        self.weighting = DeviceLossWeighting(self.device)
-        self.params = [p for p in model.parameters() if p.requires_grad]
-        self.names = [n for n, p in model.named_parameters() if p.requires_grad]
-        self.opt = torch.optim.AdamW(self.params, lr=lr, weight_decay=weight_decay, fused=self.device.type == "cuda")
-        self.bucket_elems = int(bucket_mb * (1 << 20) / 4)
-        self._bound_plan = None
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
+        self.use_graph = use_graph and self.device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=self.device) if (self.world > 1 and self.device.type == "cuda") else None
+        self.buckets_sent = []          # [(lo, hi)] of the last step, for tests / introspection
+        self._flatten_parameters()
+        dev = self.device
+        n = self.layout["total"]
+        self.exp_avg = torch.zeros(n, device=dev)
+        self.exp_avg_sq = torch.zeros(n, device=dev)
+        self.step_dev = torch.zeros((), dtype=torch.int64, device=dev)
+        self.loss_sums = torch.zeros(2, dtype=torch.float64, device=dev)
+        self.loss_state = torch.tensor([0.0, 0.0, 0.0, 0.1], device=dev)   # kp_avg, z_avg, started, weight (train.py:18)
+        self.loss_out = torch.zeros(3, device=dev)
+        self.loss_scales = torch.zeros(2, device=dev)
+        self._steps = {}     # (B, H, W) -> dict(plan, programs, static inputs, graph)
 
-    def _bind_grads(self, plan):
-        """Point every ``param.grad`` at its slice of the plan's flat gradient buffer (no copies)."""
-        if self._bound_plan is plan:
-            return
-        for n, p in zip(self.names, self.params):
-            p.grad = plan["grads"][n]
-        self._bound_plan = plan
-
-    def _allreduce(self, flat):
-        n = flat.numel()
-        handles = []
-        for s in range(0, n, self.bucket_elems):
-            handles.append(dist.all_reduce(flat[s:min(n, s + self.bucket_elems)], op=dist.ReduceOp.SUM, async_op=True))
-        for h in handles:
-            h.wait()
-        flat.mul_(1.0 / self.world)
-
-    def step(self, pixel_values, target_heatmaps, keypoints, target_z):
-        """One fine-tuning step on this rank's shard.  Returns (loss, kp_loss, z_loss) device scalars."""
+    # ------------------------------------------------------------------ parameters
+    def _flatten_parameters(self):
         model = self.model
         model.train()
         eng = model._get_engine(self.device)
-        plan = eng.forward(pixel_values, training=True)
-        hm = plan["t"]["hm"].detach().requires_grad_(True)
-        z = plan["t"]["z"].detach().requires_grad_(True)
-        conf = keypoints[..., 2]
-        kp = keypoint_loss(hm, target_heatmaps, conf)
-        zl = z_loss(z, target_z, conf)
-        self.weighting.update(kp.detach(), zl.detach())
-        loss = self.weighting.balanced(kp, zl)
-        dhm, dz = torch.autograd.grad(loss, (hm, z))
-        eng.backward(plan, dhm, dz)
-        if self.world > 1:
-            self._allreduce(plan["gflat"])
-        self._bind_grads(plan)
-        self.opt.step()
-        return loss.detach(), kp.detach(), zl.detach()
+        self.layout = lay = eng.layout()
+        flat = torch.zeros(lay["total"], device=self.device)
+        params = dict(model.named_parameters())
+        with torch.no_grad():
+            for name in lay["names"]:
+                off, k = lay["offsets"][name]
+                p = params[name]
+                flat[off:off + k].copy_(p.detach().reshape(-1))
+                p.data = flat[off:off + k].view(p.shape)
+        self.flat_params = flat
+        model._engine = None        # plans recorded on the old parameter storage are stale
+        self.engine = model._get_engine(self.device)
+
+    @property
+    def weighting_state(self):
+        """(kp_loss_avg, z_loss_avg, weight) of the reference's DynamicLossWeighting, read back from the device."""
+        s = self.loss_state.tolist()
+        return {"kp_loss_avg": s[0] if s[2] else None, "z_loss_avg": s[1] if s[2] else None, "weight": s[3]}
+
+    # ------------------------------------------------------------------ step construction
+    def _build(self, B, H, W):
+        eng, be, dev = self.engine, self.engine.be, self.device
+        plan = eng.get_plan(B, H, W, True)
+        K, hm = eng.K, plan["t"]["hm"]
+        st = {"plan": plan}
+        st["thm"] = torch.zeros_like(hm)
+        st["kps"] = torch.zeros(B, K, 3, device=dev)
+        st["tz"] = torch.zeros(B, K, device=dev)
+        st["loss"] = be.begin()
+        be.pose_loss(hm, st["thm"], st["kps"], plan["t"]["z"], st["tz"], self.loss_sums, self.loss_state, self.loss_out,
+                     self.loss_scales, plan["t"]["dhm"], plan["t"]["dz"], B=B, K=K, HW=hm.shape[2] * hm.shape[3])
+        st["opt"] = be.begin()
+        be.adamw(self.flat_params, plan["gflat"], self.exp_avg, self.exp_avg_sq, self.step_dev, n=self.layout["total"],
+                 lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.wd,
+                 grad_scale=1.0 / self.world)
+        st["graph"] = None
+        return st
+
+    def _on_mark(self, flat):
+        """Bucketing: called by the backward program when flat[:upto] is final."""
+        sent = [0]
+        total = flat.numel()
+        self.buckets_sent = []
+
+        def on_mark(tag):
+            kind, upto = tag
+            if kind != "grads_final" or self.world == 1:
+                return
+            if upto - sent[0] < self.bucket_elems and upto < total:
+                return
+            lo, hi = sent[0], upto
+            if hi <= lo:
+                return
+            sent[0] = hi
+            self.buckets_sent.append((lo, hi))
+            if self.comm_stream is not None:
+                cur = torch.cuda.current_stream()
+                self.comm_stream.wait_stream(cur)
+                with torch.cuda.stream(self.comm_stream):
+                    dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+            else:   # CPU (gloo) test path
+                dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+        return on_mark
+
+    @torch.no_grad()
+    def _run(self, st):
+        """forward -> loss + seeds -> backward (+ overlapped all-reduce) -> AdamW, on the current stream."""
+        eng, plan = self.engine, st["plan"]
+        eng.seed.add_(1)
+        plan["fwd"].run()
+        st["loss"].run()
+        eng.backward(plan, "static", "static", on_mark=self._on_mark(plan["gflat"]))
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+        st["opt"].run()
+
+    def _capture(self, st):
+        self._run(st)                     # warm-up outside capture (lazy kernel attributes, NCCL communicators)
+        self._run(st)
+        torch.cuda.synchronize(self.device)
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                self._run(st)
+        torch.cuda.current_stream().wait_stream(side)
+        st["graph"] = g
+
+    def _snapshot(self):
+        return [t.clone() for t in (self.flat_params, self.exp_avg, self.exp_avg_sq, self.step_dev, self.loss_state,
+                                    self.engine.seed)] + [b.clone() for b in self.model.buffers()]
+
+    def _restore(self, snap):
+        own = [self.flat_params, self.exp_avg, self.exp_avg_sq, self.step_dev, self.loss_state, self.engine.seed]
+        for t, s in zip(own + list(self.model.buffers()), snap):
+            t.copy_(s)
+
+    def step(self, pixel_values, target_heatmaps, keypoints, target_z):
+        """One fine-tuning step on this rank's shard.  Inputs may live on the host (pinned) or on the device."""
+        model = self.model
+        if not model.training:
+            model.train()
+        self.engine.check_frozen()
+        B, _, H, W = pixel_values.shape
+        key = (B, H, W)
+        st = self._steps.get(key)
+        if st is None or st["plan"] is not self.engine.plans.get((B, H, W, True)):
+            st = self._steps[key] = self._build(B, H, W)
+        st["plan"]["t"]["px"].copy_(pixel_values, non_blocking=True)
+        st["thm"].copy_(target_heatmaps, non_blocking=True)
+        st["kps"].copy_(keypoints, non_blocking=True)
+        st["tz"].copy_(target_z, non_blocking=True)
+        if not self.use_graph:
+            self._run(st)
+        else:
+            if st["graph"] is None:
+                snap = self._snapshot()     # the two warm-up runs and the capture must not count as training steps
+                self._capture(st)
+                self._restore(snap)
+            st["graph"].replay()
+        return self.loss_out[0], self.loss_out[1], self.loss_out[2]

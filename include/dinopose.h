@@ -169,6 +169,22 @@ int dp_colsum(const void* x, int is_bf16, float* out, long long P, int C, long l
 /* out = ref > 0 ? d * keep_scale : 0  (gradient through ReLU + inverted dropout given the saved output) */
 int dp_relu_mask(const float* d, const float* ref, float* out, long long n, float keep_scale, void* stream);
 
+/* ---------------------------------------------------------------- training step around the model */
+/* Reference losses + their backward seed (train.py:89-120, DynamicLossWeighting :17-69), state on the device.
+ * heatmaps / target_heatmaps fp32 [B,K,HW]; keypoints fp32 [B*K, kp_stride] with the visibility at column 2
+ * (mask = visibility > 1, train.py:94,114); z / target_z fp32 [B,K].
+ * sums fp64[2] (zero on entry, re-zeroed); state fp32[4] = {kp_avg, z_avg, started, weight} (init {0,0,0,0.1});
+ * out fp32[3] = {balanced loss, keypoint loss, z loss}; scales fp32[2] workspace;
+ * d_heatmaps [B,K,HW], d_z [B,K] = d(balanced loss)/d(heatmaps), /d(z).  HW % 4 == 0. */
+int dp_pose_loss(const float* heatmaps, const float* target_heatmaps, const float* keypoints, int kp_stride,
+                 const float* z, const float* target_z, double* sums, float* state, float* out, float* scales,
+                 float* d_heatmaps, float* d_z, int B, int K, int HW, float momentum, float rate, void* stream);
+/* torch.optim.AdamW step (train.py:280-284,170) over flat fp32 buffers of n elements (n % 4 == 0, 16-byte
+ * aligned); gradients are multiplied by grad_scale first (1/world_size after the all-reduce); step_dev is a
+ * device int64 holding the number of steps taken so far and is incremented. */
+int dp_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+             float beta2, float eps, float weight_decay, float grad_scale, long long* step_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

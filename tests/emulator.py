@@ -21,9 +21,13 @@ class EmuProgram:
     def __len__(self):
         return len(self.calls)
 
-    def run(self):
+    def run(self, on_mark=None):
         for fn in self.calls:
-            fn()
+            if isinstance(fn, tuple):
+                if on_mark is not None:
+                    on_mark(fn[1])
+            else:
+                fn()
 
 
 class TorchEmulator:
@@ -37,6 +41,45 @@ class TorchEmulator:
         return self.prog
 
     def host(self, name, fn):
+        self.prog.calls.append(fn)
+
+    def mark(self, tag):
+        self.prog.calls.append(("mark", tag))
+
+    # ------------------------------------------------------------------ training step around the model
+    def pose_loss(self, hm, thm, kps, z, tz, sums, state, out, scales, dhm, dz, *, B, K, HW, momentum=0.9, rate=0.1):
+        def fn():
+            mask = (kps[..., 2] > 1).float()
+            d = hm.view(B, K, HW) - thm.view(B, K, HW)
+            q = d * d
+            kp = (torch.exp(-q) * q * mask.view(B, K, 1)).double().sum() / (B * K * HW)
+            zd = z * mask.view(B, K) - tz * mask.view(B, K)
+            zl = zd.abs().double().sum() / (B * K)
+            kp, zl = kp.float(), zl.float()
+            if state[2] == 0:
+                kp_avg, z_avg = kp, zl
+            else:
+                kp_avg = momentum * state[0] + (1 - momentum) * kp
+                z_avg = momentum * state[1] + (1 - momentum) * zl
+            w = ((1 - rate) * state[3] + rate * (kp + 1e-8) / (zl + 1e-8)).clamp(1e-3, 10.0)
+            state[0], state[1], state[2], state[3] = kp_avg, z_avg, 1.0, w
+            out[0], out[1], out[2] = kp / (kp_avg + 1e-8) + zl / (z_avg + 1e-8), kp, zl
+            s0 = 2.0 / (B * K * HW * (kp_avg + 1e-8))
+            s1 = 1.0 / (B * K * (z_avg + 1e-8))
+            dhm.view(B, K, HW).copy_(s0 * torch.exp(-q) * d * mask.view(B, K, 1))
+            dz.view(B, K).copy_(s1 * mask.view(B, K) * torch.sign(zd))
+        self.prog.calls.append(fn)
+
+    def adamw(self, p, g, m, v, step_dev, *, n, lr, beta1, beta2, eps, weight_decay, grad_scale):
+        def fn():
+            t = int(step_dev.item()) + 1
+            gg = g[:n] * grad_scale
+            p[:n].mul_(1 - lr * weight_decay)
+            m[:n].mul_(beta1).add_(gg, alpha=1 - beta1)
+            v[:n].mul_(beta2).addcmul_(gg, gg, value=1 - beta2)
+            denom = v[:n].sqrt() / (1 - beta2 ** t) ** 0.5 + eps
+            p[:n].addcdiv_(m[:n], denom, value=-lr / (1 - beta1 ** t))
+            step_dev.add_(1)
         self.prog.calls.append(fn)
 
     # ------------------------------------------------------------------ GEMM family

@@ -506,3 +506,53 @@ def test_sgemm_small():
     dw = torch.zeros(N, K, device=dev())
     run(lambda b: b.sgemm_small(dpre, 1, N, x, K, 1, dw, K, M=N, N=K, K=M))
     assert rel(dw, dpre.t() @ x) < 1e-5
+
+
+# ---------------------------------------------------------------------------------- training-step kernels
+def test_pose_loss_and_seeds_vs_torch():
+    """dp_pose_loss vs the reference losses (train.py:89-120) + DynamicLossWeighting (:17-69) through autograd,
+    over two steps (the second exercises the EMA state kept on the device)."""
+    from oracle import pose_oracle
+    B, K, HW = 5, 24, 48 * 48
+    sums = torch.zeros(2, device=dev(), dtype=torch.float64)
+    state = torch.tensor([0.0, 0.0, 0.0, 0.1], device=dev())
+    out, scales = torch.zeros(3, device=dev()), torch.zeros(2, device=dev())
+    w = pose_oracle.DynamicLossWeighting()
+    for step in range(2):
+        hm = rnd(B, K, 48, 48, seed=step)
+        thm = rnd(B, K, 48, 48, seed=10 + step).abs()
+        kps = torch.cat([rnd(B, K, 2, seed=20 + step), torch.randint(0, 3, (B, K, 1), device=dev()).float()], -1).contiguous()
+        z, tz = rnd(B, K, seed=30 + step), rnd(B, K, seed=40 + step)
+        dhm, dz = torch.zeros_like(hm), torch.zeros_like(z)
+        run(lambda b: b.pose_loss(hm, thm, kps, z, tz, sums, state, out, scales, dhm, dz, B=B, K=K, HW=HW))
+        hm_r, z_r = hm.clone().requires_grad_(True), z.clone().requires_grad_(True)
+        conf = kps[..., 2]
+        kp, zl = pose_oracle.keypoint_loss(hm_r, thm, conf), pose_oracle.z_loss(z_r, tz, conf)
+        w.update(kp.item(), zl.item())
+        loss = w.balanced(kp, zl)
+        g_hm, g_z = torch.autograd.grad(loss, (hm_r, z_r))
+        assert abs(out[0].item() - loss.item()) < 1e-5 * abs(loss.item())
+        assert abs(out[1].item() - kp.item()) < 1e-5 * abs(kp.item())
+        assert abs(out[2].item() - zl.item()) < 1e-5 * abs(zl.item())
+        assert rel(dhm, g_hm) < 1e-4
+        assert rel(dz, g_z) < 1e-5
+        assert sums.abs().max().item() == 0
+    assert abs(state[3].item() - w.weight) < 1e-5
+
+
+def test_adamw_vs_torch():
+    n = 4096 * 5 + 64
+    p0, lr, wd, eps = rnd(n, seed=1), 3e-3, 1e-2, 1e-8
+    p = p0.clone()
+    m, v = torch.zeros(n, device=dev()), torch.zeros(n, device=dev())
+    step = torch.zeros((), dtype=torch.int64, device=dev())
+    ref = p0.clone().requires_grad_(True)
+    opt = torch.optim.AdamW([ref], lr=lr, weight_decay=wd, eps=eps)
+    for s in range(4):
+        g = rnd(n, seed=50 + s, scale=0.1)
+        run(lambda b: b.adamw(p, g, m, v, step, n=n, lr=lr, beta1=0.9, beta2=0.999, eps=eps, weight_decay=wd,
+                              grad_scale=0.5))
+        ref.grad = g * 0.5
+        opt.step()
+        assert rel(p, ref.detach()) < 2e-6, s
+    assert int(step.item()) == 4

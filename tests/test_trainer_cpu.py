@@ -1,0 +1,140 @@
+"""Host logic of the fine-tuning step (CPU, torch emulator of the C-ABI ops, fp32 storage): the fused loss /
+AdamW / flat-parameter trainer against the reference loop (oracle forward + train.py losses + torch AdamW), and the
+data-parallel path on world_size 2 over gloo (bucketed all-reduce of the flat gradient buffer)."""
+import os
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import pose_oracle
+from oracle.weights import make_inputs, make_state_dict
+from tests.emulator import TorchEmulator
+
+from dino_pose_b200.model import Dinov2PoseModelLoRA
+from dino_pose_b200.train import PoseTrainer
+
+ARCH = "test/dinov2-tiny"
+
+
+def build_model(seed=0):
+    m = Dinov2PoseModelLoRA(backbone=ARCH, lora_rank=8, lora_alpha=16, lora_dropout=0.0)
+    m.load_state_dict(make_state_dict(ARCH, seed, 8))
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    m._backend_factory = TorchEmulator
+    m._act_dtype = torch.float32
+    return m.train()
+
+
+def reference_loop(batches, lr, wd, steps, eps):
+    sd = make_state_dict(ARCH, 0, 8)
+    lora = {"rank": 8, "alpha": 16, "dropout": 0.0}
+    names = pose_oracle.trainable_names(sd, lora)
+    params = [sd[n].requires_grad_(True) for n in names]
+    opt = torch.optim.AdamW(params, lr=lr, weight_decay=wd, eps=eps)
+    w = pose_oracle.DynamicLossWeighting()
+    losses = []
+    for s in range(steps):
+        b = batches[s]
+        opt.zero_grad(set_to_none=True)
+        hm, z = pose_oracle.model_forward(sd, b["pixel_values"], ARCH, lora, training=True)
+        conf = b["keypoints"][..., 2]
+        kp, zl = pose_oracle.keypoint_loss(hm, b["heatmaps"], conf), pose_oracle.z_loss(z, b["z"], conf)
+        w.update(kp.item(), zl.item())
+        loss = w.balanced(kp, zl)
+        loss.backward()
+        opt.step()
+        losses.append((loss.item(), kp.item(), zl.item()))
+    return sd, names, losses, w
+
+
+def test_trainer_matches_reference_loop():
+    # eps is large on purpose: with the default 1e-8 Adam turns fp32 rounding noise on (mathematically) zero
+    # gradients -- e.g. conv biases feeding a train-mode BatchNorm -- into +-lr steps, which no two correct
+    # implementations reproduce; the AdamW arithmetic itself is exercised the same way
+    lr, wd, steps, eps = 1e-3, 1e-2, 3, 1e-3
+    batches = [make_inputs(3, 224, 224, s) for s in range(steps)]
+    sd, names, ref_losses, w = reference_loop(batches, lr, wd, steps, eps)
+    m = build_model()
+    tr = PoseTrainer(m, lr=lr, weight_decay=wd, eps=eps, use_graph=False)
+    for s in range(steps):
+        b = batches[s]
+        loss, kp, zl = tr.step(b["pixel_values"], b["heatmaps"], b["keypoints"], b["z"])
+        for got, ref in zip((loss.item(), kp.item(), zl.item()), ref_losses[s]):
+            assert abs(got - ref) <= 2e-4 * abs(ref) + 1e-7, (s, got, ref)
+    params = dict(m.named_parameters())
+    init = make_state_dict(ARCH, 0, 8)
+    worst = 0.0
+    for n in names:
+        a, b = params[n].detach(), sd[n].detach()
+        moved = (b - init[n]).norm().item()
+        if moved < 1e-7:        # (mathematically) zero gradient: neither implementation moves it
+            assert (a - init[n]).norm().item() < 1e-5, n
+            continue
+        worst = max(worst, ((a - b).norm() / moved).item())   # error relative to the 3-step UPDATE
+    assert worst < 5e-2, worst   # fp32 noise of the BN-cancelling gradients through Adam (measured 2.8e-2)
+    st = tr.weighting_state
+    assert abs(st["kp_loss_avg"] - w.kp_avg) < 1e-5 * abs(w.kp_avg) + 1e-9
+    assert abs(st["weight"] - w.weight) < 1e-5
+    assert int(tr.step_dev.item()) == steps
+    # parameters are views of the flat buffer, laid out in backward-completion order
+    lay = tr.layout
+    off, k = lay["offsets"][names[0]]
+    assert params[names[0]].data_ptr() == tr.flat_params[off:].data_ptr()
+    assert set(lay["names"]) == set(names)
+
+
+def _dp_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    try:
+        full = make_inputs(4, 224, 224, 7)
+        shard = {k: v[rank * 2:(rank + 1) * 2] for k, v in full.items()}
+        # local gradient of this shard (world-1 semantics), then the data-parallel step
+        m1 = build_model()
+        t1 = PoseTrainer.__new__(PoseTrainer)      # no process group: plain single-rank trainer
+        PoseTrainer.__init__(t1, m1, lr=0.0, weight_decay=0.0, use_graph=False)
+        t1.world = 1
+        t1.step(shard["pixel_values"], shard["heatmaps"], shard["keypoints"], shard["z"])
+        g_local = t1._steps[(2, 224, 224)]["plan"]["gflat"].clone()
+        m2 = build_model()
+        t2 = PoseTrainer(m2, lr=1e-3, weight_decay=0.0, use_graph=False, bucket_mb=0.5)
+        assert t2.world == world
+        t2.step(shard["pixel_values"], shard["heatmaps"], shard["keypoints"], shard["z"])
+        g_sum = t2._steps[(2, 224, 224)]["plan"]["gflat"].clone()
+        gathered = [torch.zeros_like(g_local) for _ in range(world)]
+        dist.all_gather(gathered, g_local)
+        expect = sum(gathered)
+        err = ((g_sum - expect).norm() / expect.norm()).item()
+        # buckets: contiguous cover of the flat buffer, more than one, in increasing order
+        b = t2.buckets_sent
+        ok_cover = b[0][0] == 0 and b[-1][1] == g_sum.numel() and all(b[i][1] == b[i + 1][0] for i in range(len(b) - 1))
+        # replicas stay identical after the update
+        ps = [torch.zeros_like(t2.flat_params) for _ in range(world)]
+        dist.all_gather(ps, t2.flat_params)
+        same = bool(torch.equal(ps[0], ps[1]))
+        moved = ((t2.flat_params - t1.flat_params).abs().max() > 0).item()
+        q.put((rank, err, len(b), ok_cover, same, moved))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_data_parallel_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, nb, ok_cover, same, moved in res:
+        assert err < 1e-5, (rank, err)
+        assert nb >= 3 and ok_cover, (rank, nb)
+        assert same and moved

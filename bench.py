@@ -278,9 +278,15 @@ def run_ours(args):
             "roofline": roof,
             "cpu_baseline": cpu,
         }
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # leave together, then exit without tearing NCCL down: destroy_process_group() blocks when communicators are
+        # still referenced by captured CUDA graphs (observed: rank 0 printed its line, then both ranks hung)
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

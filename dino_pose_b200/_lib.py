@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdinopose_sm100a.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 c_ll = C.c_longlong
 c_vp = C.c_void_p
@@ -43,7 +43,7 @@ class GemmArgs(C.Structure):
         ("aux_out", c_vp), ("aux_in", c_vp),
         ("ld_aux", c_ll),
         ("row_map", C.c_int), ("n_valid", C.c_int), ("map_a", C.c_int), ("map_b", C.c_int),
-        ("stats", c_vp), ("stats_c", C.c_int),
+        ("stats", c_vp), ("stats_c", C.c_int), ("cta_pair", C.c_int),
     ]
 
 

@@ -120,7 +120,8 @@ class CudaBackend:
     # ------------------------------------------------------------------ GEMM family
     def gemm(self, A, W, out, *, M, N, K, lda=None, ldw=None, ldo=None, out_dtype="bf16", bias=None, scale=None,
              ls=None, residual=None, ldr=None, aux_out=None, aux_in=None, ld_aux=0, act="none", row_map="identity",
-             n_valid=0, map_a=0, map_b=0, conv=None, OH=0, OW=0, NB=0, block_n=0, stats=None, stats_c=0, name="gemm"):
+             n_valid=0, map_a=0, map_b=0, conv=None, OH=0, OW=0, NB=0, block_n=0, stats=None, stats_c=0, cta_pair=0,
+             name="gemm"):
         """out = epilogue(A[M,K] @ W[N,K]^T).  ``conv`` = dict(KH, KW, pad, OH, OW) makes A an NHWC
         [NB,IH,IW,C] activation (any strides with unit channel stride) read as an implicit conv."""
         _chk(W, torch.bfloat16, name + ".W", contiguous=False)
@@ -162,6 +163,7 @@ class CudaBackend:
         a.n_valid, a.map_a, a.map_b = n_valid, map_a, map_b
         _chk(stats, torch.float64, name + ".stats")
         a.stats, a.stats_c = _p(stats), stats_c
+        a.cta_pair = cta_pair
         self.prog.add(name, self.lib.dp_gemm_bf16, C.byref(a), kernel="gemm_kmajor_tcgen05", flops=2.0 * M * N * K,
                       keep=(a, A, W, out, bias, scale, ls, residual, aux_out, aux_in, stats))
 

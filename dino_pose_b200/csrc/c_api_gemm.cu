@@ -12,7 +12,12 @@
 #include "gemm_tc.cuh"
 
 namespace dp {
-cudaError_t launch_gemm(const GemmParams& p, int block_n, int grid, cudaStream_t s);
+struct GemmVariant {
+  int bn, out, act, map, opt;
+  int pair;
+  cudaError_t (*launch)(const GemmParams&, int grid, cudaStream_t);
+};
+const GemmVariant* select_gemm_variant(const Epilogue& e, int a_mode, int block_n, int pair);
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, int grid, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
@@ -112,9 +117,59 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(-2, "dp_gemm_bf16: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
   GemmParams p;
   memset(&p, 0, sizeof(p));
-  int bn = a->block_n;
-  if (bn == 0) bn = a->N >= 128 ? 128 : (a->N > 32 ? 64 : 32);
-  if (bn != 32 && bn != 64 && bn != 128 && bn != 192 && bn != 256) return set_error(-3, "dp_gemm_bf16: block_n %d", bn);
+  // ---- epilogue
+  Epilogue& e = p.epi;
+  e.out = a->out; e.bias = a->bias; e.scale = a->scale; e.ls = a->ls; e.residual = static_cast<const float*>(a->residual); e.res_is_bf16 = a->res_is_bf16;
+  e.aux_out = a->aux_out; e.aux_in = a->aux_in;
+  e.ldo = a->ldo; e.ldr = a->ldr; e.ld_aux = a->ld_aux;
+  e.out_dtype = a->out_dtype; e.act = a->act; e.row_map = a->row_map;
+  e.n_valid = a->n_valid > 0 ? a->n_valid : a->N;
+  e.map_a = a->map_a; e.map_b = a->map_b;
+  if (e.n_valid > a->N) return set_error(-6, "dp_gemm_bf16: n_valid > N");
+  if (e.row_map != DP_ROWMAP_NCHW && (e.n_valid % 4)) return set_error(-6, "dp_gemm_bf16: n_valid %% 4 != 0");
+  static int dbg = -1, allow_pair = -1;
+  if (dbg < 0) { const char* v = getenv("DP_GEMM_DEBUG"); dbg = v ? atoi(v) : 0; }
+  // CTA-pair kernels are compiled and tested but NOT chosen automatically: at the backbone shapes they measured
+  // 5-20 % slower than the single-CTA kernel (tools/gemm_tune.py); DP_GEMM_PAIR=1 or cta_pair=1 opts in
+  if (allow_pair < 0) { const char* v = getenv("DP_GEMM_PAIR"); allow_pair = v ? atoi(v) : 0; }
+  e.debug = dbg;
+  e.stats = a->stats;
+  e.stats_c = a->stats_c > 0 ? a->stats_c : e.n_valid;
+  if (e.stats && e.row_map == DP_ROWMAP_NCHW) return set_error(-6, "dp_gemm_bf16: stats with NCHW row map");
+  if (e.row_map == DP_ROWMAP_IDENTITY || e.row_map == DP_ROWMAP_PATCH_TOKENS) {
+    const long long align = (e.out_dtype == DP_OUT_BF16) ? 8 : 4;
+    if (e.ldo % align) return set_error(-7, "dp_gemm_bf16: ldo %lld must be a multiple of %lld", e.ldo, align);
+  }
+  if (e.row_map == DP_ROWMAP_SHUFFLE2X2 && (e.map_a % 32 || e.map_a <= 0))
+    return set_error(-8, "dp_gemm_bf16: shuffle map needs Cout %% 32 == 0");
+  if ((e.row_map == DP_ROWMAP_NCHW || e.row_map == DP_ROWMAP_SHUFFLE2X2) && (a->OH <= 0 || a->OW <= 0))
+    return set_error(-8, "dp_gemm_bf16: row map needs OH/OW");
+  if (e.row_map != DP_ROWMAP_NCHW) {
+    // the epilogue addresses rows with 32-bit element offsets
+    const long long out_rows = (e.row_map == DP_ROWMAP_SHUFFLE2X2) ? 4LL * a->M
+                               : (e.row_map == DP_ROWMAP_PATCH_TOKENS) ? (long long)(a->M / e.map_a + 1) * e.map_b : a->M;
+    if (out_rows * e.ldo + a->N >= 0xffffffffLL || (e.residual && (long long)a->M * e.ldr + a->N >= 0xffffffffLL) ||
+        ((e.aux_out || e.aux_in) && (long long)a->M * e.ld_aux + a->N >= 0xffffffffLL))
+      return set_error(-9, "dp_gemm_bf16: tensor too large for 32-bit epilogue offsets");
+  }
+  // ---- tile shape: CTA-pair 256 x {192, 256, 128} tiles when a variant is compiled for this epilogue and N divides,
+  // else single-CTA 128 x {128, 64, 32}.  block_n fixes the width, cta_pair (1 pair / 2 single) the kind.
+  const GemmVariant* var = nullptr;
+  const bool may_pair = (allow_pair || a->cta_pair == 1) && a->cta_pair != 2 && a->M > 128;
+  const bool may_single = a->cta_pair != 1;
+  if (a->block_n != 0) {
+    if (may_pair) var = select_gemm_variant(e, a->a_mode, a->block_n, 1);
+    if (!var && may_single) var = select_gemm_variant(e, a->a_mode, a->block_n, 0);
+  } else {
+    if (may_pair) {
+      const int cand[3] = {192, 256, 128};
+      for (int i = 0; i < 3 && !var; ++i)
+        if (a->N % cand[i] == 0 && a->N >= 2 * cand[i] - 128) var = select_gemm_variant(e, a->a_mode, cand[i], 1);
+    }
+    if (!var && may_single) var = select_gemm_variant(e, a->a_mode, a->N >= 128 ? 128 : (a->N > 32 ? 64 : 32), 0);
+  }
+  if (!var) return set_error(-3, "dp_gemm_bf16: no kernel variant for block_n %d (cta_pair %d)", a->block_n, a->cta_pair);
+  const int bn = var->bn;
   p.N = a->N;
   p.n_tiles = (a->N + bn - 1) / bn;
   p.a_mode = a->a_mode;
@@ -154,45 +209,46 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   {
     const uint64_t dims[2] = {uint64_t(a->K), uint64_t(a->N)};
     const uint64_t st[1] = {uint64_t(a->ldw) * 2};
-    const uint32_t box[2] = {64, uint32_t(bn)};
+    const uint32_t box[2] = {64, uint32_t(var->pair ? bn / 2 : bn)};   // a pair CTA stages half of the weight rows
     if ((rc = make_tmap(&p.tmB, a->W, 2, dims, st, box))) return rc;
   }
-  Epilogue& e = p.epi;
-  e.out = a->out; e.bias = a->bias; e.scale = a->scale; e.ls = a->ls; e.residual = static_cast<const float*>(a->residual); e.res_is_bf16 = a->res_is_bf16;
-  e.aux_out = a->aux_out; e.aux_in = a->aux_in;
-  e.ldo = a->ldo; e.ldr = a->ldr; e.ld_aux = a->ld_aux;
-  e.out_dtype = a->out_dtype; e.act = a->act; e.row_map = a->row_map;
-  e.n_valid = a->n_valid > 0 ? a->n_valid : a->N;
-  e.map_a = a->map_a; e.map_b = a->map_b;
-  if (e.n_valid > a->N) return set_error(-6, "dp_gemm_bf16: n_valid > N");
-  if (e.row_map != DP_ROWMAP_NCHW && (e.n_valid % 4)) return set_error(-6, "dp_gemm_bf16: n_valid %% 4 != 0");
-  {
-    static int dbg = -1;
-    if (dbg < 0) { const char* v = getenv("DP_GEMM_DEBUG"); dbg = v ? atoi(v) : 0; }
-    e.debug = dbg;
+  int grid;
+  if (var->pair) {
+    const int tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+    grid = 2 * clusters;
+  } else {
+    const int tiles = p.m_tiles * p.n_tiles;
+    grid = tiles < sm_count() ? tiles : sm_count();
   }
-  e.stats = a->stats;
-  e.stats_c = a->stats_c > 0 ? a->stats_c : e.n_valid;
-  if (e.stats && e.row_map == DP_ROWMAP_NCHW) return set_error(-6, "dp_gemm_bf16: stats with NCHW row map");
-  if (e.row_map == DP_ROWMAP_IDENTITY || e.row_map == DP_ROWMAP_PATCH_TOKENS) {
-    const long long align = (e.out_dtype == DP_OUT_BF16) ? 8 : 4;
-    if (e.ldo % align) return set_error(-7, "dp_gemm_bf16: ldo %lld must be a multiple of %lld", e.ldo, align);
+  static int trace_on = -1;
+  if (trace_on < 0) { const char* v = getenv("DP_GEMM_TRACE"); trace_on = v ? atoi(v) : 0; }
+  if (trace_on && !var->pair) {
+    // debug only (synchronises): per-tile timeline of CTA 0, cycles relative to the first MMA start
+    static long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 4096 * sizeof(long long));
+    cudaMemsetAsync(dbuf, 0, 4096 * sizeof(long long), static_cast<cudaStream_t>(stream));
+    p.epi.trace = dbuf;
+    cudaError_t le = var->launch(p, grid, static_cast<cudaStream_t>(stream));
+    cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    static long long host[4096];
+    cudaMemcpy(host, dbuf, sizeof(host), cudaMemcpyDeviceToHost);
+    const int per_cta = (p.m_tiles * p.n_tiles + grid - 1) / grid;
+    fprintf(stderr, "[trace] M=%d N=%d K=%d bn=%d tiles/CTA=%d: tile: mma_start mma_issued epi_start epi_end (cycles)\n", a->M,
+            a->N, a->K, bn, per_cta);
+    for (int t = 0; t < per_cta && t < 12; ++t)
+      fprintf(stderr, "[trace]  %2d: %8lld %8lld %8lld %8lld\n", t, host[4 * t] - host[0], host[4 * t + 1] - host[0],
+              host[4 * t + 2] - host[0], host[4 * t + 3] - host[0]);
+    for (int t = 0; t < per_cta && t < 12; ++t) {
+      const long long* r = host + 2048 + 8 * t;
+      fprintf(stderr, "[trace]  %2d epilogue warp 2 (first chunk), relative to epi_start: ldtm_issue %lld ldtm_done %lld staged %lld "
+              "batch0 %lld batch1 %lld fenced %lld arrived %lld\n", t, r[0] - host[4 * t + 2], r[1] - host[4 * t + 2],
+              r[2] - host[4 * t + 2], r[3] - host[4 * t + 2], r[4] - host[4 * t + 2], r[5] - host[4 * t + 2],
+              host[4 * t + 3] - host[4 * t + 2]);
+    }
+    return cuda_error(le, "dp_gemm_bf16 launch");
   }
-  if (e.row_map == DP_ROWMAP_SHUFFLE2X2 && (e.map_a % 32 || e.map_a <= 0))
-    return set_error(-8, "dp_gemm_bf16: shuffle map needs Cout %% 32 == 0");
-  if ((e.row_map == DP_ROWMAP_NCHW || e.row_map == DP_ROWMAP_SHUFFLE2X2) && (a->OH <= 0 || a->OW <= 0))
-    return set_error(-8, "dp_gemm_bf16: row map needs OH/OW");
-  if (e.row_map != DP_ROWMAP_NCHW) {
-    // the epilogue addresses rows with 32-bit element offsets
-    const long long out_rows = (e.row_map == DP_ROWMAP_SHUFFLE2X2) ? 4LL * a->M
-                               : (e.row_map == DP_ROWMAP_PATCH_TOKENS) ? (long long)(a->M / e.map_a + 1) * e.map_b : a->M;
-    if (out_rows * e.ldo + a->N >= 0xffffffffLL || (e.residual && (long long)a->M * e.ldr + a->N >= 0xffffffffLL) ||
-        ((e.aux_out || e.aux_in) && (long long)a->M * e.ld_aux + a->N >= 0xffffffffLL))
-      return set_error(-9, "dp_gemm_bf16: tensor too large for 32-bit epilogue offsets");
-  }
-  const int tiles = p.m_tiles * p.n_tiles;
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  return cuda_error(launch_gemm(p, bn, grid, static_cast<cudaStream_t>(stream)), "dp_gemm_bf16 launch");
+  return cuda_error(var->launch(p, grid, static_cast<cudaStream_t>(stream)), "dp_gemm_bf16 launch");
 }
 
 extern "C" int dp_wgrad_bf16(const dp_wgrad_args* a, void* stream) {

@@ -39,13 +39,15 @@ enum : int {
 
 struct GemmVariant {
   int bn, out, act, map, opt;
+  int pair;   // 1: CTA-pair kernel (gemm_kernel2.cuh): the weight tensor map's box is bn/2 rows, grid = 2 x clusters
   cudaError_t (*launch)(const GemmParams&, int grid, cudaStream_t);
 };
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;                       // 64 bf16 = 128 B = one swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;    // 16 KB
-constexpr int kEpiWarps = 8;                      // two warps per TMEM lane quarter
+constexpr int kEpiWarps = 16;                     // four warps per TMEM lane quarter
+constexpr int kEpiGroups = kEpiWarps / 4;         // column groups: warp (q, g) handles chunks c with c % kEpiGroups == g
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;
 constexpr int kStagingBytes = kEpiWarps * 32 * 32 * 4;   // one 32x32 fp32 transpose buffer per epilogue warp
 constexpr int kSmemLimit = 232448;                // 227 KB per CTA
@@ -82,10 +84,11 @@ __device__ __forceinline__ void unpack_bf16x4(uint2 t, float (&f)[4]) {
 }
 
 constexpr uint32_t kInvalidRow = 0xffffffffu;
+constexpr int kRowBatch = 4;   // rows (x4 row groups) whose loads are in flight together in the epilogue's phase 2
 
 // ------------------------------------------------------------------------------------------------
-// Epilogue of one 128 x BN accumulator tile, executed by 8 warps: warp (q, half) owns TMEM lanes
-// [32q, 32q+32) and the 32-column chunks c with (c & 1) == half.  Per chunk:
+// Epilogue of one 128 x BN accumulator tile, executed by 16 warps: warp (q, g) owns TMEM lanes
+// [32q, 32q+32) and the 32-column chunks c with c % 4 == g (argument `half`).  Per chunk:
 //   phase 1  tcgen05.ld 32x32b.x32 (thread = row) -> 32x32 fp32 transpose buffer in shared memory
 //            (16-byte XOR swizzle, conflict free both ways)
 //   phase 2  lane = (row group rr = lane / 8, column group cg = lane % 8): each warp instruction covers
@@ -100,7 +103,7 @@ constexpr uint32_t kInvalidRow = 0xffffffffu;
 template <int BN, int OUT, int ACT, int MAP, int OPT>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int q, int half, int lane,
                                               int m_blk, int n_blk, float* __restrict__ stg,
-                                              float* __restrict__ colstats) {
+                                              float* __restrict__ colstats, long long* __restrict__ tr = nullptr) {
   const Epilogue& e = p.epi;
   const int map = (MAP == EM_RUNTIME) ? e.row_map : MAP;
   const bool conv = (OPT & OP_CONV) && p.a_mode == 1;
@@ -147,7 +150,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     const long long hw = (long long)p.OH * p.OW;
     const int act = (ACT == EA_RUNTIME) ? e.act : ACT;
 #pragma unroll 1
-    for (int c = half; c < BN / 32; c += 2) {
+    for (int c = half; c < BN / 32; c += kEpiGroups) {
       uint32_t v[32];
       tmem_ld_32x32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
       tmem_ld_wait();
@@ -190,7 +193,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   const int rr = lane >> 3, cg = lane & 7;
   constexpr uint32_t kFull = 0xffffffffu;
 #pragma unroll 1
-  for (int c = half; c < BN / 32; c += 2) {
+  for (int c = half; c < BN / 32; c += kEpiGroups) {
     if (e.debug & 8) continue;
     const int col0 = n_blk * BN + c * 32;
     if (col0 >= e.n_valid) continue;  // warp-uniform
@@ -204,8 +207,10 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       if (has_ls) lsv = ldg4(e.ls + ccol);
     }
     uint32_t v[32];
+    if (tr) tr[0] = clock64();
     tmem_ld_32x32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
     tmem_ld_wait();
+    if (tr) tr[1] = clock64();
     {
       float4* srow = reinterpret_cast<float4*>(stg + lane * 32);
 #pragma unroll
@@ -214,6 +219,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
                                             __uint_as_float(v[4 * jj + 2]), __uint_as_float(v[4 * jj + 3]));
     }
     __syncwarp();
+    if (tr) tr[2] = clock64();
     if (e.debug & 4) continue;
     uint32_t ocol = uint32_t(ccol), tap_off = 0;
     if (map == EM_SHUFFLE) {
@@ -226,15 +232,17 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     // back to back.  The residual may alias the output (in-place residual stream), which stops the compiler
     // from hoisting loads above the stores of earlier rows by itself -- each element is read before it is
     // written by the same thread, so hoisting by hand is safe.
-    uint32_t o_off[8];
-    float4 xs[8];
-    float4 res32[(OPT & OP_LSRES) ? 8 : 1];
-    uint2 res16[(OPT & OP_RES_BF16) ? 8 : 1];
-    uint2 auxin[(OPT & OP_AUX_IN) ? 8 : 1];
-    uint32_t a_off[(OPT & OP_AUX_OUT) ? 8 : 1];
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
-      const int row = it * 4 + rr;
+    for (int ib = 0; ib < 8; ib += kRowBatch) {
+    uint32_t o_off[kRowBatch];
+    float4 xs[kRowBatch];
+    float4 res32[(OPT & OP_LSRES) ? kRowBatch : 1];
+    uint2 res16[(OPT & OP_RES_BF16) ? kRowBatch : 1];
+    uint2 auxin[(OPT & OP_AUX_IN) ? kRowBatch : 1];
+    uint32_t a_off[(OPT & OP_AUX_OUT) ? kRowBatch : 1];
+#pragma unroll
+    for (int it = 0; it < kRowBatch; ++it) {
+      const int row = (ib + it) * 4 + rr;
       o_off[it] = __shfl_sync(kFull, off_out, row);
       const bool ok = o_off[it] != kInvalidRow && cvalid;
       if constexpr ((OPT & (OP_LSRES | OP_RES_BF16)) != 0) {
@@ -262,7 +270,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     }
     // pass B: branch-free math for all 8 rows (the compiler interleaves the rows), predicated stores only
 #pragma unroll
-    for (int it = 0; it < 8; ++it) {
+    for (int it = 0; it < kRowBatch; ++it) {
       const float4 x = xs[it];
       const bool ok = o_off[it] != kInvalidRow && cvalid;
       float f[4];
@@ -332,6 +340,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         }
       }
     }
+    if (tr) tr[3 + ib / kRowBatch] = clock64();
+    }  // row batch
     if constexpr ((OPT & OP_STATS) != 0) {
       if (has_stats) {
 #pragma unroll
@@ -444,6 +454,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
+        if (p.epi.trace != nullptr && blockIdx.x == 0) p.epi.trace[(tile / gridDim.x) * 4 + 0] = clock64();
         const uint32_t d_tmem = tmem_base + uint32_t(acc * BN);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&full_bar[ps.stage], ps.phase);
@@ -460,13 +471,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
           ps.template advance<C::kStages>();
         }
         umma_commit(&tfull_bar[acc]);
+        if (p.epi.trace != nullptr && blockIdx.x == 0) p.epi.trace[(tile / gridDim.x) * 4 + 1] = clock64();
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }
     }
   } else {
     const int q = warp & 3;             // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;   // which 32-column chunks (odd / even) this warp handles
+    const int half = (warp - 2) >> 2;   // column group of this warp
     float* stg = staging + (warp - 2) * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -474,10 +486,14 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
       DP_TILE_COORDS(tile, m_blk, n_blk)
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      epilogue_tile<BN, OUT, ACT, MAP, OPT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk, stg, colstats);
+      if (p.epi.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64) p.epi.trace[(tile / gridDim.x) * 4 + 2] = clock64();
+      long long* tr = (p.epi.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64) ? p.epi.trace + 2048 + (tile / gridDim.x) * 8 : nullptr;
+      epilogue_tile<BN, OUT, ACT, MAP, OPT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk, stg, colstats, tr);
       tc_fence_before();
       __syncwarp();
+      if (tr) tr[5] = clock64();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (p.epi.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64) p.epi.trace[(tile / gridDim.x) * 4 + 3] = clock64();
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
       if constexpr ((OPT & OP_STATS) != 0) {
@@ -485,7 +501,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
           const int next = tile + gridDim.x;
           const int next_n = next < num_tiles ? next / p.m_tiles : -1;
           if (next_n != n_blk) {  // CTA-uniform: flush this column block's statistics
-            const int et = threadIdx.x - 64;  // 0 .. 255
+            const int et = threadIdx.x - 64;  // 0 .. 32 * kEpiWarps - 1
             named_bar_sync(1, 32 * kEpiWarps);
             for (int i = et; i < 2 * BN; i += 32 * kEpiWarps) {
               const int which = i / BN, cl = i - which * BN;
@@ -522,6 +538,6 @@ cudaError_t launch_gemm_variant(const GemmParams& p, int grid, cudaStream_t s) {
 }
 
 #define DP_GEMM_VARIANT(BN, OUT, ACT, MAP, OPT) \
-  GemmVariant { BN, OUT, ACT, MAP, OPT, &launch_gemm_variant<BN, OUT, ACT, MAP, OPT> }
+  GemmVariant { BN, OUT, ACT, MAP, OPT, 0, &launch_gemm_variant<BN, OUT, ACT, MAP, OPT> }
 
 }  // namespace dp

@@ -207,12 +207,14 @@ template <int BN> cudaError_t launch_wgrad_t(const WgradParams& p, int grid, cud
 
 }  // namespace
 
-extern const GemmVariant kGemmVariantsA[], kGemmVariantsB[], kGemmVariantsC[], kGemmVariantsD[], kGemmVariantsGeneric[];
-extern const int kNumGemmVariantsA, kNumGemmVariantsB, kNumGemmVariantsC, kNumGemmVariantsD, kNumGemmVariantsGeneric;
+extern const GemmVariant kGemmVariantsA[], kGemmVariantsB[], kGemmVariantsC[], kGemmVariantsD[], kGemmVariantsGeneric[],
+    kGemmVariantsPair[];
+extern const int kNumGemmVariantsA, kNumGemmVariantsB, kNumGemmVariantsC, kNumGemmVariantsD, kNumGemmVariantsGeneric,
+    kNumGemmVariantsPair;
 
-// Pick the cheapest compiled variant whose compile-time feature set covers what this launch needs.
-cudaError_t launch_gemm(const GemmParams& p, int block_n, int grid, cudaStream_t s) {
-  const Epilogue& e = p.epi;
+// Pick the cheapest compiled variant (single-CTA or CTA-pair, as requested) whose compile-time feature set covers
+// what this launch needs; nullptr if none is compiled for this tile width.
+const GemmVariant* select_gemm_variant(const Epilogue& e, int a_mode, int block_n, int pair) {
   int need = 0;
   if (e.scale) need |= OP_SCALE;
   if (e.ls || (e.residual && !e.res_is_bf16)) need |= OP_LSRES;
@@ -220,15 +222,17 @@ cudaError_t launch_gemm(const GemmParams& p, int block_n, int grid, cudaStream_t
   if (e.aux_out) need |= OP_AUX_OUT;
   if (e.aux_in) need |= OP_AUX_IN;
   if (e.stats) need |= OP_STATS;
-  if (p.a_mode == 1) need |= OP_CONV;
-  const GemmVariant* tables[5] = {kGemmVariantsA, kGemmVariantsB, kGemmVariantsC, kGemmVariantsD, kGemmVariantsGeneric};
-  const int counts[5] = {kNumGemmVariantsA, kNumGemmVariantsB, kNumGemmVariantsC, kNumGemmVariantsD, kNumGemmVariantsGeneric};
+  if (a_mode == 1) need |= OP_CONV;
+  const GemmVariant* tables[6] = {kGemmVariantsA, kGemmVariantsB, kGemmVariantsC, kGemmVariantsD, kGemmVariantsGeneric,
+                                  kGemmVariantsPair};
+  const int counts[6] = {kNumGemmVariantsA, kNumGemmVariantsB, kNumGemmVariantsC, kNumGemmVariantsD, kNumGemmVariantsGeneric,
+                         kNumGemmVariantsPair};
   const GemmVariant* best = nullptr;
   int best_cost = 1 << 30;
-  for (int t = 0; t < 5; ++t)
+  for (int t = 0; t < 6; ++t)
     for (int i = 0; i < counts[t]; ++i) {
       const GemmVariant& v = tables[t][i];
-      if (v.bn != block_n) continue;
+      if (v.bn != block_n || v.pair != pair) continue;
       if (v.out != EO_RUNTIME && v.out != e.out_dtype) continue;
       if (v.act != EA_RUNTIME && v.act != e.act) continue;
       if (v.map != EM_RUNTIME && v.map != e.row_map) continue;
@@ -236,8 +240,7 @@ cudaError_t launch_gemm(const GemmParams& p, int block_n, int grid, cudaStream_t
       const int cost = __builtin_popcount(v.opt) + 8 * ((v.out == EO_RUNTIME) + (v.act == EA_RUNTIME) + (v.map == EM_RUNTIME));
       if (cost < best_cost) { best_cost = cost; best = &v; }
     }
-  if (!best) return cudaErrorInvalidValue;
-  return best->launch(p, grid, s);
+  return best;
 }
 
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, int grid, cudaStream_t s) {

@@ -32,6 +32,7 @@ struct Epilogue {
   int res_is_bf16;  // residual tensor dtype (0 fp32, 1 bf16)
   int n_valid;      // number of valid output columns (<= N)
   int stats_c;      // number of channels of `stats`
+  long long* trace; // debug: per-tile timestamps of CTA 0 (DP_GEMM_TRACE=1), [tile][4] = mma start, mma issued, epilogue start, epilogue end
   int debug;        // tuning knobs (DP_GEMM_DEBUG env): 1 skip stores, 2 skip residual/aux loads, 4 skip phase 2, 8 skip TMEM loads
   int map_a, map_b; // ROWMAP_PATCH_TOKENS: (patches per image, tokens per image); NCHW: (channels K, 0);
                     // SHUFFLE2X2: (Cout, 0)

@@ -167,6 +167,34 @@ class PoseTrainer:
         for t, s in zip(own + list(self.model.buffers()), snap):
             t.copy_(s)
 
+    def _load_inputs(self, st, tensors):
+        """Copy this step's inputs into the static buffers the recorded programs read.  Host tensors go through a
+        double-buffered staging area on a copy stream, so the H2D transfer of step k overlaps the still-running
+        graph of step k-1 (``step`` returns as soon as the replay is enqueued); the compute stream then only does a
+        device-to-device copy."""
+        static = (st["plan"]["t"]["px"], st["thm"], st["kps"], st["tz"])
+        if self.device.type != "cuda" or all(t.is_cuda for t in tensors):
+            for d, t in zip(static, tensors):
+                d.copy_(t, non_blocking=True)
+            return
+        if "staging" not in st:
+            st["staging"] = [[torch.empty_like(d) for d in static] for _ in range(2)]
+            st["stage_free"] = [torch.cuda.Event(), torch.cuda.Event()]
+            st["stage_idx"] = 0
+            self.copy_stream = getattr(self, "copy_stream", None) or torch.cuda.Stream(device=self.device)
+            for ev in st["stage_free"]:
+                ev.record()
+        i = st["stage_idx"] = 1 - st["stage_idx"]
+        cur, cs = torch.cuda.current_stream(), self.copy_stream
+        cs.wait_event(st["stage_free"][i])          # the D2D copy that last read this staging slot has finished
+        with torch.cuda.stream(cs):
+            for d, t in zip(st["staging"][i], tensors):
+                d.copy_(t, non_blocking=True)
+        cur.wait_stream(cs)
+        for d, sbuf in zip(static, st["staging"][i]):
+            d.copy_(sbuf, non_blocking=True)
+        st["stage_free"][i].record(cur)
+
     def step(self, pixel_values, target_heatmaps, keypoints, target_z):
         """One fine-tuning step on this rank's shard.  Inputs may live on the host (pinned) or on the device."""
         model = self.model
@@ -178,10 +206,7 @@ class PoseTrainer:
         st = self._steps.get(key)
         if st is None or st["plan"] is not self.engine.plans.get((B, H, W, True)):
             st = self._steps[key] = self._build(B, H, W)
-        st["plan"]["t"]["px"].copy_(pixel_values, non_blocking=True)
-        st["thm"].copy_(target_heatmaps, non_blocking=True)
-        st["kps"].copy_(keypoints, non_blocking=True)
-        st["tz"].copy_(target_z, non_blocking=True)
+        self._load_inputs(st, (pixel_values, target_heatmaps, keypoints, target_z))
         if not self.use_graph:
             self._run(st)
         else:

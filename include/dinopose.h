@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 2
+#define DP_ABI_VERSION 3
 
 const char* dp_last_error(void);
 int dp_abi_version(void);
@@ -73,6 +73,7 @@ typedef struct {
                              dp_bn_stats: zero on entry, dp_bn_finalize re-zeroes).  With DP_ROWMAP_SHUFFLE2X2
                              the channel of column j is j % map_a. */
   int stats_c;
+  int cta_pair;           /* 0 auto, 1 force the CTA-pair (cta_group::2, 256-row tile) kernel, 2 force single-CTA */
 } dp_gemm_args;
 int dp_gemm_bf16(const dp_gemm_args* a, void* stream);
 

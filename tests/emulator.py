@@ -85,7 +85,8 @@ class TorchEmulator:
     # ------------------------------------------------------------------ GEMM family
     def gemm(self, A, W, out, *, M, N, K, lda=None, ldw=None, ldo=None, out_dtype="bf16", bias=None, scale=None,
              ls=None, residual=None, ldr=None, aux_out=None, aux_in=None, ld_aux=0, act="none", row_map="identity",
-             n_valid=0, map_a=0, map_b=0, conv=None, OH=0, OW=0, NB=0, block_n=0, stats=None, stats_c=0, name="gemm"):
+             n_valid=0, map_a=0, map_b=0, conv=None, OH=0, OW=0, NB=0, block_n=0, stats=None, stats_c=0, cta_pair=0,
+             name="gemm"):
         def fn():
             Wf = W.float()[:N, :K]
             if conv is not None:

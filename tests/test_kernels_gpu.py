@@ -56,6 +56,32 @@ def test_gemm_plain(M, N, K, bn):
     assert rel(out.float(), ref) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(256, 192, 64, 192), (257, 384, 384, 192), (1000, 1152, 384, 192),
+                                      (16448, 1536, 384, 192), (16448, 1152, 384, 256), (515, 512, 1536, 256),
+                                      (640, 256, 128, 128), (129, 384, 384, 128), (16448, 384, 384, 192)])
+def test_gemm_cta_pair(M, N, K, bn):
+    """cta_group::2 kernel: 256-row tiles over two CTAs, incl. an odd number of 128-row blocks (phantom half)."""
+    A = rnd(M, K, dtype=BF)
+    W = rnd(N, K, scale=0.05, seed=1, dtype=BF)
+    bias = rnd(N, seed=2)
+    out = torch.zeros(M, N, device=dev(), dtype=BF)
+    run(lambda b: b.gemm(A, W, out, M=M, N=N, K=K, bias=bias, block_n=bn, cta_pair=1))
+    ref = A.float() @ W.float().t() + bias
+    assert rel(out.float(), ref) < 1e-2
+    # fp32 out + LayerScale + in-place residual, and GELU (+ saved pre-activation) through the pair kernel
+    ls = rnd(N, seed=4)
+    x = rnd(M, N, seed=5)
+    x0 = x.clone()
+    run(lambda b: b.gemm(A, W, x, M=M, N=N, K=K, bias=bias, ls=ls, residual=x, out_dtype="f32", block_n=bn, cta_pair=1))
+    assert rel(x, x0 + ref * ls) < 2e-3
+    if bn != 128:
+        out2 = torch.zeros(M, N, device=dev(), dtype=BF)
+        aux = torch.zeros(M, N, device=dev(), dtype=BF)
+        run(lambda b: b.gemm(A, W, out2, M=M, N=N, K=K, bias=bias, act="gelu", aux_out=aux, ld_aux=N, block_n=bn, cta_pair=1))
+        assert rel(aux.float(), ref) < 1e-2
+        assert rel(out2.float(), F.gelu(ref)) < 1e-2
+
+
 def test_gemm_epilogues():
     M, N, K = 700, 384, 256
     A = rnd(M, K, dtype=BF)

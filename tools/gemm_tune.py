@@ -23,7 +23,7 @@ SHAPES = {
 }
 
 
-def bench(name, bn, reps=20, nbuf=6):
+def bench(name, bn, reps=20, nbuf=6, pair=2):
     m, n, k, epi = SHAPES[name]
     be = CudaBackend()
     progs = []
@@ -34,15 +34,15 @@ def bench(name, bn, reps=20, nbuf=6):
         prog = be.begin()
         if epi == "bias_bf16":
             out = torch.empty(m, n, device=dev, dtype=BF)
-            be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, block_n=bn)
+            be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, block_n=bn, cta_pair=pair)
         elif epi == "gelu_bf16":
             out = torch.empty(m, n, device=dev, dtype=BF)
-            be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, act="gelu", block_n=bn)
+            be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, act="gelu", block_n=bn, cta_pair=pair)
         else:
             out = torch.empty(m, n, device=dev)
             res = torch.randn(m, n, device=dev)
             ls = torch.ones(n, device=dev)
-            be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, ls=ls, residual=res, out_dtype="f32", block_n=bn)
+            be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, ls=ls, residual=res, out_dtype="f32", block_n=bn, cta_pair=pair)
         progs.append(prog)
     for p in progs:
         p.run()
@@ -72,7 +72,13 @@ if __name__ == "__main__":
     names = sys.argv[1].split(",") if len(sys.argv) > 1 else list(SHAPES)
     bns = [int(x) for x in sys.argv[2].split(",")] if len(sys.argv) > 2 else [128, 192, 256]
     dbg = os.environ.get("DP_GEMM_DEBUG", "0")
+    pairs = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [2, 1]   # 2 = single CTA, 1 = CTA pair
     for nm in names:
         for bn in bns:
-            us, tf = bench(nm, bn)
-            print(f"debug={dbg} {nm:6s} bn={bn:3d}  {us:8.1f} us  {tf:7.1f} TFLOP/s", flush=True)
+            for pr in pairs:
+                try:
+                    us, tf = bench(nm, bn, pair=pr)
+                except Exception as ex:   # no variant compiled for this combination
+                    print(f"debug={dbg} {nm:6s} bn={bn:3d} {'pair' if pr == 1 else 'single'}: {str(ex)[:80]}", flush=True)
+                    continue
+                print(f"debug={dbg} {nm:6s} bn={bn:3d} {'pair  ' if pr == 1 else 'single'} {us:8.1f} us  {tf:7.1f} TFLOP/s", flush=True)

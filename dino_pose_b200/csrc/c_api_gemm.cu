@@ -304,6 +304,11 @@ extern "C" int dp_wgrad_bf16(const dp_wgrad_args* a, void* stream) {
   // make sure no split is empty
   while (splits > 1 && ((p.total_k_blocks + splits - 1) / splits) * (splits - 1) >= p.total_k_blocks) --splits;
   p.splits = splits;
+  {
+    static int dbg = -1;
+    if (dbg < 0) { const char* v = getenv("DP_WGRAD_DEBUG"); dbg = v ? atoi(v) : 0; }
+    p.debug = dbg;
+  }
   const int items = base_items * splits;
   const int grid = items < sm_count() ? items : sm_count();
   return cuda_error(launch_wgrad(p, bn, grid, static_cast<cudaStream_t>(stream)), "dp_wgrad_bf16 launch");

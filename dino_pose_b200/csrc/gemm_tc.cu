@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const __grid_co
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
         tmem_ld_wait();
-        if (!mvalid) continue;
+        if (!mvalid || (p.debug & 1)) continue;
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const int n = n_blk * BN + c0 + j;

@@ -67,6 +67,7 @@ struct alignas(64) WgradParams {
   int bw, bh, bb;
   int tiles_x, tiles_y, tiles_b;
   int total_k_blocks, splits;
+  int debug;                // DP_WGRAD_DEBUG: 1 skip the atomic scatter (tuning aid)
 };
 
 }  // namespace dp

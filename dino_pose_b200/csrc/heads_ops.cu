@@ -98,20 +98,32 @@ __global__ void __launch_bounds__(256) col2im_kernel(const uint4* __restrict__ c
 
 // depthwise 3x3, pad 1 (HourglassModule.depthwise_conv[0], pose_heads.py:219).  w fp32 [C,1,3,3].
 // flip = 1 gives the input-gradient (correlation with the flipped kernel).
+// A thread owns ONE group of 8 channels for the whole kernel: its 72 filter taps and 8 biases live in registers,
+// and it walks over pixels (4 pixel lanes per 256-thread block when C = 512), 9 x 16-byte loads + 72 FMAs per pixel.
 template <typename OutT>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const uint4* __restrict__ in, const float* __restrict__ w,
                                                         const float* __restrict__ bias, const uint4* __restrict__ add,
                                                         OutT* __restrict__ out, int NB, int H, int W, int C8, int flip) {
-  const long long total = (long long)NB * H * W * C8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = int(i % C8);
-    long long r = i / C8;
-    const int x = int(r % W); r /= W;
-    const int y = int(r % H);
-    const int b = int(r / H);
+  const int c = threadIdx.x % C8;
+  const int ppb = blockDim.x / C8;          // pixels per block iteration
+  const int pl = threadIdx.x / C8;
+  if (pl >= ppb) return;
+  float wt[9][8], bs[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int tap = flip ? 8 - t : t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wt[t][j] = __ldg(w + (c * 8 + j) * 9 + tap);
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bs[j] = bias ? __ldg(bias + c * 8 + j) : 0.f;
+  const long long P = (long long)NB * H * W;
+  for (long long p = (long long)blockIdx.x * ppb + pl; p < P; p += (long long)gridDim.x * ppb) {
+    const int x = int(p % W);
+    const int y = int((p / W) % H);
     float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias ? __ldg(bias + c * 8 + j) : 0.f;
+    for (int j = 0; j < 8; ++j) acc[j] = bs[j];
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
       const int iy = y + ky - 1;
@@ -120,43 +132,42 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const uint4* __restrict_
       for (int kx = 0; kx < 3; ++kx) {
         const int ix = x + kx - 1;
         if (ix < 0 || ix >= W) continue;
-        const uint4 t = __ldg(in + (((long long)b * H + iy) * W + ix) * C8 + c);
         float f[8];
-        unpack8(t, f);
-        const int tap = flip ? (2 - ky) * 3 + (2 - kx) : ky * 3 + kx;
+        unpack8(__ldg(in + (p + (long long)(ky - 1) * W + (kx - 1)) * C8 + c), f);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] += f[j] * __ldg(w + (c * 8 + j) * 9 + tap);
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], wt[ky * 3 + kx][j], acc[j]);
       }
     }
     if (add != nullptr) {
       float f[8];
-      unpack8(__ldg(add + i), f);
+      unpack8(__ldg(add + p * C8 + c), f);
 #pragma unroll
       for (int j = 0; j < 8; ++j) acc[j] += f[j];
     }
-    store8(out + i * 8, acc);
+    store8(out + (p * C8 + c) * 8, acc);
   }
 }
 
-// depthwise weight gradient: dW[c,tap] += sum_p dRaw[p,c] * in[p+tap,c].  One block per (row chunk, 64 channels).
-__global__ void __launch_bounds__(256) dwconv3x3_wgrad_kernel(const __nv_bfloat16* __restrict__ in,
-                                                              const __nv_bfloat16* __restrict__ dout, float* __restrict__ dw,
-                                                              int NB, int H, int W, int C, int rows_per_block) {
-  // thread = (channel within 64-block, pixel lane); each thread accumulates 9 taps for one channel
-  const int c = blockIdx.y * 64 + (threadIdx.x & 63);
-  const int pl = threadIdx.x >> 6;  // 0..3
-  const long long P = (long long)NB * H * W;
-  const long long p0 = (long long)blockIdx.x * rows_per_block;
-  const long long p1 = min(p0 + rows_per_block, P);
-  float acc[9];
+// depthwise weight gradient: dW[c,tap] += sum_p dRaw[p,c] * in[p+tap,c].  Same thread mapping as the forward:
+// 8 channels x 9 taps = 72 fp32 accumulators per thread over its pixels, then one shared-memory reduction over the
+// block's pixel lanes and fp32 atomics (grid = a few hundred blocks, so <= a few hundred atomics per address).
+__global__ void __launch_bounds__(256) dwconv3x3_wgrad_kernel(const uint4* __restrict__ in, const uint4* __restrict__ dout,
+                                                              float* __restrict__ dw, int NB, int H, int W, int C8) {
+  const int c = threadIdx.x % C8;
+  const int ppb = blockDim.x / C8;
+  const int pl = threadIdx.x / C8;
+  float acc[9][8];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) acc[t] = 0.f;
-  if (c < C) {
-    for (long long p = p0 + pl; p < p1; p += 4) {
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  const long long P = (long long)NB * H * W;
+  if (pl < ppb) {
+    for (long long p = (long long)blockIdx.x * ppb + pl; p < P; p += (long long)gridDim.x * ppb) {
       const int x = int(p % W);
       const int y = int((p / W) % H);
-      const long long b = p / ((long long)W * H);
-      const float g = __bfloat162float(dout[p * C + c]);
+      float g[8];
+      unpack8(__ldg(dout + p * C8 + c), g);
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int iy = y + ky - 1;
@@ -165,21 +176,36 @@ __global__ void __launch_bounds__(256) dwconv3x3_wgrad_kernel(const __nv_bfloat1
         for (int kx = 0; kx < 3; ++kx) {
           const int ix = x + kx - 1;
           if (ix < 0 || ix >= W) continue;
-          acc[ky * 3 + kx] += g * __bfloat162float(in[((b * H + iy) * W + ix) * C + c]);
+          float f[8];
+          unpack8(__ldg(in + (p + (long long)(ky - 1) * W + (kx - 1)) * C8 + c), f);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(g[j], f[j], acc[ky * 3 + kx][j]);
         }
       }
     }
   }
-  __shared__ float red[4][64][9];
+  // reduce over the pixel lanes of the block: lane 0 of each channel group accumulates through shared memory
+  extern __shared__ float red[];   // [ppb - 1][C8][72]
+  if (pl > 0 && pl < ppb) {
+    float* r = red + ((long long)(pl - 1) * C8 + c) * 72;
 #pragma unroll
-  for (int t = 0; t < 9; ++t) red[pl][threadIdx.x & 63][t] = acc[t];
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[t * 8 + j] = acc[t][j];
+  }
   __syncthreads();
-  if (pl == 0 && c < C) {
+  if (pl == 0) {
+    for (int l = 1; l < ppb; ++l) {
+      const float* r = red + ((long long)(l - 1) * C8 + c) * 72;
 #pragma unroll
-    for (int t = 0; t < 9; ++t) {
-      const int cc = threadIdx.x & 63;
-      atomicAdd(dw + c * 9 + t, red[0][cc][t] + red[1][cc][t] + red[2][cc][t] + red[3][cc][t]);
+      for (int t = 0; t < 9; ++t)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[t][j] += r[t * 8 + j];
     }
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dw + (c * 8 + j) * 9 + t, acc[t][j]);
   }
 }
 
@@ -357,19 +383,30 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
     is[j] = __ldg(invstd + c8 * 8 + j);
     s[j] = q[j] = 0.f;
   }
-  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C8; row < P; row += (long long)gridDim.x * rpb) {
-    const long long o = row * C + c8 * 8;
-    float r[8], g[8], a[8];
-    load8(raw + o, r);
-    load8(dout + o, g);
-    if (mode == 1) load8(add1 + o, a);
+  // two rows per iteration: all loads of both rows are issued before the math (bytes in flight per thread x2)
+  const long long stride = (long long)gridDim.x * rpb;
+  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C8; row < P; row += 2 * stride) {
+    const long long o0 = row * C + c8 * 8;
+    const bool two = row + stride < P;
+    const long long o1 = two ? (row + stride) * C + c8 * 8 : o0;
+    float r0[8], g0[8], a0[8], r1[8], g1[8], a1[8];
+    load8(raw + o0, r0);
+    load8(dout + o0, g0);
+    load8(raw + o1, r1);
+    load8(dout + o1, g1);
+    if (mode == 1) {
+      load8(add1 + o0, a0);
+      load8(add1 + o1, a1);
+    }
+    const float w1 = two ? 1.f : 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float y = r[j] * sc[j] + sh[j];
-      if (mode == 1) y += a[j];
-      const float gj = ((relu || mode == 1) && !(y > 0.f)) ? 0.f : g[j];
-      s[j] += gj;
-      q[j] += gj * (r[j] - mu[j]) * is[j];
+      float y0 = r0[j] * sc[j] + sh[j], y1 = r1[j] * sc[j] + sh[j];
+      if (mode == 1) { y0 += a0[j]; y1 += a1[j]; }
+      const float gj0 = ((relu || mode == 1) && !(y0 > 0.f)) ? 0.f : g0[j];
+      const float gj1 = ((relu || mode == 1) && !(y1 > 0.f)) ? 0.f : g1[j] * w1;
+      s[j] += gj0 + gj1;
+      q[j] += (gj0 * (r0[j] - mu[j]) + gj1 * (r1[j] - mu[j])) * is[j];
     }
   }
   bn_block_reduce_atomic(s, q, c8, C8, C, sums);
@@ -517,10 +554,14 @@ __global__ void __launch_bounds__(128) sgemm_small_kernel(const float* __restric
                                                           const float* __restrict__ bias, int relu,
                                                           const float* __restrict__ mask_ref, long long ld_ref,
                                                           float p_drop, const unsigned long long* __restrict__ seed_ptr,
-                                                          int accumulate) {
+                                                          int accumulate, int k_per_split) {
   // 32x32 output tile, 32-deep k-steps, 128 threads x (2 rows x 4 cols); loads are coalesced along whichever
-  // operand dimension has unit stride
+  // operand dimension has unit stride.  gridDim.z > 1: split-K -- each z-slice adds its partial sums to C with
+  // fp32 atomics (C pre-zeroed or accumulated onto) and the epilogue runs in sgemm_small_finish_kernel.
   const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
+  const bool split = gridDim.z > 1;
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
   __shared__ float As[32][33];
   __shared__ float Bs[32][33];
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
@@ -531,19 +572,19 @@ __global__ void __launch_bounds__(128) sgemm_small_kernel(const float* __restric
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const bool a_kfast = (sa_k == 1), b_kfast = (sb_k == 1);
-  for (int k0 = 0; k0 < K; k0 += 32) {
+  for (int k0 = k_begin; k0 < k_end; k0 += 32) {
 #pragma unroll
     for (int i = threadIdx.x; i < 32 * 32; i += 128) {
       const int lo = i & 31, hi = i >> 5;
       {
         const int kk = a_kfast ? lo : hi, mm = a_kfast ? hi : lo;
         const int m = m0 + mm, k = k0 + kk;
-        As[kk][mm] = (m < M && k < K) ? __ldg(A + m * sa_m + k * sa_k) : 0.f;
+        As[kk][mm] = (m < M && k < k_end) ? __ldg(A + m * sa_m + k * sa_k) : 0.f;
       }
       {
         const int kk = b_kfast ? lo : hi, nn = b_kfast ? hi : lo;
         const int n = n0 + nn, k = k0 + kk;
-        Bs[kk][nn] = (n < N && k < K) ? __ldg(Bm + k * sb_k + n * sb_n) : 0.f;
+        Bs[kk][nn] = (n < N && k < k_end) ? __ldg(Bm + k * sb_k + n * sb_n) : 0.f;
       }
     }
     __syncthreads();
@@ -572,6 +613,10 @@ __global__ void __launch_bounds__(128) sgemm_small_kernel(const float* __restric
       const int n = n0 + tx * 4 + j;
       if (n >= N) continue;
       float v = acc[i][j];
+      if (split) {
+        atomicAdd(Cc + m * ldc + n, v);
+        continue;
+      }
       if (bias) v += bias[n];
       if (relu) v = fmaxf(v, 0.f);
       if (mask_ref) v = mask_ref[m * ld_ref + n] > 0.f ? v : 0.f;
@@ -580,6 +625,24 @@ __global__ void __launch_bounds__(128) sgemm_small_kernel(const float* __restric
       Cc[m * ldc + n] = v;
     }
   }
+}
+
+// epilogue of the split-K path, in place on C
+__global__ void sgemm_small_finish_kernel(float* __restrict__ Cc, long long ldc, int M, int N, const float* __restrict__ bias,
+                                          int relu, const float* __restrict__ mask_ref, long long ld_ref, float p_drop,
+                                          const unsigned long long* __restrict__ seed_ptr) {
+  const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
+  const uint32_t thresh = p_drop > 0.f ? uint32_t(fminf(p_drop, 0.999999f) * 4294967296.0f) : 0u;
+  const float keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * N) return;
+  const int m = int(i / N), n = int(i % N);
+  float v = Cc[m * ldc + n];
+  if (bias) v += bias[n];
+  if (relu) v = fmaxf(v, 0.f);
+  if (mask_ref) v = mask_ref[m * ld_ref + n] > 0.f ? v : 0.f;
+  if (p_drop > 0.f) v = (mix32h(seed * 0xD1342543DE82EF95ull + uint64_t(m) * N + n) >= thresh) ? v * keep : 0.f;
+  Cc[m * ldc + n] = v;
 }
 
 // out = (ref > 0) ? d * keep_scale : 0      (gradient through ReLU [+ inverted dropout] given the saved output)
@@ -630,26 +693,39 @@ cudaError_t launch_col2im(const void* col, const float* bias, void* big, int big
 }
 cudaError_t launch_dwconv3x3(const void* in, const float* w, const float* bias, const void* add, void* out, int out_f32,
                              int NB, int H, int W, int C, int flip, cudaStream_t s) {
-  const long long total = (long long)NB * H * W * (C / 8);
+  const int C8 = C / 8;
+  if (C % 8 || C8 > 256) return cudaErrorInvalidValue;
+  const int ppb = 256 / C8;
+  const long long P = (long long)NB * H * W;
+  long long g = (P + ppb - 1) / ppb;
+  if (g > 148 * 8) g = 148 * 8;
   if (out_f32)
-    dwconv3x3_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), w, bias,
-                                                                 reinterpret_cast<const uint4*>(add),
-                                                                 reinterpret_cast<float*>(out), NB, H, W, C / 8, flip);
+    dwconv3x3_kernel<float><<<unsigned(g), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), w, bias,
+                                                        reinterpret_cast<const uint4*>(add), reinterpret_cast<float*>(out),
+                                                        NB, H, W, C8, flip);
   else
-    dwconv3x3_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), w, bias,
-                                                                         reinterpret_cast<const uint4*>(add),
-                                                                         reinterpret_cast<__nv_bfloat16*>(out), NB, H, W,
-                                                                         C / 8, flip);
+    dwconv3x3_kernel<__nv_bfloat16><<<unsigned(g), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), w, bias,
+                                                                reinterpret_cast<const uint4*>(add),
+                                                                reinterpret_cast<__nv_bfloat16*>(out), NB, H, W, C8, flip);
   return cudaGetLastError();
 }
 cudaError_t launch_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, int NB, int H, int W, int C,
                                    cudaStream_t s) {
+  const int C8 = C / 8;
+  if (C % 8 || C8 > 256) return cudaErrorInvalidValue;
+  const int ppb = 256 / C8;
   const long long P = (long long)NB * H * W;
-  int rpb = int((P + 295) / 296);
-  if (rpb < 64) rpb = 64;
-  dim3 grid(unsigned((P + rpb - 1) / rpb), unsigned((C + 63) / 64));
-  dwconv3x3_wgrad_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(in),
-                                              reinterpret_cast<const __nv_bfloat16*>(dout), dw, NB, H, W, C, rpb);
+  long long g = (P + ppb - 1) / ppb;
+  if (g > 148 * 2) g = 148 * 2;
+  const size_t smem = size_t(ppb > 1 ? ppb - 1 : 1) * C8 * 72 * sizeof(float);
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(dwconv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  dwconv3x3_wgrad_kernel<<<unsigned(g), 256, smem, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<const uint4*>(dout),
+                                                        dw, NB, H, W, C8);
   return cudaGetLastError();
 }
 static unsigned bn_grid(long long P, int C8) {
@@ -749,8 +825,30 @@ cudaError_t launch_sgemm_small(const float* A, long long sa_m, long long sa_k, c
                                const float* mask_ref, long long ld_ref, float p_drop, const unsigned long long* seed,
                                int accumulate, cudaStream_t s) {
   dim3 grid((N + 31) / 32, (M + 31) / 32);
+  // M is the batch (or a layer width) and the tile count is small: split K until ~2 CTAs per SM are busy
+  const int base = int(grid.x * grid.y), ksteps = (K + 31) / 32;
+  int splits = (2 * 148 + base - 1) / base;
+  if (splits > ksteps / 2) splits = ksteps / 2;
+  if (splits < 1) splits = 1;
+  const int k_per_split = ((ksteps + splits - 1) / splits) * 32;
+  splits = (K + k_per_split - 1) / k_per_split;
+  if (splits > 1) {
+    grid.z = unsigned(splits);
+    if (!accumulate) {
+      cudaError_t e = cudaMemset2DAsync(C, size_t(ldc) * sizeof(float), 0, size_t(N) * sizeof(float), size_t(M), s);
+      if (e != cudaSuccess) return e;
+    }
+    sgemm_small_kernel<<<grid, 128, 0, s>>>(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, nullptr, 0, nullptr, 0, 0.f, nullptr,
+                                            1, k_per_split);
+    if (bias != nullptr || relu || mask_ref != nullptr || p_drop > 0.f) {
+      const long long total = (long long)M * N;
+      sgemm_small_finish_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(C, ldc, M, N, bias, relu, mask_ref, ld_ref, p_drop,
+                                                                             seed);
+    }
+    return cudaGetLastError();
+  }
   sgemm_small_kernel<<<grid, 128, 0, s>>>(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, bias, relu, mask_ref, ld_ref,
-                                          p_drop, seed, accumulate);
+                                          p_drop, seed, accumulate, K);
   return cudaGetLastError();
 }
 cudaError_t launch_relu_mask(const float* d, const float* ref, float* out, long long n, float keep_scale, cudaStream_t s) {

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdinopose_sm100a.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 c_ll = C.c_longlong
 c_vp = C.c_void_p
@@ -61,6 +61,7 @@ class WgradArgs(C.Structure):
         ("so_m", c_ll), ("so_mo", c_ll), ("so_n", c_ll), ("so_no", c_ll), ("so_t", c_ll),
         ("m_inner", C.c_int), ("n_inner", C.c_int),
         ("block_n", C.c_int), ("splits", C.c_int),
+        ("workspace", c_vp), ("workspace_bytes", c_ll),
     ]
 
 

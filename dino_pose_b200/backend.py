@@ -168,7 +168,7 @@ class CudaBackend:
                       keep=(a, A, W, out, bias, scale, ls, residual, aux_out, aux_in, stats))
 
     def wgrad(self, A, B, out, *, Mc, Nc, so_m, so_n, so_t=0, so_mo=0, so_no=0, m_inner=0, n_inner=0, conv=None,
-              P=0, lda=None, ldb=None, block_n=0, splits=0, name="wgrad"):
+              P=0, lda=None, ldb=None, block_n=0, splits=0, workspace=None, name="wgrad"):
         """out[off(m)+off(n)+tap*so_t] += sum_p A[p,m] * B[p(+tap),n] (fp32 atomics; out pre-zeroed)."""
         _chk(A, torch.bfloat16, name + ".A", contiguous=False)
         _chk(B, torch.bfloat16, name + ".B", contiguous=False)
@@ -179,6 +179,8 @@ class CudaBackend:
         a.so_m, a.so_mo, a.so_n, a.so_no, a.so_t = so_m, so_mo, so_n, so_no, so_t
         a.m_inner, a.n_inner = m_inner, n_inner
         a.block_n, a.splits = block_n, splits
+        if workspace is not None:
+            a.workspace, a.workspace_bytes = _p(workspace), workspace.numel() * workspace.element_size()
         if conv is not None:
             assert A.dim() == 4 and B.dim() == 4 and A.stride(3) == 1 and B.stride(3) == 1
             a.mode = 1
@@ -197,7 +199,7 @@ class CudaBackend:
         pix = (A.shape[0] * A.shape[1] * A.shape[2]) if conv is not None else P
         taps = conv["KH"] * conv["KW"] if conv is not None else 1
         self.prog.add(name, self.lib.dp_wgrad_bf16, C.byref(a), kernel="gemm_wgrad_tcgen05",
-                      flops=2.0 * pix * Mc * Nc * taps, keep=(a, A, B, out))
+                      flops=2.0 * pix * Mc * Nc * taps, keep=(a, A, B, out, workspace), launches=2 if workspace is not None else 1)
 
     # ------------------------------------------------------------------ backbone row-wise
     def layernorm_fwd(self, x, gamma, beta, y_bf16, y_f32, *, rows, D, T=0, drop_cls=False, eps=1e-6):

@@ -293,17 +293,38 @@ extern "C" int dp_wgrad_bf16(const dp_wgrad_args* a, void* stream) {
     if ((rc = make_tmap(&p.tmB, a->B, 4, db, sb, box))) return rc;
   }
   const int base_items = p.taps * p.m_tiles * p.n_tiles;
+  const long long slice_bytes = (long long)p.taps * p.m_tiles * 128 * p.n_tiles * bn * 4;   // workspace per split
+  const bool use_ws = a->workspace != nullptr && a->workspace_bytes >= slice_bytes;
   int splits = a->splits;
   if (splits <= 0) {
-    splits = (2 * sm_count() + base_items - 1) / base_items;
-    const int max_by_k = (p.total_k_blocks + 3) / 4;  // at least 4 k-blocks per split
-    if (splits > max_by_k) splits = max_by_k;
-    if (splits < 1) splits = 1;
+    if (use_ws) {
+      // atomic-free path: pick the split count with the best SM utilisation (rounds of 148 items per unit of K),
+      // a small linear term for the workspace traffic, at least 8 k-blocks per split, workspace permitting
+      double best = 1e30;
+      splits = 1;
+      for (int sN = 1; sN <= 32; ++sN) {
+        if (sN > 1 && (p.total_k_blocks / sN < 8 || (long long)sN * slice_bytes > a->workspace_bytes)) break;
+        const int rounds = (base_items * sN + sm_count() - 1) / sm_count();
+        const double cost = double(rounds) / sN + 0.01 * sN;
+        if (cost < best - 1e-9) { best = cost; splits = sN; }
+      }
+    } else {
+      splits = (2 * sm_count() + base_items - 1) / base_items;
+      const int max_by_k = (p.total_k_blocks + 3) / 4;  // at least 4 k-blocks per split
+      if (splits > max_by_k) splits = max_by_k;
+      if (splits < 1) splits = 1;
+    }
   }
+  if (use_ws && (long long)splits * slice_bytes > a->workspace_bytes) splits = int(a->workspace_bytes / slice_bytes);
   if (splits > p.total_k_blocks) splits = p.total_k_blocks;
   // make sure no split is empty
   while (splits > 1 && ((p.total_k_blocks + splits - 1) / splits) * (splits - 1) >= p.total_k_blocks) --splits;
   p.splits = splits;
+  if (use_ws) {
+    if (reinterpret_cast<uintptr_t>(a->workspace) & 15) return set_error(-11, "dp_wgrad_bf16: workspace not 16-byte aligned");
+    p.ws = static_cast<float*>(a->workspace);
+    p.ws_ld = p.n_tiles * bn;
+  }
   {
     static int dbg = -1;
     if (dbg < 0) { const char* v = getenv("DP_WGRAD_DEBUG"); dbg = v ? atoi(v) : 0; }

@@ -164,6 +164,31 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const __grid_co
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const int m = m_blk * kBlockM + q * 32 + lane;
+      if (p.ws != nullptr) {
+        // atomic-free path: this item's 128 x BN partial tile goes to its own slice of the workspace
+        // (rows / columns beyond Mc / Nc are stored too: they are zero and never read)
+        float* wrow = p.ws + ((long long)(split * p.taps + tap) * (p.m_tiles * kBlockM) + m) * p.ws_ld + n_blk * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + uint32_t(acc * BN) + (uint32_t(q * 32) << 16) + uint32_t(c0), v);
+          tmem_ld_wait();
+          if (!(p.debug & 1)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(wrow + c0)[j] =
+                  has_k ? make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                                      __uint_as_float(v[4 * j + 3]))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+        continue;
+      }
       const bool mvalid = (m < p.Mc) && has_k;
       float* orow = p.out + (long long)(m % p.m_inner) * p.so_m + (long long)(m / p.m_inner) * p.so_mo +
                     (long long)tap * p.so_t;
@@ -191,6 +216,25 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const __grid_co
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// out[off(m) + off(n) + tap * so_t] = sum over splits of the workspace partials (overwrites: no pre-zeroing needed)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int splits,
+                                                           int taps, int Mpad, int ld, int Mc, int Nc, long long so_m,
+                                                           long long so_mo, long long so_n, long long so_no, long long so_t,
+                                                           int m_inner, int n_inner) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)Mc * Nc) return;
+  const int m = int(idx / Nc), n = int(idx - (long long)m * Nc);
+  const long long base = (long long)(m % m_inner) * so_m + (long long)(m / m_inner) * so_mo +
+                         (long long)(n % n_inner) * so_n + (long long)(n / n_inner) * so_no;
+  const long long slice = (long long)Mpad * ld;
+  for (int t = 0; t < taps; ++t) {
+    float acc = 0.f;
+    const float* p = ws + (long long)t * slice + (long long)m * ld + n;
+    for (int s = 0; s < splits; ++s) acc += __ldg(p + (long long)s * taps * slice);
+    out[base + (long long)t * so_t] = acc;
+  }
 }
 
 template <int BN> cudaError_t launch_wgrad_t(const WgradParams& p, int grid, cudaStream_t s) {
@@ -244,11 +288,18 @@ const GemmVariant* select_gemm_variant(const Epilogue& e, int a_mode, int block_
 }
 
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, int grid, cudaStream_t s) {
+  cudaError_t e;
   switch (block_n) {
-    case 64: return launch_wgrad_t<64>(p, grid, s);
-    case 128: return launch_wgrad_t<128>(p, grid, s);
+    case 64: e = launch_wgrad_t<64>(p, grid, s); break;
+    case 128: e = launch_wgrad_t<128>(p, grid, s); break;
     default: return cudaErrorInvalidValue;
   }
+  if (e != cudaSuccess || p.ws == nullptr) return e;
+  const long long total = (long long)p.Mc * p.Nc;
+  wgrad_reduce_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(p.ws, p.out, p.splits, p.taps, p.m_tiles * kBlockM, p.ws_ld,
+                                                                    p.Mc, p.Nc, p.so_m, p.so_mo, p.so_n, p.so_no, p.so_t,
+                                                                    p.m_inner, p.n_inner);
+  return cudaGetLastError();
 }
 
 }  // namespace dp

@@ -67,6 +67,8 @@ struct alignas(64) WgradParams {
   int bw, bh, bb;
   int tiles_x, tiles_y, tiles_b;
   int total_k_blocks, splits;
+  float* ws;                // split-K workspace [splits][taps][m_tiles*128][n_tiles*BN] fp32 (nullptr: fp32 atomics into out)
+  int ws_ld;                // n_tiles * BN
   int debug;                // DP_WGRAD_DEBUG: 1 skip the atomic scatter (tuning aid)
 };
 

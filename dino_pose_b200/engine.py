@@ -622,6 +622,9 @@ class PoseEngine:
             be.mark(("grads_final", lay["group_end"][key]))
         t["dhm"] = self.new(tuple(t["hm"].shape), F32)
         t["dz"] = self.new((B, K), F32)
+        # split-K workspace shared by all weight-gradient launches (they run one after the other): partial tiles are
+        # stored without atomics and reduced by a second kernel (deterministic, no contention on the gradient buffer)
+        ws = t["wgrad_ws"] = self.new((16 << 20,), F32)
         be.host("zero_grads", flat.zero_)
         s47, s48 = Ls["ups0"].oh, Ls["ups1"].oh
         P48 = B * s48 * s48
@@ -649,7 +652,8 @@ class PoseEngine:
             P_in = B * L.ih * L.iw
             dx = None
             if L.kind == "conv" and k == 1:
-                be.wgrad(draw, x_in.reshape(P_in, ci), gw, Mc=co, Nc=ci, so_m=ci, so_n=1, P=P_out, name=L.name + ".wgrad")
+                be.wgrad(draw, x_in.reshape(P_in, ci), gw, Mc=co, Nc=ci, so_m=ci, so_n=1, P=P_out, name=L.name + ".wgrad",
+                         workspace=ws)
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
                     be.gemm(draw, L.t["wd"], dx, M=P_out, N=ci, K=draw.shape[1], residual=dx_residual,
@@ -657,8 +661,15 @@ class PoseEngine:
             elif L.kind == "conv":
                 d4 = draw.view(B, L.oh, L.ow, co)
                 x4 = x_in.view(B, L.ih, L.iw, ci) if x_in.dim() == 2 else x_in
-                be.wgrad(d4, x4, gw, Mc=co, Nc=ci, so_m=ci * kk, so_n=kk, so_t=1, conv=dict(KH=k, KW=k, pad=L.pad),
-                         name=L.name + ".wgrad")
+                if co <= 64 < ci and (L.oh, L.ow) == (L.ih, L.iw):
+                    # few output channels (prediction.0: 128 -> 64): put the INPUT channels on the 128-row MMA side.
+                    # dW[co,ci,ky,kx] = sum_q x[q,ci] * dRaw[q - (ky,kx) + pad, co]: the shift moves to the N operand
+                    # with mirrored taps (tap' = kk-1-tap, pad' = k-1-pad), hence so_t = -1 from the last tap
+                    be.wgrad(x4, d4, gw.view(-1)[kk - 1:], Mc=ci, Nc=co, so_m=kk, so_n=ci * kk, so_t=-1,
+                             conv=dict(KH=k, KW=k, pad=k - 1 - L.pad), block_n=64, name=L.name + ".wgrad", workspace=ws)
+                else:
+                    be.wgrad(d4, x4, gw, Mc=co, Nc=ci, so_m=ci * kk, so_n=kk, so_t=1, conv=dict(KH=k, KW=k, pad=L.pad),
+                             name=L.name + ".wgrad", workspace=ws)
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
                     be.gemm(d4, L.t["wd"], dx, M=P_in, N=ci, K=kk * co, residual=dx_residual,
@@ -667,14 +678,14 @@ class PoseEngine:
                 x4 = x_in.view(B, L.ih, L.iw, ci)
                 d4 = draw.view(B, L.oh, L.ow, co)
                 be.wgrad(x4, d4, gw, Mc=ci, Nc=co, so_m=co * kk, so_n=kk, so_t=1, conv=dict(KH=k, KW=k, pad=L.pad),
-                         name=L.name + ".wgrad")
+                         name=L.name + ".wgrad", workspace=ws)
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
                     be.gemm(d4, L.t["wd"], dx, M=P_in, N=ci, K=kk * co, residual=dx_residual,
                             conv=dict(KH=k, KW=k, pad=L.pad, OH=L.ih, OW=L.iw), name=L.name + ".dgrad")
             elif L.kind == "conv_s2":
                 be.wgrad(draw, L.t["col"], gw, Mc=co, Nc=kk * ci, so_m=ci * kk, so_n=kk, so_no=1, n_inner=ci, P=P_out,
-                         name=L.name + ".wgrad")
+                         name=L.name + ".wgrad", workspace=ws)
                 if want_dx:
                     dcol = self.new((P_out, kk * ci), self.adt)
                     be.gemm(draw, L.t["wd"], dcol, M=P_out, N=kk * ci, K=co, name=L.name + ".dgrad")
@@ -685,7 +696,7 @@ class PoseEngine:
                 # draw arrives in the un-shuffled [P_in, 4*Cout] layout (bn_bwd(..., shuffle=True))
                 dcol = draw.view(P_in, kk * co)
                 be.wgrad(x_in.reshape(P_in, ci), dcol, gw, Mc=ci, Nc=kk * co, so_m=co * kk, so_n=kk, so_no=1, n_inner=co,
-                         P=P_in, name=L.name + ".wgrad")
+                         P=P_in, name=L.name + ".wgrad", workspace=ws)
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
                     be.gemm(dcol, L.t["wd"], dx, M=P_in, N=ci, K=kk * co, residual=dx_residual, name=L.name + ".dgrad")
@@ -694,7 +705,7 @@ class PoseEngine:
                 be.im2col(draw, dcol, NB=B, IH=L.oh, IW=L.ow, C=co, OH=L.ih, OW=L.iw, KH=k, KW=k, stride=L.stride,
                           pad=L.pad)
                 be.wgrad(x_in.reshape(P_in, ci), dcol, gw, Mc=ci, Nc=kk * co, so_m=co * kk, so_n=kk, so_no=1, n_inner=co,
-                         P=P_in, name=L.name + ".wgrad")
+                         P=P_in, name=L.name + ".wgrad", workspace=ws)
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
                     be.gemm(dcol, L.t["wd"], dx, M=P_in, N=ci, K=kk * co, residual=dx_residual, name=L.name + ".dgrad")
@@ -709,7 +720,7 @@ class PoseEngine:
         L = Ls["pred3"]
         be.colsum(t["ghm"], G[L.name + ".bias"], P=P48, C=K, ld=HM_PAD)
         be.wgrad(t["ghm"], a["pred0"], G[L.name + ".weight"], Mc=K, Nc=64, so_m=64, so_n=1, P=P48, block_n=64,
-                 name="pred3.wgrad")
+                 name="pred3.wgrad", workspace=ws)
         d = self.new((P48, 64), self.adt)
         be.gemm(t["ghm"], L.t["wd"], d, M=P48, N=64, K=HM_PAD, name="pred3.dgrad")
         d = conv_bwd("pred0", bn_bwd("pred0", d), a["ups1"])

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 3
+#define DP_ABI_VERSION 4
 
 const char* dp_last_error(void);
 int dp_abi_version(void);
@@ -77,8 +77,8 @@ typedef struct {
 } dp_gemm_args;
 int dp_gemm_bf16(const dp_gemm_args* a, void* stream);
 
-/* Weight gradient: out[off(m)+off(n)+tap*so_t] += sum_p A[p,m] * B[p (+tap), n]  (fp32 atomics,
- * caller zeroes `out`).  Replaces autograd's conv / linear weight-gradient kernels for
+/* Weight gradient: out[off(m)+off(n)+tap*so_t] (+)= sum_p A[p,m] * B[p (+tap), n]  (fp32 atomics onto a
+ * caller-zeroed `out`, or -- with a workspace -- plain stores of split-K partials + a reduce kernel).  Replaces autograd's conv / linear weight-gradient kernels for
  * model/pose_heads.py layers (train.py:169 loss.backward()).
  * mode 0: A [P,Mc] (lda), B [P,Nc] (ldb).  mode 1: A NHWC [NB,OH,OW,Mc], B NHWC [NB,IH,IW,Nc],
  * B read at (y+ky-pad_y, x+kx-pad_x) for tap (ky,kx).                                           */
@@ -95,6 +95,11 @@ typedef struct {
   long long so_m, so_mo, so_n, so_no, so_t;
   int m_inner, n_inner;
   int block_n, splits;
+  void* workspace;            /* optional split-K workspace (fp32, 16-byte aligned): when it holds at least
+                                 taps * ceil(Mc/128)*128 * ceil(Nc/block_n)*block_n * 4 bytes per split, the partial
+                                 tiles are stored there without atomics and a second kernel reduces them into `out`
+                                 (which then needs no zeroing and the result is deterministic) */
+  long long workspace_bytes;
 } dp_wgrad_args;
 int dp_wgrad_bf16(const dp_wgrad_args* a, void* stream);
 

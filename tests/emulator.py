@@ -144,9 +144,14 @@ class TorchEmulator:
         self.prog.calls.append(fn)
 
     def wgrad(self, A, B, out, *, Mc, Nc, so_m, so_n, so_t=0, so_mo=0, so_no=0, m_inner=0, n_inner=0, conv=None,
-              P=0, lda=None, ldb=None, block_n=0, splits=0, name="wgrad"):
+              P=0, lda=None, ldb=None, block_n=0, splits=0, workspace=None, name="wgrad"):
         def fn():
             flat = out.view(-1)
+            shift = 0
+            if conv is not None and so_t < 0:
+                # mirrored taps: `out` points at the LAST tap and the kernel walks backwards (so_t = -1)
+                shift = (conv["KH"] * conv["KW"] - 1) * (-so_t)
+                flat = torch.as_strided(out, (out.numel() + shift,), (1,), out.storage_offset() - shift)
             m = torch.arange(Mc, device=out.device)
             n = torch.arange(Nc, device=out.device)
             mi = m_inner if m_inner > 0 else 1 << 30
@@ -166,7 +171,7 @@ class TorchEmulator:
                     for kx in range(k):
                         sh = xb[:, :Nc, ky:ky + oh, kx:kx + ow].permute(0, 2, 3, 1).reshape(nb * oh * ow, Nc)
                         g = a2.t() @ sh
-                        idx = (offm[:, None] + offn[None, :] + (ky * k + kx) * so_t).reshape(-1)
+                        idx = (offm[:, None] + offn[None, :] + (ky * k + kx) * so_t + shift).reshape(-1)
                         flat.index_put_((idx,), g.reshape(-1), accumulate=True)
         self.prog.calls.append(fn)
 

@@ -229,6 +229,48 @@ def test_wgrad_plain(P, Mc, Nc, bn):
     assert rel(out, ref) < 2e-3
 
 
+@pytest.mark.parametrize("case", ["plain", "conv3", "convT4", "decomposed"])
+def test_wgrad_workspace_path_is_exact_and_deterministic(case):
+    """Atomic-free split-K: partial tiles in a workspace + reduce kernel; `out` needs no zeroing, two runs are bit-identical."""
+    ws = torch.empty(8 << 20, device=dev())
+    outs = []
+    for rep in range(2):
+        if case == "plain":
+            P, Mc, Nc = 16384, 512, 192
+            A, Bm = rnd(P, Mc, dtype=BF), rnd(P, Nc, seed=1, dtype=BF)
+            out = torch.full((Mc, Nc), 7.0, device=dev())
+            run(lambda b: b.wgrad(A, Bm, out, Mc=Mc, Nc=Nc, so_m=Nc, so_n=1, P=P, workspace=ws))
+            ref = A.float().t() @ Bm.float()
+        elif case == "conv3":
+            NB, H, W, Cin, Cout, k, pad = 6, 16, 16, 128, 256, 3, 1
+            x, dy = rnd(NB, H, W, Cin, dtype=BF), rnd(NB, H, W, Cout, seed=1, dtype=BF)
+            out = torch.full((Cout, Cin, k, k), 7.0, device=dev())
+            run(lambda b: b.wgrad(dy, x, out, Mc=Cout, Nc=Cin, so_m=Cin * k * k, so_n=k * k, so_t=1,
+                                  conv=dict(KH=k, KW=k, pad=pad), workspace=ws))
+            w = torch.zeros(Cout, Cin, k, k, device=dev(), requires_grad=True)
+            F.conv2d(x.float().permute(0, 3, 1, 2), w, None, 1, pad).backward(dy.float().permute(0, 3, 1, 2))
+            ref = w.grad
+        elif case == "convT4":
+            NB, Cin, Cout = 3, 128, 128
+            x, dy = rnd(NB, 47, 47, Cin, dtype=BF), rnd(NB, 48, 48, Cout, seed=1, dtype=BF)
+            out = torch.full((Cin, Cout, 4, 4), 7.0, device=dev())
+            run(lambda b: b.wgrad(x, dy, out, Mc=Cin, Nc=Cout, so_m=Cout * 16, so_n=16, so_t=1, conv=dict(KH=4, KW=4, pad=1),
+                                  workspace=ws))
+            w = torch.zeros(Cin, Cout, 4, 4, device=dev(), requires_grad=True)
+            F.conv_transpose2d(x.float().permute(0, 3, 1, 2), w, None, 1, 1).backward(dy.float().permute(0, 3, 1, 2))
+            ref = w.grad
+        else:
+            P, Cout, Cin, taps = 2048, 128, 64, 9
+            A, col = rnd(P, Cout, dtype=BF), rnd(P, taps * Cin, seed=1, dtype=BF)
+            out = torch.full((Cout, Cin, taps), 7.0, device=dev())
+            run(lambda b: b.wgrad(A, col, out, Mc=Cout, Nc=taps * Cin, so_m=Cin * taps, so_n=taps, so_no=1, n_inner=Cin, P=P,
+                                  workspace=ws))
+            ref = (A.float().t() @ col.float()).view(Cout, taps, Cin).permute(0, 2, 1)
+        assert rel(out, ref) < 2e-3
+        outs.append(out.clone())
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_wgrad_plain_decomposed_offsets():
     """n = tap*Cin + ci scattered into a [Cout, Cin, 9] gradient (strided-conv layers)."""
     P, Cout, Cin, taps = 512, 128, 64, 9

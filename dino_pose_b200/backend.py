@@ -284,7 +284,7 @@ class CudaBackend:
                       _p(add1), _p(gamma), _p(scale),
                       _p(shift), _p(mean), _p(invstd), _p(sums), _p(draw), _p(dres), _p(dgamma), _p(dbeta), P, C,
                       int(relu), mode, int(eval_mode), shuffle_oh, shuffle_ow,
-                      keep=(dout, raw, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta))
+                      keep=(dout, raw, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta), launches=2)
 
     def avgpool2(self, x, out, *, planes, OH, OW):
         self.prog.add("avgpool2", self.lib.dp_avgpool2, _p(x), _p(out), planes, OH, OW, keep=(x, out))

@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 
@@ -205,8 +206,19 @@ __global__ void __launch_bounds__(128) attention_fwd_kernel(const __nv_bfloat16*
 
 }  // namespace
 
+cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, int B, int T, int heads, float scale,
+                                cudaStream_t s);
+
 cudaError_t launch_attention_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, int B, int T, int heads, float scale,
                                  cudaStream_t s) {
+  // short sequences (224x224 images: 257 tokens) run on the tcgen05 kernel; longer ones (448x448: 1025) on the
+  // mma.sync flash kernel below.  DP_ATTN_LEGACY=1 forces the latter (A/B comparison).
+  static int legacy = -1;
+  if (legacy < 0) { const char* v = getenv("DP_ATTN_LEGACY"); legacy = v ? atoi(v) : 0; }
+  if (!legacy) {
+    cudaError_t e = launch_attention_tc(qkv, ctx, B, T, heads, scale, s);
+    if (e != cudaErrorNotSupported) return e;
+  }
   const int D = heads * kDH;
   dim3 grid((T + kBQ - 1) / kBQ, heads, B);
   attention_fwd_kernel<<<grid, 128, 0, s>>>(qkv, ctx, T, D, scale * 1.4426950408889634f);

@@ -1,0 +1,254 @@
+// Multi-head attention forward on tcgen05 / TMEM for short sequences (T <= 272: the 257 tokens of a 224x224 image).
+// HF modeling_dinov2.py:203-234: softmax(q k^T / sqrt(dh)) v, non-causal, no mask, dropout 0, head dim 64.
+//
+// One CTA per (image, head); the whole K and V of that head stay in shared memory (TMA, 128B swizzle):
+//     S[128 q, Tk] = Q_tile K^T      tcgen05.mma, both operands K-major, N = 256 (+16), accumulator in TMEM
+//     P = exp2(S*c - max*c)          4 warps, thread = query row, two passes over the TMEM row (max, then exp + row sum),
+//                                    P written as bf16 into a K-major 128B-swizzled shared-memory operand
+//     O[128 q, 64] = P V             tcgen05.mma, A = P (K-major), B = V (MN-major: keys are the reduction dim)
+//     ctx = O / rowsum               TMEM -> registers -> 128 contiguous bytes per query row
+// Query tiles of 128 rows (3 per head at T = 257; the last holds the single remaining row).  One thread issues TMA and
+// MMA; the S-MMA of tile i+1 is issued right behind the PV-MMA of tile i so it runs under the epilogue of tile i.
+// Rows of the K / V boxes beyond T belong to the next image (or are zero-filled past the end of the tensor): their
+// scores are masked to -inf, so their P is exactly 0.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "ptx.cuh"
+
+namespace dp {
+namespace {
+
+constexpr int kTile = 128;          // query rows per tile, key rows per TMA box
+constexpr int kDh = 64;
+constexpr int kTileBytes = kTile * kDh * 2;   // 16 KB
+constexpr int kMaxKeyTiles = 3;     // 384 key rows staged, 272 used at most
+constexpr int kMaxPTiles = 5;       // 5 x 64 keys
+constexpr int kThreads = 192;       // warp 0: TMA + MMA issue, warp 1: TMEM alloc, warps 2..5: softmax / epilogue
+constexpr int kSmemBytes = (2 * kMaxKeyTiles + 2 + kMaxPTiles) * kTileBytes + 256;
+constexpr uint32_t kTmemCols = 512;
+constexpr uint32_t kColO = 320;     // O accumulator columns [320, 384)
+
+struct AttnParams {
+  CUtensorMap tm;      // 2-D {3*D, B*T} bf16, box {64, 128}, 128B swizzle
+  __nv_bfloat16* ctx;  // [B*T, D]
+  int T, D, heads, tk_pad, q_tiles;
+  float scale_log2;
+};
+
+__global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_constant__ AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;
+  uint8_t* sV = sK + kMaxKeyTiles * kTileBytes;
+  uint8_t* sQ = sV + kMaxKeyTiles * kTileBytes;       // 2 buffers
+  uint8_t* sP = sQ + 2 * kTileBytes;                   // 5 tiles [128 q x 64 keys]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + kMaxPTiles * kTileBytes);
+  uint64_t* kv_full = bars;          // 1
+  uint64_t* q_full = bars + 1;       // 2
+  uint64_t* s_full = bars + 3;       // 1
+  uint64_t* p_ready = bars + 4;      // 1 (4 warp arrivals)
+  uint64_t* o_full = bars + 5;       // 1
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 6);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x % p.heads, b = blockIdx.x / p.heads;
+  const int row0 = b * p.T;
+  const int key_tiles = (p.tk_pad + kTile - 1) / kTile;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    tma_prefetch_desc(&p.tm);
+    mbar_init(kv_full, 1);
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      // ---- K, V of this (image, head), and the first Q tile
+      mbar_arrive_expect_tx(kv_full, 2 * key_tiles * kTileBytes);
+      for (int t = 0; t < key_tiles; ++t) {
+        tma_load_2d(sK + t * kTileBytes, &p.tm, kv_full, p.D + h * kDh, row0 + t * kTile);
+        tma_load_2d(sV + t * kTileBytes, &p.tm, kv_full, 2 * p.D + h * kDh, row0 + t * kTile);
+      }
+      mbar_arrive_expect_tx(&q_full[0], kTileBytes);
+      tma_load_2d(sQ, &p.tm, &q_full[0], h * kDh, row0);
+      const int n1 = p.tk_pad < 256 ? p.tk_pad : 256, n2 = p.tk_pad - n1;   // S = [N = n1] (+ [N = n2 = 16])
+      const uint32_t idesc_s1 = make_idesc_bf16(kTile, n1, 0, 0);
+      const uint32_t idesc_s2 = make_idesc_bf16(kTile, n2 > 0 ? n2 : 16, 0, 0);
+      const uint32_t idesc_pv = make_idesc_bf16(kTile, kDh, 0, 1);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), p_addr = smem_u32(sP);
+      mbar_wait(kv_full, 0);
+      auto issue_s = [&](int i) {
+        mbar_wait(&q_full[i & 1], (i >> 1) & 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(sQ + (i & 1) * kTileBytes);
+#pragma unroll
+        for (int k = 0; k < kDh / 16; ++k) {
+          const uint64_t adesc = make_sdesc_sw128(q_addr + k * 32, 0, 1024);
+          umma_bf16(tmem_base, adesc, make_sdesc_sw128(k_addr + k * 32, 0, 1024), idesc_s1, k != 0 ? 1u : 0u);
+          if (n2 > 0)
+            umma_bf16(tmem_base + 256, adesc, make_sdesc_sw128(k_addr + 2 * kTileBytes + k * 32, 0, 1024), idesc_s2,
+                      k != 0 ? 1u : 0u);
+        }
+        umma_commit(s_full);
+      };
+      issue_s(0);
+      for (int i = 0; i < p.q_tiles; ++i) {
+        if (i + 1 < p.q_tiles) {   // prefetch the next Q tile (its buffer was last read by S-MMA i-1, long complete)
+          mbar_arrive_expect_tx(&q_full[(i + 1) & 1], kTileBytes);
+          tma_load_2d(sQ + ((i + 1) & 1) * kTileBytes, &p.tm, &q_full[(i + 1) & 1], h * kDh, row0 + (i + 1) * kTile);
+        }
+        mbar_wait(p_ready, i & 1);
+        tc_fence_after();
+        const int ksteps = p.tk_pad / 16;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t adesc = make_sdesc_sw128(p_addr + (k >> 2) * kTileBytes + (k & 3) * 32, 0, 1024);
+          const uint64_t bdesc = make_sdesc_sw128(v_addr + k * 2048, kTileBytes, 1024);
+          umma_bf16(tmem_base + kColO, adesc, bdesc, idesc_pv, k != 0 ? 1u : 0u);
+        }
+        umma_commit(o_full);
+        if (i + 1 < p.q_tiles) issue_s(i + 1);   // S was fully consumed before p_ready(i)
+      }
+    }
+  } else if (warp >= 2) {
+    const int q = warp & 3;                 // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;            // query row inside the tile
+    const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+    const float sl = p.scale_log2;
+    const int nchunks = p.tk_pad / 16;
+    for (int i = 0; i < p.q_tiles; ++i) {
+      mbar_wait(s_full, i & 1);
+      tc_fence_after();
+      // pass 1: row maximum over the valid keys
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(trow + uint32_t(c * 16), v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (c * 16 + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
+      }
+      const float ms = m * sl;
+      // pass 2: P = exp2(s*c - m*c) as bf16 into the K-major swizzled operand tiles, row sum in fp32
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < nchunks; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(trow + uint32_t(c * 16), v);
+        tmem_ld_wait();
+        uint32_t pk[8];
+#pragma unroll
+        for (int j = 0; j < 16; j += 2) {
+          const float e0 = (c * 16 + j < p.T) ? ex2_approx(fmaf(__uint_as_float(v[j]), sl, -ms)) : 0.f;
+          const float e1 = (c * 16 + j + 1 < p.T) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl, -ms)) : 0.f;
+          sum += e0 + e1;
+          pk[j >> 1] = pack_bf16x2(e0, e1);
+        }
+        uint8_t* tile = sP + (c >> 2) * kTileBytes + r * 128;
+        const int c16 = (c & 3) * 2;
+        *reinterpret_cast<uint4*>(tile + (((c16) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        *reinterpret_cast<uint4*>(tile + (((c16 + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+      }
+      fence_proxy_async_smem();   // make the st.shared of P visible to the tensor core (async proxy)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(p_ready);
+      // epilogue of this tile: O / sum -> bf16 -> ctx
+      mbar_wait(o_full, i & 1);
+      tc_fence_after();
+      const float inv = 1.0f / sum;
+      const int t = i * kTile + r;
+      __nv_bfloat16* dst = p.ctx + (long long)(row0 + t) * p.D + h * kDh;
+#pragma unroll
+      for (int c = 0; c < kDh / 16; ++c) {
+        uint32_t v[16];
+        tmem_ld_32x16(trow + kColO + uint32_t(c * 16), v);
+        tmem_ld_wait();
+        if (t < p.T) {
+          uint4 a, bq;
+          a.x = pack_bf16x2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv);
+          a.y = pack_bf16x2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv);
+          a.z = pack_bf16x2(__uint_as_float(v[4]) * inv, __uint_as_float(v[5]) * inv);
+          a.w = pack_bf16x2(__uint_as_float(v[6]) * inv, __uint_as_float(v[7]) * inv);
+          bq.x = pack_bf16x2(__uint_as_float(v[8]) * inv, __uint_as_float(v[9]) * inv);
+          bq.y = pack_bf16x2(__uint_as_float(v[10]) * inv, __uint_as_float(v[11]) * inv);
+          bq.z = pack_bf16x2(__uint_as_float(v[12]) * inv, __uint_as_float(v[13]) * inv);
+          bq.w = pack_bf16x2(__uint_as_float(v[14]) * inv, __uint_as_float(v[15]) * inv);
+          reinterpret_cast<uint4*>(dst + c * 16)[0] = a;
+          reinterpret_cast<uint4*>(dst + c * 16)[1] = bq;
+        }
+      }
+      tc_fence_before();   // O and S of this tile are consumed before the next tile's MMAs may overwrite them
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn attn_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+}  // namespace
+
+// returns cudaErrorNotSupported when the shape is outside this kernel's range (caller falls back to the mma.sync kernel)
+cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, int B, int T, int heads, float scale,
+                                cudaStream_t s) {
+  const int tk_pad = ((T + 15) / 16) * 16;
+  if (tk_pad > 272 || T < 1) return cudaErrorNotSupported;
+  EncodeTiledFn fn = attn_encode_fn();
+  if (!fn || (reinterpret_cast<uintptr_t>(qkv) & 15)) return cudaErrorNotSupported;
+  AttnParams p;
+  const int D = heads * kDh;
+  const cuuint64_t dims[2] = {cuuint64_t(3 * D), cuuint64_t(B) * cuuint64_t(T)};
+  const cuuint64_t strides[1] = {cuuint64_t(3 * D) * 2};
+  const cuuint32_t box[2] = {kDh, kTile}, es[2] = {1, 1};
+  if (fn(&p.tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(qkv), dims, strides, box, es,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return cudaErrorInvalidValue;
+  p.ctx = ctx;
+  p.T = T; p.D = D; p.heads = heads; p.tk_pad = tk_pad;
+  p.q_tiles = (T + kTile - 1) / kTile;
+  p.scale_log2 = scale * 1.4426950408889634f;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr = true;
+  }
+  attention_tc_kernel<<<B * heads, kThreads, kSmemBytes, s>>>(p);
+  return cudaGetLastError();
+}
+
+}  // namespace dp

@@ -302,10 +302,13 @@ extern "C" int dp_wgrad_bf16(const dp_wgrad_args* a, void* stream) {
       // a small linear term for the workspace traffic, at least 8 k-blocks per split, workspace permitting
       double best = 1e30;
       splits = 1;
-      for (int sN = 1; sN <= 32; ++sN) {
+      double per_split = double(slice_bytes) / 4.0e8;   // workspace write + read relative to the operand streaming
+      if (per_split < 0.0005) per_split = 0.0005;
+      if (per_split > 0.01) per_split = 0.01;
+      for (int sN = 1; sN <= 148; ++sN) {
         if (sN > 1 && (p.total_k_blocks / sN < 8 || (long long)sN * slice_bytes > a->workspace_bytes)) break;
         const int rounds = (base_items * sN + sm_count() - 1) / sm_count();
-        const double cost = double(rounds) / sN + 0.01 * sN;
+        const double cost = double(rounds) / sN + per_split * sN;
         if (cost < best - 1e-9) { best = cost; splits = sN; }
       }
     } else {

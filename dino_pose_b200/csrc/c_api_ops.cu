@@ -35,7 +35,7 @@ cudaError_t launch_bn_apply(const void*, int, const float*, const float*, const 
 cudaError_t launch_bn_bwd_reduce(const void*, const void*, int, const void*, const float*, const float*, const float*,
                                  const float*, double*, long long, int, int, int, cudaStream_t);
 cudaError_t launch_bn_bwd_apply(const void*, const void*, int, const void*, const float*, const float*, const float*,
-                                const float*, const float*, const double*, void*, void*, float*, float*, long long, int, int,
+                                const float*, const float*, double*, void*, void*, float*, float*, long long, int, int,
                                 int, int, int, int, cudaStream_t);
 cudaError_t launch_avgpool2(const float*, float*, long long, int, int, cudaStream_t);
 cudaError_t launch_hm_grad_to_nhwc(const float*, void*, int, int, int, int, int, int, cudaStream_t);
@@ -160,10 +160,11 @@ extern "C" int dp_bn_bwd_reduce(const void* dout, const void* raw, int raw_f32, 
 }
 extern "C" int dp_bn_bwd_apply(const void* dout, const void* raw, int raw_f32, const void* add1, const float* gamma,
                                const float* scale,
-                               const float* shift, const float* mean, const float* invstd, const double* sums, void* draw,
+                               const float* shift, const float* mean, const float* invstd, double* sums, void* draw,
                                void* dres, float* dgamma, float* dbeta, long long P, int C, int relu, int mode,
                                int eval_mode, int shuffle_oh, int shuffle_ow, void* stream) {
-  if (!dout || !raw || !scale || !shift || !draw || C % 8) return set_error(-1, "dp_bn_bwd_apply: bad args");
+  if (!dout || !raw || !scale || !shift || !draw || !sums || C % 8 || (!eval_mode && (!gamma || !mean || !invstd)))
+    return set_error(-1, "dp_bn_bwd_apply: bad args");
   return cuda_error(launch_bn_bwd_apply(dout, raw, raw_f32, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta,
                                         P, C, relu, mode, eval_mode, shuffle_oh, shuffle_ow, ST),
                     "dp_bn_bwd_apply");

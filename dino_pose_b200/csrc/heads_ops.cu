@@ -229,6 +229,7 @@ __device__ __forceinline__ void store8(float* p, const float (&f)[8]) {
 }
 
 constexpr int kBnThreads = 256;
+constexpr int kBnBwdReplicas = 8;   // == DP_BN_BWD_REPLICAS (include/dinopose.h)
 
 // block-level reduction of per-thread partial sums that share a channel group, then fp64 atomics
 __device__ __forceinline__ void bn_block_reduce_atomic(float (&s)[8], float (&q)[8], int c8, int C8, int C,
@@ -363,117 +364,192 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const RawT* __rest
   }
 }
 
-// BatchNorm backward, pass 1: with y = raw*scale+shift, xhat = (raw-mean)*invstd,
+// ---- 4-channel helpers for the BatchNorm backward kernels (a thread owns 4 channels: ~50 registers, 5 blocks / SM)
+template <typename T> __device__ __forceinline__ void load4(const T* p, float (&f)[4]);
+template <> __device__ __forceinline__ void load4<float>(const float* p, float (&f)[4]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w;
+}
+template <> __device__ __forceinline__ void load4<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[4]) {
+  const uint2 t = __ldg(reinterpret_cast<const uint2*>(p));
+  const __nv_bfloat162 h0 = *reinterpret_cast<const __nv_bfloat162*>(&t.x);
+  const __nv_bfloat162 h1 = *reinterpret_cast<const __nv_bfloat162*>(&t.y);
+  f[0] = __low2float(h0); f[1] = __high2float(h0); f[2] = __low2float(h1); f[3] = __high2float(h1);
+}
+__device__ __forceinline__ void store4(__nv_bfloat16* p, const float (&f)[4]) {
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]), h1 = __floats2bfloat162_rn(f[2], f[3]);
+  uint2 t;
+  t.x = *reinterpret_cast<uint32_t*>(&h0);
+  t.y = *reinterpret_cast<uint32_t*>(&h1);
+  *reinterpret_cast<uint2*>(p) = t;
+}
+
+// BatchNorm backward, pass 1: with y = raw*scale+shift,
 //   dy = dout * [y > 0]            (mode 0, relu)      | dy = dout * [y + add1 > 0]   (mode 1)
-//   sums[c] += dy ; sums[C + c] += dy * xhat
+//   sums[c] += dy ; sums[C + c] += dy * raw
+// (sum dy*xhat = invstd * (sum dy*raw - mean * sum dy) is formed in fp64 by pass 2: the loop needs no mean / invstd)
 template <typename RawT>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dout, const RawT* __restrict__ raw, const __nv_bfloat16* __restrict__ add1,
-    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ mean,
-    const float* __restrict__ invstd, double* __restrict__ sums, long long P, int C8, int relu, int mode) {
-  const int C = C8 * 8;
-  const int c8 = threadIdx.x % C8;
-  const int rpb = kBnThreads / C8;
-  float sc[8], sh[8], mu[8], is[8], s[8], q[8];
+    const float* __restrict__ scale, const float* __restrict__ shift, double* __restrict__ sums, long long P, int C4,
+    int relu, int mode) {
+  const int C = C4 * 4;
+  const int c4 = threadIdx.x % C4;
+  const int rpb = kBnThreads / C4;
+  float sc[4], sh[4], s[4], q[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    sc[j] = __ldg(scale + c8 * 8 + j);
-    sh[j] = __ldg(shift + c8 * 8 + j);
-    mu[j] = __ldg(mean + c8 * 8 + j);
-    is[j] = __ldg(invstd + c8 * 8 + j);
+  for (int j = 0; j < 4; ++j) {
+    sc[j] = __ldg(scale + c4 * 4 + j);
+    sh[j] = __ldg(shift + c4 * 4 + j);
     s[j] = q[j] = 0.f;
   }
-  // two rows per iteration: all loads of both rows are issued before the math (bytes in flight per thread x2)
+  const bool masked = relu || mode == 1;
+  // two rows per iteration: all loads of both rows are issued before the math
   const long long stride = (long long)gridDim.x * rpb;
-  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C8; row < P; row += 2 * stride) {
-    const long long o0 = row * C + c8 * 8;
+  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C4; row < P; row += 2 * stride) {
+    const long long o0 = row * C + c4 * 4;
     const bool two = row + stride < P;
-    const long long o1 = two ? (row + stride) * C + c8 * 8 : o0;
-    float r0[8], g0[8], a0[8], r1[8], g1[8], a1[8];
-    load8(raw + o0, r0);
-    load8(dout + o0, g0);
-    load8(raw + o1, r1);
-    load8(dout + o1, g1);
+    const long long o1 = two ? (row + stride) * C + c4 * 4 : o0;
+    float r0[4], g0[4], a0[4], r1[4], g1[4], a1[4];
+    load4(raw + o0, r0);
+    load4(dout + o0, g0);
+    load4(raw + o1, r1);
+    load4(dout + o1, g1);
     if (mode == 1) {
-      load8(add1 + o0, a0);
-      load8(add1 + o1, a1);
+      load4(add1 + o0, a0);
+      load4(add1 + o1, a1);
     }
     const float w1 = two ? 1.f : 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y0 = r0[j] * sc[j] + sh[j], y1 = r1[j] * sc[j] + sh[j];
+    for (int j = 0; j < 4; ++j) {
+      float y0 = fmaf(r0[j], sc[j], sh[j]), y1 = fmaf(r1[j], sc[j], sh[j]);
       if (mode == 1) { y0 += a0[j]; y1 += a1[j]; }
-      const float gj0 = ((relu || mode == 1) && !(y0 > 0.f)) ? 0.f : g0[j];
-      const float gj1 = ((relu || mode == 1) && !(y1 > 0.f)) ? 0.f : g1[j] * w1;
+      const float gj0 = (masked && !(y0 > 0.f)) ? 0.f : g0[j];
+      const float gj1 = (masked && !(y1 > 0.f)) ? 0.f : g1[j] * w1;
       s[j] += gj0 + gj1;
-      q[j] += (gj0 * (r0[j] - mu[j]) + gj1 * (r1[j] - mu[j])) * is[j];
+      q[j] = fmaf(gj0, r0[j], fmaf(gj1, r1[j], q[j]));
     }
   }
-  bn_block_reduce_atomic(s, q, c8, C8, C, sums);
+  // block reduction over the threads that share a channel group, then fp64 atomics
+  __shared__ float red[kBnThreads][9];
+  const int tid = threadIdx.x;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    red[tid][j] = s[j];
+    red[tid][4 + j] = q[j];
+  }
+  __syncthreads();
+  if (tid < C4) {
+    float ts[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ts[j] = 0.f;
+    for (int t = tid; t < kBnThreads; t += C4)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) ts[j] += red[t][j];
+    // kBnBwdReplicas copies of the accumulators: ~700 blocks adding to the same 2*C addresses serialise in L2
+    double* dst = sums + (long long)(blockIdx.x % kBnBwdReplicas) * 2 * C;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(dst + c4 * 4 + j, double(ts[j]));
+      atomicAdd(dst + C + c4 * 4 + j, double(ts[4 + j]));
+    }
+  }
+}
+
+// between the passes (C threads): add the replicas up, form the three per-channel coefficients of pass 2 in fp64,
+// emit dgamma / dbeta, and re-zero the accumulators for the next step.  coef = [A | B | K] fp32, 3*C.
+__global__ void bn_bwd_coeffs_kernel(double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ scale,
+                                     const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ coef,
+                                     float* __restrict__ dgamma, float* __restrict__ dbeta, int C, double invP, int eval_mode) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double S1 = 0.0, Q = 0.0;
+#pragma unroll
+  for (int rpl = 0; rpl < kBnBwdReplicas; ++rpl) {
+    S1 += sums[(long long)rpl * 2 * C + c];
+    Q += sums[(long long)rpl * 2 * C + C + c];
+    sums[(long long)rpl * 2 * C + c] = 0.0;
+    sums[(long long)rpl * 2 * C + C + c] = 0.0;
+  }
+  if (eval_mode) {
+    coef[c] = scale[c];
+    coef[C + c] = 0.f;
+    coef[2 * C + c] = 0.f;
+    if (dgamma != nullptr) { dgamma[c] = 0.f; dbeta[c] = float(S1); }
+    return;
+  }
+  const double mu = double(mean[c]), is = double(invstd[c]);
+  const double S2 = is * (Q - mu * S1);
+  const double A = double(gamma[c]) * is, k2 = is * S2 * invP;
+  coef[c] = float(A);
+  coef[C + c] = float(-A * k2);
+  coef[2 * C + c] = float(A * (k2 * mu - S1 * invP));
+  if (dgamma != nullptr) { dgamma[c] = float(S2); dbeta[c] = float(S1); }
 }
 
 // pass 2: draw = gamma*invstd * (dy - S1/P - xhat*S2/P)  (train)   |   draw = dy * scale (eval_mode)
+// with S1 = sum dy, S2 = sum dy*xhat = invstd * (sums[C+c] - mean*S1).  Per channel this is  A*dy + B*raw + K
+// (A = gamma*invstd, B = -A*invstd*S2/P, K = A*(invstd*S2/P*mean - S1/P)), so the row loop needs 5 coefficients.
 // Also emits dgamma = S2, dbeta = S1 (block 0) and, for mode 1, the masked gradient of the residual branch.
 // shuffle_oh > 0: write draw in the un-shuffled [P/4, 4*Cout] "col" layout of a k2 s2 transposed conv
 // (row = input pixel, column = tap*Cout + co), the operand layout of its weight / input gradients.
 template <typename RawT>
 __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ dout, const RawT* __restrict__ raw, const __nv_bfloat16* __restrict__ add1,
-    const float* __restrict__ gamma, const float* __restrict__ scale, const float* __restrict__ shift,
-    const float* __restrict__ mean, const float* __restrict__ invstd, const double* __restrict__ sums,
-    __nv_bfloat16* __restrict__ draw, __nv_bfloat16* __restrict__ dres, float* __restrict__ dgamma,
-    float* __restrict__ dbeta, long long P, int C8, int relu, int mode, int eval_mode, int shuffle_oh, int shuffle_ow) {
-  const int C = C8 * 8;
-  const int c8 = threadIdx.x % C8;
-  const int rpb = kBnThreads / C8;
-  const float invP = 1.0f / float(P);
-  float sc[8], sh[8], mu[8], is[8], gi[8], s1[8], s2[8];
+    const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
+    __nv_bfloat16* __restrict__ draw, __nv_bfloat16* __restrict__ dres, long long P, int C4, int relu, int mode,
+    int shuffle_oh, int shuffle_ow) {
+  const int C = C4 * 4;
+  const int c4 = threadIdx.x % C4;
+  const int rpb = kBnThreads / C4;
+  float sc[4], sh[4], ka[4], kb[4], kc[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = c8 * 8 + j;
+  for (int j = 0; j < 4; ++j) {
+    const int c = c4 * 4 + j;
     sc[j] = __ldg(scale + c);
     sh[j] = __ldg(shift + c);
-    if (!eval_mode) {
-      mu[j] = __ldg(mean + c);
-      is[j] = __ldg(invstd + c);
-      gi[j] = __ldg(gamma + c) * is[j];
-      s1[j] = float(sums[c]) * invP;
-      s2[j] = float(sums[C + c]) * invP;
-    } else {
-      mu[j] = is[j] = gi[j] = s1[j] = s2[j] = 0.f;
-    }
+    ka[j] = __ldg(coef + c);
+    kb[j] = __ldg(coef + C + c);
+    kc[j] = __ldg(coef + 2 * C + c);
   }
-  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C8; row < P; row += (long long)gridDim.x * rpb) {
-    const long long o = row * C + c8 * 8;
-    float r[8], g[8], a[8], ov[8];
-    load8(raw + o, r);
-    load8(dout + o, g);
-    if (mode == 1) load8(add1 + o, a);
+  const bool masked = relu || mode == 1;
+  const long long stride = (long long)gridDim.x * rpb;
+  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C4; row < P; row += 2 * stride) {
+    const bool two = row + stride < P;
+    const long long rows[2] = {row, two ? row + stride : row};
+    float r[2][4], g[2][4], a[2][4];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float y = r[j] * sc[j] + sh[j];
-      if (mode == 1) y += a[j];
-      if ((relu || mode == 1) && !(y > 0.f)) g[j] = 0.f;
-      ov[j] = eval_mode ? g[j] * sc[j] : gi[j] * (g[j] - s1[j] - (r[j] - mu[j]) * is[j] * s2[j]);
+    for (int u = 0; u < 2; ++u) {
+      const long long o = rows[u] * C + c4 * 4;
+      load4(raw + o, r[u]);
+      load4(dout + o, g[u]);
+      if (mode == 1) load4(add1 + o, a[u]);
     }
-    long long oo = o;
-    if (shuffle_oh > 0) {
-      // row indexes the shuffled NHWC output [NB, 2*ih, 2*iw, C]; destination is [NB*ih*iw, 4*C]
-      long long p = row;
-      const int x = int(p % shuffle_ow); p /= shuffle_ow;
-      const int y = int(p % shuffle_oh);
-      const long long b = p / shuffle_oh;
-      const int ih = shuffle_oh / 2, iw = shuffle_ow / 2;
-      const int tap = (y & 1) * 2 + (x & 1);
-      oo = ((((b * ih + (y >> 1)) * iw + (x >> 1)) * 4 + tap) * C8 + c8) * 8;
-    }
-    store8(draw + oo, ov);
-    if (dres != nullptr) store8(dres + o, g);
-  }
-  if (blockIdx.x == 0 && dgamma != nullptr) {
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-      dbeta[c] = float(sums[c]);
-      dgamma[c] = float(sums[C + c]);
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (u == 1 && !two) break;
+      const long long o = rows[u] * C + c4 * 4;
+      float ov[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float y = fmaf(r[u][j], sc[j], sh[j]);
+        if (mode == 1) y += a[u][j];
+        if (masked && !(y > 0.f)) g[u][j] = 0.f;
+        ov[j] = fmaf(ka[j], g[u][j], fmaf(kb[j], r[u][j], kc[j]));
+      }
+      long long oo = o;
+      if (shuffle_oh > 0) {
+        // row indexes the shuffled NHWC output [NB, 2*ih, 2*iw, C]; destination is [NB*ih*iw, 4*C]
+        long long p = rows[u];
+        const int x = int(p % shuffle_ow); p /= shuffle_ow;
+        const int y = int(p % shuffle_oh);
+        const long long b = p / shuffle_oh;
+        const int ih = shuffle_oh / 2, iw = shuffle_ow / 2;
+        const int tap = (y & 1) * 2 + (x & 1);
+        oo = ((((b * ih + (y >> 1)) * iw + (x >> 1)) * 4 + tap) * C4 + c4) * 4;
+      }
+      store4(draw + oo, ov);
+      if (dres != nullptr) store4(dres + o, g[u]);
     }
   }
 }
@@ -728,6 +804,14 @@ cudaError_t launch_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, 
                                                         dw, NB, H, W, C8);
   return cudaGetLastError();
 }
+// backward kernels: 4 channels per thread, 2 rows per iteration, up to 5 resident blocks per SM
+static unsigned bn_grid4(long long P, int C4) {
+  const int rpb = kBnThreads / C4;
+  long long g = (P + 2 * rpb - 1) / (2 * rpb);
+  const long long cap = 148 * 5;
+  if (g > cap) g = cap;
+  return unsigned(g < 1 ? 1 : g);
+}
 static unsigned bn_grid(long long P, int C8) {
   const int rpb = kBnThreads / C8;
   long long g = (P + rpb - 1) / rpb;
@@ -772,28 +856,32 @@ cudaError_t launch_bn_apply(const void* raw, int raw_f32, const float* scale, co
 cudaError_t launch_bn_bwd_reduce(const void* dout, const void* raw, int raw_f32, const void* add1, const float* scale,
                                  const float* shift, const float* mean, const float* invstd, double* sums, long long P,
                                  int C, int relu, int mode, cudaStream_t s) {
-  if (!bn_c_ok(C)) return cudaErrorInvalidValue;
+  if (!bn_c_ok(C) || C / 4 > kBnThreads) return cudaErrorInvalidValue;
   auto d = reinterpret_cast<const __nv_bfloat16*>(dout);
   auto a1 = reinterpret_cast<const __nv_bfloat16*>(add1);
   if (raw_f32)
-    bn_bwd_reduce_kernel<float><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(d, reinterpret_cast<const float*>(raw), a1, scale, shift, mean, invstd, sums, P, C / 8, relu, mode);
+    bn_bwd_reduce_kernel<float><<<bn_grid4(P, C / 4), kBnThreads, 0, s>>>(d, reinterpret_cast<const float*>(raw), a1, scale, shift, sums, P, C / 4, relu, mode);
   else
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, mean, invstd, sums, P, C / 8, relu, mode);
+    bn_bwd_reduce_kernel<__nv_bfloat16><<<bn_grid4(P, C / 4), kBnThreads, 0, s>>>(d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, sums, P, C / 4, relu, mode);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_bwd_apply(const void* dout, const void* raw, int raw_f32, const void* add1, const float* gamma,
                                 const float* scale, const float* shift, const float* mean, const float* invstd,
-                                const double* sums, void* draw, void* dres, float* dgamma, float* dbeta, long long P, int C,
+                                double* sums, void* draw, void* dres, float* dgamma, float* dbeta, long long P, int C,
                                 int relu, int mode, int eval_mode, int shuffle_oh, int shuffle_ow, cudaStream_t s) {
-  if (!bn_c_ok(C)) return cudaErrorInvalidValue;
+  if (!bn_c_ok(C) || C / 4 > kBnThreads) return cudaErrorInvalidValue;
   auto d = reinterpret_cast<const __nv_bfloat16*>(dout);
   auto a1 = reinterpret_cast<const __nv_bfloat16*>(add1);
   auto dr = reinterpret_cast<__nv_bfloat16*>(draw);
   auto ds = reinterpret_cast<__nv_bfloat16*>(dres);
+  // coefficient scratch: the (DP_BN_BWD_REPLICAS + 1)-th 2*C block of `sums` (16*C bytes >= 3*C floats)
+  float* coef = reinterpret_cast<float*>(sums + (long long)kBnBwdReplicas * 2 * C);
+  bn_bwd_coeffs_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, gamma, scale, mean, invstd, coef, dgamma, dbeta, C, 1.0 / double(P),
+                                                      eval_mode);
   if (raw_f32)
-    bn_bwd_apply_kernel<float><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(d, reinterpret_cast<const float*>(raw), a1, gamma, scale, shift, mean, invstd, sums, dr, ds, dgamma, dbeta, P, C / 8, relu, mode, eval_mode, shuffle_oh, shuffle_ow);
+    bn_bwd_apply_kernel<float><<<bn_grid4(P, C / 4), kBnThreads, 0, s>>>(d, reinterpret_cast<const float*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow);
   else
-    bn_bwd_apply_kernel<__nv_bfloat16><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, gamma, scale, shift, mean, invstd, sums, dr, ds, dgamma, dbeta, P, C / 8, relu, mode, eval_mode, shuffle_oh, shuffle_ow);
+    bn_bwd_apply_kernel<__nv_bfloat16><<<bn_grid4(P, C / 4), kBnThreads, 0, s>>>(d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow);
   return cudaGetLastError();
 }
 cudaError_t launch_zero_f64(double* p, int n, cudaStream_t s) {

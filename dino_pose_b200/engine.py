@@ -399,7 +399,9 @@ class PoseEngine:
         c = L.cout
         for n in ("scale", "shift", "mean", "invstd"):
             L.t[n] = self.new((c,), F32)
-        L.t["sums"] = self.new((2 * c,), torch.float64)
+        # fp64 statistic accumulators: [:2c] for the forward (fused GEMM statistics / bn_stats -> bn_finalize),
+        # 8 replicas of 2c for the backward reduce (DP_BN_BWD_REPLICAS) + one 2c block of coefficient scratch
+        L.t["sums"] = self.new((2 * c * 9,), torch.float64)
 
     def _conv_forward(self, L, x, NB, training, out_override=None):
         """Records conv (no BN) of layer L on NHWC input x; returns raw (train) or activated (eval) output.
@@ -639,7 +641,6 @@ class PoseEngine:
             be.bn_bwd_apply(dact, r[key], add1, self.p(bn + ".weight"), L.t["scale"], L.t["shift"], L.t["mean"],
                             L.t["invstd"], L.t["sums"], draw, dres, G[bn + ".weight"], G[bn + ".bias"], P=P, C=L.cout,
                             relu=L.relu, mode=mode, shuffle_oh=L.oh if shuffle else 0, shuffle_ow=L.ow if shuffle else 0)
-            be.host("zero_sums", L.t["sums"].zero_)
             return draw
 
         def conv_bwd(key, draw, x_in, want_dx=True, dx_residual=None):

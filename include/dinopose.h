@@ -156,11 +156,16 @@ int dp_bn_fold_eval(const float* gamma, const float* beta, const float* running_
                     const float* conv_bias, float* scale, float* shift, int C, float eps, void* stream);
 int dp_bn_apply(const void* raw, int raw_is_f32, const float* scale, const float* shift, const void* add1,
                 const void* add2, void* out, long long P, int C, int relu, int mode, void* stream);
+/* BatchNorm backward.  `sums` here is fp64 [DP_BN_BWD_REPLICAS + 1][2*C]: the first DP_BN_BWD_REPLICAS blocks are
+ * accumulators, zero on entry of dp_bn_bwd_reduce (the thread blocks spread their atomics over the replicas);
+ * dp_bn_bwd_apply first adds the replicas up, forms the per-channel coefficients (scratch = the last block), writes
+ * dgamma / dbeta and RE-ZEROES the accumulators, then applies draw = A*dy + B*raw + K. */
+#define DP_BN_BWD_REPLICAS 8
 int dp_bn_bwd_reduce(const void* dout, const void* raw, int raw_is_f32, const void* add1, const float* scale, const float* shift,
                      const float* mean, const float* invstd, double* sums, long long P, int C, int relu, int mode,
                      void* stream);
 int dp_bn_bwd_apply(const void* dout, const void* raw, int raw_is_f32, const void* add1, const float* gamma, const float* scale,
-                    const float* shift, const float* mean, const float* invstd, const double* sums, void* draw,
+                    const float* shift, const float* mean, const float* invstd, double* sums, void* draw,
                     void* dres, float* dgamma, float* dbeta, long long P, int C, int relu, int mode, int eval_mode,
                     int shuffle_oh, int shuffle_ow, void* stream);
 int dp_avgpool2(const float* in, float* out, long long planes, int OH, int OW, void* stream);

@@ -291,13 +291,13 @@ class TorchEmulator:
         def fn():
             r = raw.float().view(P, C).double()
             sums[:C] += r.sum(0)
-            sums[C:] += (r * r).sum(0)
+            sums[C:2 * C] += (r * r).sum(0)
         self.prog.calls.append(fn)
 
     def bn_finalize(self, sums, gamma, beta, rm, rv, scale, shift, mean, invstd, *, C, count, eps=1e-5, momentum=0.1):
         def fn():
             m = sums[:C] / count
-            var = (sums[C:] / count - m * m).clamp_min(0)
+            var = (sums[C:2 * C] / count - m * m).clamp_min(0)
             inv = (1.0 / torch.sqrt(var + eps)).float()
             scale.copy_(gamma.detach() * inv)
             shift.copy_(beta.detach() - m.float() * scale)
@@ -347,7 +347,7 @@ class TorchEmulator:
             r, g = self._masked_dy(dout, raw, add1, scale, shift, P, C, relu, mode)
             xhat = (r - mean) * invstd
             sums[:C] += g.double().sum(0)
-            sums[C:] += (g * xhat).double().sum(0)
+            sums[C:2 * C] += (g * xhat).double().sum(0)
         self.prog.calls.append(fn)
 
     def bn_bwd_apply(self, dout, raw, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta, *, P, C,
@@ -359,7 +359,7 @@ class TorchEmulator:
             else:
                 xhat = (r - mean) * invstd
                 s1 = (sums[:C] / P).float()
-                s2 = (sums[C:] / P).float()
+                s2 = (sums[C:2 * C] / P).float()
                 o = gamma.detach() * invstd * (g - s1 - xhat * s2)
             if shuffle_oh > 0:
                 nb = P // (shuffle_oh * shuffle_ow)
@@ -372,7 +372,8 @@ class TorchEmulator:
                 dres.view(P, C).copy_(g.to(dres.dtype))
             if dgamma is not None:
                 dbeta.copy_(sums[:C].float())
-                dgamma.copy_(sums[C:].float())
+                dgamma.copy_(sums[C:2 * C].float())
+            sums.zero_()      # dp_bn_bwd_apply re-zeroes the accumulators
         self.prog.calls.append(fn)
 
     def avgpool2(self, x, out, *, planes, OH, OW):

@@ -485,7 +485,7 @@ def test_batchnorm_train_fwd_bwd(mode, rawdt, C):
     rm, rv = rnd(C, seed=3) * 0.1, rnd(C, seed=4).abs() + 0.5
     add1 = rnd(P, C, seed=5, dtype=BF)
     add2 = rnd(P, C, seed=6, dtype=BF) if mode == 0 else None
-    sums = torch.zeros(2 * C, device=dev(), dtype=torch.float64)
+    sums = torch.zeros(2 * C * 9, device=dev(), dtype=torch.float64)     # (DP_BN_BWD_REPLICAS + 1) x 2C (backward)
     scale, shift, mean, invstd = [torch.zeros(C, device=dev()) for _ in range(4)]
     rm2, rv2 = rm.clone(), rv.clone()
     out = torch.zeros(P, C, device=dev(), dtype=BF)

@@ -135,37 +135,79 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_
     for (int i = 0; i < p.q_tiles; ++i) {
       mbar_wait(s_full, i & 1);
       tc_fence_after();
-      // pass 1: row maximum over the valid keys
-      float m = -INFINITY;
+      const bool warp_active = i * kTile + q * 32 < p.T;   // warp-uniform: a warp whose 32 rows are all past T skips
+      float sum = 1.f;
+      if (warp_active) {
+        const int nfull = p.tk_pad >> 6, ntail = (p.tk_pad & 63) >> 4;   // 64-key blocks + 16-key chunks
+        // pass 1: row maximum over the valid keys (64 columns per tcgen05.wait::ld)
+        float m = -INFINITY;
 #pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x16(trow + uint32_t(c * 16), v);
-        tmem_ld_wait();
+        for (int c = 0; c < nfull; ++c) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(trow + uint32_t(c * 64), v0);
+          tmem_ld_32x32(trow + uint32_t(c * 64 + 32), v1);
+          tmem_ld_wait();
+          const bool all_valid = c * 64 + 64 <= p.T;
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (c * 16 + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
-      }
-      const float ms = m * sl;
-      // pass 2: P = exp2(s*c - m*c) as bf16 into the K-major swizzled operand tiles, row sum in fp32
-      float sum = 0.f;
-#pragma unroll 1
-      for (int c = 0; c < nchunks; ++c) {
-        uint32_t v[16];
-        tmem_ld_32x16(trow + uint32_t(c * 16), v);
-        tmem_ld_wait();
-        uint32_t pk[8];
-#pragma unroll
-        for (int j = 0; j < 16; j += 2) {
-          const float e0 = (c * 16 + j < p.T) ? ex2_approx(fmaf(__uint_as_float(v[j]), sl, -ms)) : 0.f;
-          const float e1 = (c * 16 + j + 1 < p.T) ? ex2_approx(fmaf(__uint_as_float(v[j + 1]), sl, -ms)) : 0.f;
-          sum += e0 + e1;
-          pk[j >> 1] = pack_bf16x2(e0, e1);
+          for (int j = 0; j < 32; ++j) {
+            if (all_valid || c * 64 + j < p.T) m = fmaxf(m, __uint_as_float(v0[j]));
+            if (all_valid || c * 64 + 32 + j < p.T) m = fmaxf(m, __uint_as_float(v1[j]));
+          }
         }
-        uint8_t* tile = sP + (c >> 2) * kTileBytes + r * 128;
-        const int c16 = (c & 3) * 2;
-        *reinterpret_cast<uint4*>(tile + (((c16) ^ (r & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        *reinterpret_cast<uint4*>(tile + (((c16 + 1) ^ (r & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+#pragma unroll 1
+        for (int c = 0; c < ntail; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x16(trow + uint32_t(nfull * 64 + c * 16), v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (nfull * 64 + c * 16 + j < p.T) m = fmaxf(m, __uint_as_float(v[j]));
+        }
+        const float ms = m * sl;
+        // pass 2: P = exp2(s*c - m*c) as bf16 into the K-major swizzled operand tiles, row sum in fp32
+        sum = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < nfull; ++c) {
+          uint32_t v0[32], v1[32];
+          tmem_ld_32x32(trow + uint32_t(c * 64), v0);
+          tmem_ld_32x32(trow + uint32_t(c * 64 + 32), v1);
+          tmem_ld_wait();
+          const bool all_valid = c * 64 + 64 <= p.T;
+          uint8_t* tile = sP + c * kTileBytes + r * 128;
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {        // 8 x 16-byte chunks (8 keys each) of this row of the P tile
+            const uint32_t* v = g < 4 ? v0 + g * 8 : v1 + (g - 4) * 8;
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float x = ex2_approx(fmaf(__uint_as_float(v[j]), sl, -ms));
+              e[j] = (all_valid || c * 64 + g * 8 + j < p.T) ? x : 0.f;
+            }
+            s0 += (e[0] + e[1]) + (e[2] + e[3]);
+            s1 += (e[4] + e[5]) + (e[6] + e[7]);
+            *reinterpret_cast<uint4*>(tile + ((g ^ (r & 7)) << 4)) =
+                make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+          }
+          sum += s0 + s1;
+        }
+#pragma unroll 1
+        for (int c = 0; c < ntail; ++c) {
+          uint32_t v[16];
+          tmem_ld_32x16(trow + uint32_t(nfull * 64 + c * 16), v);
+          tmem_ld_wait();
+          uint8_t* tile = sP + nfull * kTileBytes + r * 128;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float e[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              e[j] = (nfull * 64 + c * 16 + g * 8 + j < p.T) ? ex2_approx(fmaf(__uint_as_float(v[g * 8 + j]), sl, -ms)) : 0.f;
+            sum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+            *reinterpret_cast<uint4*>(tile + (((c * 2 + g) ^ (r & 7)) << 4)) =
+                make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+          }
+        }
       }
       fence_proxy_async_smem();   // make the st.shared of P visible to the tensor core (async proxy)
       tc_fence_before();
@@ -174,6 +216,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_
       // epilogue of this tile: O / sum -> bf16 -> ctx
       mbar_wait(o_full, i & 1);
       tc_fence_after();
+      if (!warp_active) continue;
       const float inv = 1.0f / sum;
       const int t = i * kTile + r;
       __nv_bfloat16* dst = p.ctx + (long long)(row0 + t) * p.D + h * kDh;

@@ -811,7 +811,28 @@ class PoseEngine:
         plan["t"]["px"].copy_(pixel_values, non_blocking=True)
         if training:
             self.seed.add_(1)
-        plan["fwd"].run()
+            plan["fwd"].run()
+            return plan
+        # inference: the ~130 launches of the forward program are replayed as ONE CUDA graph (batch-1 latency is
+        # launch-bound otherwise); first call runs eagerly (lazy kernel attributes), second call captures
+        if getattr(self.be, "name", "") != "cuda" or not self.cfg.get("infer_graph", True):
+            plan["fwd"].run()
+            return plan
+        calls = plan["calls"] = plan.get("calls", 0) + 1
+        if calls == 1:
+            plan["fwd"].run()
+        else:
+            if plan.get("graph") is None:
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                side = torch.cuda.Stream(device=self.device)
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side), torch.no_grad():
+                    with torch.cuda.graph(g, stream=side, capture_error_mode="thread_local"):
+                        plan["fwd"].run()
+                torch.cuda.current_stream().wait_stream(side)
+                plan["graph"] = g
+            plan["graph"].replay()
         return plan
 
     def backward(self, plan, dhm, dz, on_mark=None):

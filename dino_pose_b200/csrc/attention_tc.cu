@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 #include "ptx.cuh"
 
@@ -247,6 +249,326 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_
   if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------
+// T == 257 (CLS + 16x16 patches of a 224x224 image): the shape of every benchmark configuration at 224^2.
+// One CTA per (image, head, 128-query tile), TWO CTAs per SM (96 KB shared memory, 256 TMEM columns each), so the
+// TMA / MMA / softmax / epilogue phases of two tiles interleave on one SM.  257 = 2*128 + 1 on both axes:
+//   * the 257th KEY is a rank-1 correction on the CUDA cores: s_x = q.k_256 joins the row max / sum, and
+//     p_x * v_256 is added to O in the epilogue -- the tensor-core part is exactly N = 256 keys;
+//   * the 257th QUERY is computed entirely on the CUDA cores by the otherwise idle warp 1 of the second tile's CTA.
+// Shared memory is re-used inside the tile: P (4 tiles of 64 keys) overwrites K (dead after the S-MMA, tiles 0-1) and
+// Q (tile 2); O overwrites TMEM columns [0, 64) of S.
+constexpr int kSmem257 = 6 * kTileBytes + 1024;   // K0 K1 V0 V1 Q P3 + extra rows / barriers
+
+struct Attn257Params {
+  CUtensorMap tm;
+  const __nv_bfloat16* qkv;
+  __nv_bfloat16* ctx;
+  long long* trace;   // debug (DP_ATTN_TRACE=1): timestamps of CTA 1 (second query tile of image 0, head 0)
+  int D, heads;
+  float scale_log2;
+};
+
+__device__ __forceinline__ void unpack8_bf16(const uint4& t, float (&f)[8]) {
+  const uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const __nv_bfloat162 hh = *reinterpret_cast<const __nv_bfloat162*>(&w[k]);
+    f[2 * k] = __low2float(hh);
+    f[2 * k + 1] = __high2float(hh);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 2) attention_tc257_kernel(const __grid_constant__ Attn257Params p) {
+  constexpr int T = 257;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sK = smem;                          // 2 tiles; later P tiles 0, 1
+  uint8_t* sV = sK + 2 * kTileBytes;           // 2 tiles
+  uint8_t* sQ = sV + 2 * kTileBytes;           // 1 tile; later P tile 2
+  uint8_t* sP3 = sQ + kTileBytes;              // P tile 3
+  float* xk = reinterpret_cast<float*>(sP3 + kTileBytes);   // k_256, v_256, q_256 as fp32 [64] each
+  float* xv = xk + 64;
+  float* xq = xv + 64;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(xq + 64);
+  uint64_t* ld_full = bars;
+  uint64_t* s_full = bars + 1;
+  uint64_t* k_free = bars + 2;
+  uint64_t* p_ready = bars + 3;
+  uint64_t* o_full = bars + 4;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qt = blockIdx.x & 1;
+  const int h = (blockIdx.x >> 1) % p.heads, b = (blockIdx.x >> 1) / p.heads;
+  const int row0 = b * T;
+  const int ld = 3 * p.D;
+
+  if (threadIdx.x == 0) {
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    tma_prefetch_desc(&p.tm);
+    mbar_init(ld_full, 1);
+    mbar_init(s_full, 1);
+    mbar_init(k_free, 1);
+    mbar_init(p_ready, 4);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+    // loads are issued before the CTA-wide sync: their latency overlaps the TMEM allocation and the extra-row loads
+    mbar_arrive_expect_tx(ld_full, 5 * kTileBytes);
+    tma_load_2d(sQ, &p.tm, ld_full, h * kDh, row0 + qt * kTile);
+    tma_load_2d(sK, &p.tm, ld_full, p.D + h * kDh, row0);
+    tma_load_2d(sK + kTileBytes, &p.tm, ld_full, p.D + h * kDh, row0 + kTile);
+    tma_load_2d(sV, &p.tm, ld_full, 2 * p.D + h * kDh, row0);
+    tma_load_2d(sV + kTileBytes, &p.tm, ld_full, 2 * p.D + h * kDh, row0 + kTile);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_holder, 256);
+    tmem_relinquish();
+    // the 257th token's k / v / q rows of this head (plain loads: 3 x 128 bytes)
+    const __nv_bfloat16* xrow = p.qkv + (long long)(row0 + 256) * ld + h * kDh;
+    for (int i = lane; i < 64; i += 32) {
+      xq[i] = __bfloat162float(xrow[i]);
+      xk[i] = __bfloat162float(xrow[p.D + i]);
+      xv[i] = __bfloat162float(xrow[2 * p.D + i]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  long long* tr = (p.trace != nullptr && blockIdx.x == 1) ? p.trace : nullptr;
+  if (tr && threadIdx.x == 64) tr[0] = clock64();
+
+  if (warp == 0) {
+    if (elect_one()) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(kTile, 256, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(kTile, kDh, 0, 1);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV), q_addr = smem_u32(sQ), p3_addr = smem_u32(sP3);
+      mbar_wait(ld_full, 0);
+      tc_fence_after();
+      if (tr) tr[1] = clock64();
+#pragma unroll
+      for (int k = 0; k < kDh / 16; ++k)
+        umma_bf16(tmem_base, make_sdesc_sw128(q_addr + k * 32, 0, 1024), make_sdesc_sw128(k_addr + k * 32, 0, 1024), idesc_s,
+                  k != 0 ? 1u : 0u);
+      umma_commit(s_full);
+      mbar_wait(p_ready, 0);
+      tc_fence_after();
+      if (tr) tr[6] = clock64();
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int pt = k >> 2;   // P tile: 0, 1 live where K was, 2 where Q was, 3 in its own buffer
+        const uint32_t pa = (pt < 2 ? k_addr + pt * kTileBytes : (pt == 2 ? q_addr : p3_addr)) + (k & 3) * 32;
+        umma_bf16(tmem_base, make_sdesc_sw128(pa, 0, 1024), make_sdesc_sw128(v_addr + k * 2048, kTileBytes, 1024), idesc_pv,
+                  k != 0 ? 1u : 0u);
+      }
+      umma_commit(o_full);
+    }
+  } else if (warp == 1) {
+    if (qt == 0) {
+      if (lane == 0) mbar_arrive(k_free);
+    } else {
+      // ---- query row 256 on the CUDA cores.  Lane owns keys j = lane + 32*i (i < 8) and, on lane 0, key 256.
+      float qr[64];
+#pragma unroll
+      for (int e = 0; e < 64; ++e) qr[e] = xq[e];
+      mbar_wait(ld_full, 0);
+      const float sl = p.scale_log2;
+      float sc[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) sc[i] = 0.f;
+      // chunk-outer / key-inner: 8 independent FMA chains (one per key) instead of one 64-long chain per key
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 kv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = lane + 32 * i;
+          kv[i] = *reinterpret_cast<const uint4*>(sK + (j >> 7) * kTileBytes + (j & 127) * 128 + ((c ^ (j & 7)) << 4));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float f[8];
+          unpack8_bf16(kv[i], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sc[i] = fmaf(f[e], qr[c * 8 + e], sc[i]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(k_free);   // K has been read: the softmax warps may overwrite it with P
+      if (tr && lane == 0) tr[12] = clock64();
+      {
+        float acc = 0.f;
+#pragma unroll
+        for (int e = 0; e < 64; ++e) acc = fmaf(xk[e], qr[e], acc);
+        sc[8] = (lane == 0) ? acc : -INFINITY;   // key 256
+      }
+      float m = sc[0];
+#pragma unroll
+      for (int i = 1; i < 9; ++i) m = fmaxf(m, sc[i]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 9; ++i) {
+        sc[i] = ex2_approx((sc[i] - m) * sl);   // exp2(-inf) = 0 for the padding lanes of i = 8
+        sum += sc[i];
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      // partial O over this lane's keys, all 64 dims in registers (re-using qr), then a recursive-halving reduction
+      // over the lanes: after the step with offset `o` a lane keeps `o * 2` of its dims, at the end 2 dims per lane
+#pragma unroll
+      for (int e = 0; e < 64; ++e) qr[e] = (lane == 0) ? sc[8] * xv[e] : 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        uint4 vv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int j = lane + 32 * i;
+          vv[i] = *reinterpret_cast<const uint4*>(sV + (j >> 7) * kTileBytes + (j & 127) * 128 + ((c ^ (j & 7)) << 4));
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float f[8];
+          unpack8_bf16(vv[i], f);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) qr[c * 8 + e] = fmaf(sc[i], f[e], qr[c * 8 + e]);
+        }
+      }
+      // halving: with offset 16 the lower half-warp keeps dims [0,32), the upper [32,64); and so on
+#pragma unroll
+      for (int e = 0; e < 32; ++e) {
+        const bool up = (lane & 16) != 0;
+        const float send = up ? qr[e] : qr[32 + e];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
+        qr[e] = (up ? qr[32 + e] : qr[e]) + recv;
+      }
+#pragma unroll
+      for (int e = 0; e < 16; ++e) {
+        const bool up = (lane & 8) != 0;
+        const float send = up ? qr[e] : qr[16 + e];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
+        qr[e] = (up ? qr[16 + e] : qr[e]) + recv;
+      }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const bool up = (lane & 4) != 0;
+        const float send = up ? qr[e] : qr[8 + e];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
+        qr[e] = (up ? qr[8 + e] : qr[e]) + recv;
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool up = (lane & 2) != 0;
+        const float send = up ? qr[e] : qr[4 + e];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
+        qr[e] = (up ? qr[4 + e] : qr[e]) + recv;
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool up = (lane & 1) != 0;
+        const float send = up ? qr[e] : qr[2 + e];
+        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
+        qr[e] = (up ? qr[2 + e] : qr[e]) + recv;
+      }
+      // lane now holds dims d0, d0 + 1 with d0 = 32*b4 + 16*b3 + 8*b2 + 4*b1 + 2*b0 (b_k = bit k of the lane id)
+      const int d0 = ((lane >> 4) & 1) * 32 + ((lane >> 3) & 1) * 16 + ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
+      const float inv = 1.0f / sum;
+      *reinterpret_cast<uint32_t*>(p.ctx + (long long)(row0 + 256) * p.D + h * kDh + d0) = pack_bf16x2(qr[0] * inv, qr[1] * inv);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+    const float sl = p.scale_log2;
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    if (tr && threadIdx.x == 64) tr[2] = clock64();
+    // score against the 257th key: s_x = q_r . k_256 (Q row r from the swizzled tile, k_256 broadcast)
+    float sx = 0.f;
+    {
+      const uint8_t* qrow = sQ + r * 128;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        float f[8];
+        unpack8_bf16(*reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4)), f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sx = fmaf(f[e], xk[c * 8 + e], sx);
+      }
+    }
+    float m = sx;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(trow + uint32_t(c * 64), v0);
+      tmem_ld_32x32(trow + uint32_t(c * 64 + 32), v1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
+    }
+    const float ms = m * sl;
+    const float px = ex2_approx(fmaf(sx, sl, -ms));
+    float sum = px;
+    if (tr && threadIdx.x == 64) tr[3] = clock64();
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      const int c = (cc + 2) & 3;   // P tiles 2, 3 first: tiles 0, 1 overwrite K, which the extra-query warp may still read
+      if (cc == 2) {
+        if (tr && threadIdx.x == 64) tr[4] = clock64();
+        mbar_wait(k_free, 0);
+        if (tr && threadIdx.x == 64) tr[5] = clock64();
+      }
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(trow + uint32_t(c * 64), v0);
+      tmem_ld_32x32(trow + uint32_t(c * 64 + 32), v1);
+      tmem_ld_wait();
+      uint8_t* tile = (c < 2 ? sK + c * kTileBytes : (c == 2 ? sQ : sP3)) + r * 128;
+      float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t* v = g < 4 ? v0 + g * 8 : v1 + (g - 4) * 8;
+        float e[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(v[j]), sl, -ms));
+        s0 += (e[0] + e[1]) + (e[2] + e[3]);
+        s1 += (e[4] + e[5]) + (e[6] + e[7]);
+        *reinterpret_cast<uint4*>(tile + ((g ^ (r & 7)) << 4)) =
+            make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
+      }
+      sum += s0 + s1;
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p_ready);
+    if (tr && threadIdx.x == 64) tr[7] = clock64();
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    if (tr && threadIdx.x == 64) tr[8] = clock64();
+    const float inv = 1.0f / sum;
+    __nv_bfloat16* dst = p.ctx + (long long)(row0 + qt * kTile + r) * p.D + h * kDh;
+    uint32_t v0[32], v1[32];
+    tmem_ld_32x32(trow, v0);
+    tmem_ld_32x32(trow + 32, v1);
+    tmem_ld_wait();
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const uint32_t* v = g < 4 ? v0 + g * 8 : v1 + (g - 4) * 8;
+      float o[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(px, xv[g * 8 + j], __uint_as_float(v[j])) * inv;
+      reinterpret_cast<uint4*>(dst)[g] =
+          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+  }
+  if (tr && threadIdx.x == 64) tr[9] = clock64();
+  if (tr && threadIdx.x == 32) tr[10] = clock64();
+  tc_fence_before();
+  __syncthreads();
+  if (tr && threadIdx.x == 64) tr[11] = clock64();
+  if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -271,6 +593,47 @@ cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, in
   if (tk_pad > 272 || T < 1) return cudaErrorNotSupported;
   EncodeTiledFn fn = attn_encode_fn();
   if (!fn || (reinterpret_cast<uintptr_t>(qkv) & 15)) return cudaErrorNotSupported;
+  static int v1_only = -1;
+  if (v1_only < 0) { const char* v = getenv("DP_ATTN_V1"); v1_only = v ? atoi(v) : 0; }
+  if (T == 257 && !v1_only) {
+    Attn257Params q;
+    const int Dm = heads * kDh;
+    const cuuint64_t dims[2] = {cuuint64_t(3 * Dm), cuuint64_t(B) * cuuint64_t(T)};
+    const cuuint64_t strides[1] = {cuuint64_t(3 * Dm) * 2};
+    const cuuint32_t box[2] = {kDh, kTile}, es[2] = {1, 1};
+    if (fn(&q.tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(qkv), dims, strides, box, es,
+           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return cudaErrorInvalidValue;
+    q.qkv = qkv; q.ctx = ctx; q.D = Dm; q.heads = heads;
+    q.scale_log2 = scale * 1.4426950408889634f;
+    q.trace = nullptr;
+    static int trace_on = -1;
+    if (trace_on < 0) { const char* v = getenv("DP_ATTN_TRACE"); trace_on = v ? atoi(v) : 0; }
+    static long long* dbuf = nullptr;
+    if (trace_on) {
+      if (!dbuf) cudaMalloc(&dbuf, 16 * sizeof(long long));
+      cudaMemsetAsync(dbuf, 0, 16 * sizeof(long long), s);
+      q.trace = dbuf;
+    }
+    static bool attr2 = false;
+    if (!attr2) {
+      cudaError_t e = cudaFuncSetAttribute(attention_tc257_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem257);
+      if (e != cudaSuccess) return e;
+      attr2 = true;
+    }
+    attention_tc257_kernel<<<B * heads * 2, kThreads, kSmem257, s>>>(q);
+    if (trace_on) {   // debug only: synchronises
+      long long h[16];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(h, dbuf, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[attn trace, cycles after CTA sync] ld_full %lld  s_full %lld  pass1 %lld  k_free wait %lld..%lld  "
+              "p_ready(mma) %lld  p_done %lld  o_full %lld  epilogue %lld  warp1 scores %lld  warp1 end %lld  cta end %lld\n",
+              h[1] - h[0], h[2] - h[0], h[3] - h[0], h[4] - h[0], h[5] - h[0], h[6] - h[0], h[7] - h[0], h[8] - h[0],
+              h[9] - h[0], h[12] - h[0], h[10] - h[0], h[11] - h[0]);
+    }
+    return cudaGetLastError();
+  }
   AttnParams p;
   const int D = heads * kDh;
   const cuuint64_t dims[2] = {cuuint64_t(3 * D), cuuint64_t(B) * cuuint64_t(T)};

@@ -266,8 +266,19 @@ def run_ours(args):
         name, a = top
         total_ms = sum(v["ms"] for v in agg.values())
         achieved = a["flops"] / (a["ms"] * 1e-3) / 1e12 if a["ms"] > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")   # ncu --set full of one step, tools/ncu_summary.py traffic
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as f:
+                    traffic = json.load(f).get(name, {}).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
         roof = {"bound": "tensor", "kernel": name, "achieved": achieved, "peak": peaks["tf_sustained"],
-                "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": None,
+                "unit": "TFLOP/s", "frac": achieved / peaks["tf_sustained"], "traffic": traffic,
+                "traffic_source": "profiles/traffic.json (dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over "
+                                  "the launches of this kernel family in one step)" if traffic is not None else None,
+                "algorithmic_flops_per_launch": a["flops"] / a["n"],
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                 "share_of_step": a["ms"] / total_ms, "launches_per_step": a["n"] // reps,
                 "avg_launch_ms": a["ms"] / a["n"],

@@ -211,17 +211,21 @@ cudaError_t launch_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
 // up to Kp (a multiple of 64, so the GEMM k-loop needs no tail).
 __global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ out,
                                                            int B, int H, int W, int gh, int gw, int Kp) {
-  // one block per (b, patch row); threads sweep (c, ky, x) with x fastest -> coalesced reads
+  // one block per (b, patch row); threads sweep (c, ky, x-pair) with x fastest: 8-byte coalesced reads, and an
+  // even x never straddles a 14-wide patch, so each pair is one 4-byte bf16x2 store
   const int b = blockIdx.x / gh, py = blockIdx.x % gh;
-  const int Wv = gw * 14;
-  const int total = 3 * 14 * Wv;
+  const int Wv = gw * 14, Wh = Wv >> 1;
+  const int total = 3 * 14 * Wh;
+#pragma unroll 4
   for (int i = threadIdx.x; i < total; i += blockDim.x) {
-    const int x = i % Wv;
-    const int ky = (i / Wv) % 14;
-    const int c = i / (Wv * 14);
-    const float v = __ldg(px + (((long long)b * 3 + c) * H + (py * 14 + ky)) * W + x);
+    const int xh = i % Wh;
+    const int t = i / Wh;
+    const int ky = t % 14;
+    const int c = t / 14;
+    const int x = xh * 2;
+    const float2 v = __ldg(reinterpret_cast<const float2*>(px + (((long long)b * 3 + c) * H + (py * 14 + ky)) * W + x));
     const long long row = ((long long)b * gh + py) * gw + x / 14;
-    out[row * Kp + c * 196 + ky * 14 + (x % 14)] = __float2bfloat16_rn(v);
+    *reinterpret_cast<uint32_t*>(out + row * Kp + c * 196 + ky * 14 + (x % 14)) = pack_bf16x2(v.x, v.y);
   }
   // zero the K padding of the gw rows owned by this block
   const int padw = Kp - 588;
@@ -291,8 +295,9 @@ __global__ void __launch_bounds__(256) lora_fwd_kernel(const float* __restrict__
     float u[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) u[r] = 0.f;
+#pragma unroll 4
     for (int d = lane; d < D; d += 32) {
-      const float yv = y[row * D + d];
+      const float yv = __ldg(y + row * D + d);
 #pragma unroll
       for (int r = 0; r < R; ++r) u[r] += yv * sA[d * R + r];
     }
@@ -304,6 +309,7 @@ __global__ void __launch_bounds__(256) lora_fwd_kernel(const float* __restrict__
       for (int r = 0; r < R; ++r) mine = (lane == r) ? u[r] : mine;
       u_save[row * R + lane] = mine;
     }
+#pragma unroll 4
     for (int d = lane; d < D; d += 32) {
       float v = 0.f;
 #pragma unroll
@@ -339,8 +345,9 @@ __global__ void __launch_bounds__(256) lora_bwd_gu_kernel(const float* __restric
     float gu[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) gu[r] = 0.f;
+#pragma unroll 4
     for (int d = lane; d < D; d += 32) {
-      float gv = g[row * D + d] * lambda1[d] * scaling;
+      float gv = __ldg(g + row * D + d) * __ldg(lambda1 + d) * scaling;
       if (p_drop > 0.f) gv = dropout_keep(seed, uint64_t(row) * D + d, thresh) ? gv * keep_scale : 0.f;
 #pragma unroll
       for (int r = 0; r < R; ++r) gu[r] += gv * sB[r * D + d];
@@ -374,14 +381,28 @@ __global__ void __launch_bounds__(256) lora_bwd_acc_kernel(const float* __restri
   float aB[R], aA[R];
 #pragma unroll
   for (int r = 0; r < R; ++r) aB[r] = aA[r] = 0.f;
-  for (long long row = r0; row < r1; ++row) {
-    float gv = g[row * D + d] * ld;
-    if (p_drop > 0.f) gv = dropout_keep(seed, uint64_t(row) * D + d, thresh) ? gv * keep_scale : 0.f;
-    const float yv = y[row * D + d];
+  // 4 rows per iteration: the g / y loads of all four rows are in flight together (the loop is latency bound otherwise)
+  for (long long row = r0; row < r1; row += 4) {
+    float gv[4], yv[4];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      aB[r] += __ldg(u_saved + row * R + r) * gv;
-      aA[r] += yv * __ldg(gu + row * R + r);
+    for (int k = 0; k < 4; ++k) {
+      const long long rr = row + k < r1 ? row + k : r1 - 1;
+      gv[k] = __ldg(g + rr * D + d);
+      yv[k] = __ldg(y + rr * D + d);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (row + k >= r1) break;
+      float gk = gv[k] * ld;
+      if (p_drop > 0.f) gk = dropout_keep(seed, uint64_t(row + k) * D + d, thresh) ? gk * keep_scale : 0.f;
+      const float4* up = reinterpret_cast<const float4*>(u_saved + (row + k) * R);
+      const float4* gp = reinterpret_cast<const float4*>(gu + (row + k) * R);
+#pragma unroll
+      for (int r4 = 0; r4 < R / 4; ++r4) {
+        const float4 uu = __ldg(up + r4), gg = __ldg(gp + r4);
+        aB[4 * r4 + 0] += uu.x * gk; aB[4 * r4 + 1] += uu.y * gk; aB[4 * r4 + 2] += uu.z * gk; aB[4 * r4 + 3] += uu.w * gk;
+        aA[4 * r4 + 0] += yv[k] * gg.x; aA[4 * r4 + 1] += yv[k] * gg.y; aA[4 * r4 + 2] += yv[k] * gg.z; aA[4 * r4 + 3] += yv[k] * gg.w;
+      }
     }
   }
 #pragma unroll
@@ -395,7 +416,7 @@ cudaError_t launch_lora_fwd(const float* y, const float* A, const float* Bm, con
                             float* x_out, float* u_save, long long rows, int D, int R, float scaling, float p_drop,
                             const unsigned long long* seed, int sms, cudaStream_t s) {
   const size_t smem = size_t(2) * D * R * sizeof(float);
-  const int grid = sms * 2;
+  const int grid = sms * 6;
   if (R == 8) {
     cudaFuncSetAttribute(lora_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
     lora_fwd_kernel<8><<<grid, 256, smem, s>>>(y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed);
@@ -417,13 +438,13 @@ static cudaError_t lora_bwd_t(const float* g, const float* y, const float* u_sav
                               const unsigned long long* seed, int sms, cudaStream_t s) {
   const size_t smem = size_t(D) * R * sizeof(float);
   cudaFuncSetAttribute(lora_bwd_gu_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  lora_bwd_gu_kernel<R><<<sms * 2, 256, smem, s>>>(g, Bm, lambda1, gu_ws, rows, D, scaling, p_drop, seed);
+  lora_bwd_gu_kernel<R><<<sms * 6, 256, smem, s>>>(g, Bm, lambda1, gu_ws, rows, D, scaling, p_drop, seed);
   const int bx = 128;
   const int gy = (D + bx - 1) / bx;
-  int gx = (sms * 4) / gy;
+  int gx = (sms * 4) / gy;   // more blocks = more same-address atomics on the 2*D*R outputs (measured slower)
   if (gx < 1) gx = 1;
   int rpb = int((rows + gx - 1) / gx);
-  if (rpb < 8) rpb = 8;
+  if (rpb < 16) rpb = 16;
   gx = int((rows + rpb - 1) / rpb);
   lora_bwd_acc_kernel<R><<<dim3(gx, gy), bx, 0, s>>>(g, y, u_saved, gu_ws, lambda1, dA, dB, rows, D, scaling, p_drop, seed, rpb);
   return cudaGetLastError();

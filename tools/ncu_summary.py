@@ -55,5 +55,33 @@ def launch(path):
         print(f"| `{n}` | {c} | {t:.1f} | {100 * t / tot:.1f}% |")
 
 
+def traffic(path):
+    """JSON for bench.py's roofline.traffic: DRAM bytes (read + write) per launch, averaged per kernel family."""
+    import json
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(raw)))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    fam = collections.OrderedDict()
+    for r in rows[2:]:
+        name = short(r[idx["Kernel Name"]])
+        key = "gemm_kmajor_tcgen05" if "gemm_fwd" in name else ("gemm_wgrad_tcgen05" if "gemm_wgrad" in name else name.split("<")[0])
+        b = sum(float(r[idx[k]]) * mult.get(units[idx[k]], 1.0) for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"))
+        us = float(r[idx["gpu__time_duration.sum"]]) * {"us": 1.0, "ns": 1e-3, "ms": 1e3}.get(units[idx["gpu__time_duration.sum"]], 1.0)
+        tens = float(r[idx["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]]) if "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active" in idx else 0.0
+        f = fam.setdefault(key, {"launches": 0, "dram_bytes": 0.0, "us": 0.0, "tensor_pct_time_weighted": 0.0})
+        f["launches"] += 1
+        f["dram_bytes"] += b
+        f["us"] += us
+        f["tensor_pct_time_weighted"] += tens * us
+    out = {}
+    for k, f in fam.items():
+        out[k] = {"launches": f["launches"], "dram_bytes_per_launch": f["dram_bytes"] / f["launches"],
+                  "ncu_us_per_launch": f["us"] / f["launches"],
+                  "tensor_pipe_active_pct": f["tensor_pct_time_weighted"] / f["us"] if f["us"] else 0.0, "source": path}
+    print(json.dumps(out, indent=1))
+
+
 if __name__ == "__main__":
-    {"full": full, "launch": launch}[sys.argv[1]](sys.argv[2])
+    {"full": full, "launch": launch, "traffic": traffic}[sys.argv[1]](sys.argv[2])

@@ -331,6 +331,37 @@ class CudaBackend:
     def mark(self, tag):
         self.prog.add_mark(tag)
 
+    def pack_weights(self, jobs):
+        """jobs: list of (dst bf16 tensor, w fp32 [d0,d1,kh,kw] parameter, order, flips, dst_strides|None): dst (viewed in
+        dst order, extents w.shape[order]) = bf16(w with dims `flips` mirrored, permuted by `order`).  One launch."""
+        rows, max_total = [], 1
+        for dst, w, order, flips, dst_strides in jobs:
+            _chk(dst, torch.bfloat16, "pack.dst", contiguous=False)
+            _chk(w, torch.float32, "pack.src")
+            n = [w.shape[d] for d in order]
+            st, off = [], 0
+            for d in order:
+                sd = w.stride(d)
+                if d in flips:
+                    off += (w.shape[d] - 1) * sd
+                    sd = -sd
+                st.append(sd)
+            if dst_strides is None:
+                dt = [n[1] * n[2] * n[3], n[2] * n[3], n[3], 1]
+            else:
+                dt = list(dst_strides)
+            total = n[0] * n[1] * n[2] * n[3]
+            max_total = max(max_total, total)
+            rows.append([w.data_ptr(), dst.data_ptr()] + n + st + dt + [off, total])
+        table = torch.tensor(rows, dtype=torch.int64).to(jobs[0][0].device)
+        self.prog.add("pack_weights", self.lib.dp_pack_weights_bf16, _p(table), len(rows), max_total,
+                      keep=(table,) + tuple(j[0] for j in jobs) + tuple(j[1] for j in jobs))
+
+    def add_i64(self, tensors, inc=1):
+        """tensors: int64 scalar buffers (BatchNorm num_batches_tracked); *t += inc for all of them in one launch."""
+        ptrs = torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64).to(tensors[0].device)
+        self.prog.add("add_i64", self.lib.dp_add_i64, _p(ptrs), len(tensors), inc, keep=(ptrs,) + tuple(tensors))
+
     # ------------------------------------------------------------------ host-side steps on static tensors
     def host(self, name, fn):
         """Record a torch-level step (memset of gradient buffers, seed increment, ...)."""

@@ -225,3 +225,16 @@ extern "C" int dp_adamw(float* params, const float* grads, float* exp_avg, float
   return cuda_error(launch_adamw(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_scale,
                                  step_dev, sm_count(), ST), "dp_adamw");
 }
+
+namespace dp {
+cudaError_t launch_pack_weights(const long long*, int, long long, int, cudaStream_t);
+cudaError_t launch_add_i64(const long long*, int, long long, cudaStream_t);
+}  // namespace dp
+extern "C" int dp_pack_weights_bf16(const long long* jobs_dev, int njobs, long long max_total, void* stream) {
+  if (!jobs_dev || njobs <= 0 || njobs > 65535 || max_total <= 0) return set_error(-1, "dp_pack_weights_bf16: bad args");
+  return cuda_error(launch_pack_weights(jobs_dev, njobs, max_total, sm_count(), ST), "dp_pack_weights_bf16");
+}
+extern "C" int dp_add_i64(const long long* ptrs_dev, int n, long long inc, void* stream) {
+  if (!ptrs_dev || n <= 0) return set_error(-1, "dp_add_i64: bad args");
+  return cuda_error(launch_add_i64(ptrs_dev, n, inc, ST), "dp_add_i64");
+}

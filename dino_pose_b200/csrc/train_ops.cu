@@ -7,6 +7,7 @@
 //  adamw         torch.optim.AdamW(lr, weight_decay) (train.py:280-284) over ONE flat fp32 parameter buffer with
 //                the flat gradient buffer the backward program fills; bias correction from a device step counter;
 //                gradients pre-scaled by 1/world_size after the data-parallel all-reduce.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -165,4 +166,51 @@ cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long
   return cudaGetLastError();
 }
 
+}  // namespace dp
+
+// ------------------------------------------------------------------------------------------------
+// Weight re-packing after an optimizer step: every trainable conv / transposed-conv weight (fp32 [d0, d1, kh, kw])
+// is copied into the bf16 GEMM layouts the forward and input-gradient kernels read (permuted, taps optionally
+// mirrored).  One launch for all layers: blockIdx.y selects a job from a device-resident table
+//   job[16] = { src ptr, dst ptr, n0..n3 (dst-order extents), s0..s3 (signed src element strides),
+//               t0..t3 (dst element strides), src offset, total }
+// and BatchNorm's num_batches_tracked counters (14 separate int64 buffers) are bumped by one launch too.
+namespace dp {
+namespace {
+__global__ void __launch_bounds__(256) pack_weights_kernel(const long long* __restrict__ jobs) {
+  const long long* j = jobs + (long long)blockIdx.y * 16;
+  const float* src = reinterpret_cast<const float*>(j[0]);
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(j[1]);
+  const long long n1 = j[3], n2 = j[4], n3 = j[5];
+  const long long s0 = j[6], s1 = j[7], s2 = j[8], s3 = j[9];
+  const long long t0 = j[10], t1 = j[11], t2 = j[12], t3 = j[13];
+  const long long off = j[14], total = j[15];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long c3 = i % n3;
+    long long r = i / n3;
+    const long long c2 = r % n2;
+    r /= n2;
+    const long long c1 = r % n1;
+    const long long c0 = r / n1;
+    dst[c0 * t0 + c1 * t1 + c2 * t2 + c3 * t3] = __float2bfloat16_rn(__ldg(src + off + c0 * s0 + c1 * s1 + c2 * s2 + c3 * s3));
+  }
+}
+__global__ void add_i64_kernel(const long long* __restrict__ ptrs, int n, long long inc) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) *reinterpret_cast<long long*>(ptrs[i]) += inc;
+}
+}  // namespace
+
+cudaError_t launch_pack_weights(const long long* jobs_dev, int njobs, long long max_total, int sms, cudaStream_t s) {
+  long long gx = (max_total + 255) / 256;
+  if (gx > 64) gx = 64;     // jobs run side by side: njobs x 64 blocks fill the GPU
+  if (gx < 1) gx = 1;
+  (void)sms;
+  pack_weights_kernel<<<dim3(unsigned(gx), unsigned(njobs)), 256, 0, s>>>(jobs_dev);
+  return cudaGetLastError();
+}
+cudaError_t launch_add_i64(const long long* ptrs_dev, int n, long long inc, cudaStream_t s) {
+  add_i64_kernel<<<(n + 127) / 128, 128, 0, s>>>(ptrs_dev, n, inc);
+  return cudaGetLastError();
+}
 }  // namespace dp

@@ -254,35 +254,33 @@ class PoseEngine:
         for L in Ls.values():
             alloc(L)
 
-        def pack():
-            with torch.no_grad():
-                for L in Ls.values():
-                    if L.kind == "dw":
-                        continue
-                    w = self.p(L.name + ".weight").detach()
-                    k, ci, co = L.k, L.cin, L.cout
-                    kk = k * k
-                    if L.kind == "conv":
-                        L.t["wf"].copy_(w.permute(0, 2, 3, 1).reshape(co, kk * ci))
-                        if L.name.endswith("prediction.3"):
-                            L.t["wd"][:, :co].copy_(w.reshape(co, ci).t())
-                        else:
-                            # dgrad: dIn[y,x,ci] = sum dRaw[y+ky'-pad, x+kx'-pad, co] * W[co,ci,k-1-ky',k-1-kx']
-                            L.t["wd"].copy_(w.flip(2, 3).permute(1, 2, 3, 0).reshape(ci, kk * co))
-                    elif L.kind == "conv_s2":
-                        wf = w.permute(0, 2, 3, 1).reshape(co, kk * ci)
-                        L.t["wf"].copy_(wf)
-                        L.t["wd"].copy_(wf.t())                           # dcol = dRaw @ Wf  -> B operand [N=(tap,ci), K=co]
-                    elif L.kind in ("convT2", "convT"):
-                        L.t["wf"].copy_(w.permute(2, 3, 1, 0).reshape(kk * co, ci))
-                        L.t["wd"].copy_(w.permute(0, 2, 3, 1).reshape(ci, kk * co))
-                    elif L.kind == "convT_s1":
-                        # out[y,x,co] = sum in[y+ky'-2, x+kx'-2, ci] * Wt[ci,co,3-ky',3-kx']
-                        L.t["wf"].copy_(w.flip(2, 3).permute(1, 2, 3, 0).reshape(co, kk * ci))
-                        # dIn[iy,ix,ci] = sum dOut[iy-1+ky, ix-1+kx, co] * Wt[ci,co,ky,kx]
-                        L.t["wd"].copy_(w.permute(0, 2, 3, 1).reshape(ci, kk * co))
-        plan["pack_heads_fn"] = pack
-        be.host("pack_heads", pack)
+        # one launch re-packs every layer (dp_pack_weights_bf16): (dst, parameter, dim order, mirrored dims, dst strides)
+        jobs = []
+        for L in Ls.values():
+            if L.kind == "dw":
+                continue
+            w = self.p(L.name + ".weight")
+            ci, co = L.cin, L.cout
+            if L.kind == "conv":
+                jobs.append((L.t["wf"], w, (0, 2, 3, 1), (), None))                    # [co, (ky,kx,ci)]
+                if L.name.endswith("prediction.3"):
+                    jobs.append((L.t["wd"], w, (1, 0, 2, 3), (), (HM_PAD, 1, 1, 1)))   # [ci, co | zero padding]
+                else:
+                    # dgrad: dIn[y,x,ci] = sum dRaw[y+ky'-pad, x+kx'-pad, co] * W[co,ci,k-1-ky',k-1-kx']
+                    jobs.append((L.t["wd"], w, (1, 2, 3, 0), (2, 3), None))            # [ci, (ky',kx',co)] mirrored taps
+            elif L.kind == "conv_s2":
+                jobs.append((L.t["wf"], w, (0, 2, 3, 1), (), None))
+                jobs.append((L.t["wd"], w, (2, 3, 1, 0), (), None))                    # wf^T: [(ky,kx,ci), co]
+            elif L.kind in ("convT2", "convT"):
+                jobs.append((L.t["wf"], w, (2, 3, 1, 0), (), None))                    # [(ky,kx,co), ci]
+                jobs.append((L.t["wd"], w, (0, 2, 3, 1), (), None))                    # [ci, (ky,kx,co)]
+            elif L.kind == "convT_s1":
+                # out[y,x,co] = sum in[y+ky'-2, x+kx'-2, ci] * Wt[ci,co,3-ky',3-kx']
+                jobs.append((L.t["wf"], w, (1, 2, 3, 0), (2, 3), None))
+                # dIn[iy,ix,ci] = sum dOut[iy-1+ky, ix-1+kx, co] * Wt[ci,co,ky,kx]
+                jobs.append((L.t["wd"], w, (0, 2, 3, 1), (), None))
+        be.pack_weights(jobs)
+
 
     # ------------------------------------------------------------------ plans
     def get_plan(self, B, H, W, training):
@@ -599,12 +597,9 @@ class PoseEngine:
         t["z"] = cur
         plan["zdims"] = dims
         if training:
+            # torch BatchNorm bookkeeping (momentum is fixed, the value is unused): one launch for the 14 counters
             counters = [self.Bufs[L.bn + ".num_batches_tracked"] for L in Ls.values() if L.bn is not None]
-
-            def bump():
-                for c in counters:      # torch BatchNorm bookkeeping (momentum is fixed, value unused)
-                    c.add_(1)
-            be.host("num_batches_tracked", bump)
+            be.add_i64(counters, 1)
 
     # ------------------------------------------------------------------ backward
     def record_backward(self, plan):

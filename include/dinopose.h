@@ -196,6 +196,14 @@ int dp_pose_loss(const float* heatmaps, const float* target_heatmaps, const floa
 int dp_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
              float beta2, float eps, float weight_decay, float grad_scale, long long* step_dev, void* stream);
 
+/* Re-pack trainable conv weights (fp32 [d0,d1,kh,kw] nn.Parameters, reference model/pose_heads.py) into the bf16 GEMM
+ * layouts, all layers in one launch.  jobs_dev: device table, 16 int64 per job =
+ * { src ptr, dst ptr, n0,n1,n2,n3 (extents in dst order), s0..s3 (signed src element strides: a negative stride +
+ *   src offset mirrors the filter taps), t0..t3 (dst element strides), src element offset, element count }. */
+int dp_pack_weights_bf16(const long long* jobs_dev, int njobs, long long max_total, void* stream);
+/* *ptrs[i] += inc for n device int64 scalars (BatchNorm num_batches_tracked, torch bookkeeping). */
+int dp_add_i64(const long long* ptrs_dev, int n, long long inc, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,6 +46,26 @@ class TorchEmulator:
     def mark(self, tag):
         self.prog.calls.append(("mark", tag))
 
+    def pack_weights(self, jobs):
+        def fn():
+            with torch.no_grad():
+                for dst, w, order, flips, dst_strides in jobs:
+                    src = w.detach()
+                    if flips:
+                        src = src.flip(*sorted(flips))
+                    src = src.permute(*order)
+                    if dst_strides is None:
+                        dst.view(-1)[:src.numel()].view(src.shape).copy_(src)
+                    else:
+                        torch.as_strided(dst, tuple(src.shape), tuple(dst_strides)).copy_(src)
+        self.prog.calls.append(fn)
+
+    def add_i64(self, tensors, inc=1):
+        def fn():
+            for t in tensors:
+                t.add_(inc)
+        self.prog.calls.append(fn)
+
     # ------------------------------------------------------------------ training step around the model
     def pose_loss(self, hm, thm, kps, z, tz, sums, state, out, scales, dhm, dz, *, B, K, HW, momentum=0.9, rate=0.1):
         def fn():

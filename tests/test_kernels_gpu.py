@@ -624,3 +624,27 @@ def test_adamw_vs_torch():
         opt.step()
         assert rel(p, ref.detach()) < 2e-6, s
     assert int(step.item()) == 4
+
+
+def test_pack_weights_and_counters():
+    """dp_pack_weights_bf16: permuted / tap-mirrored bf16 GEMM layouts of fp32 conv weights, all jobs in one launch."""
+    w1 = rnd(96, 64, 3, 3)
+    w2 = rnd(128, 32, 4, 4, seed=1)
+    w3 = rnd(24, 64, 1, 1, seed=2)
+    d1 = torch.zeros(96, 9 * 64, device=dev(), dtype=BF)
+    d2 = torch.zeros(64, 9 * 96, device=dev(), dtype=BF)
+    d3 = torch.zeros(16 * 32, 128, device=dev(), dtype=BF)
+    d4 = torch.zeros(64, 32, device=dev(), dtype=BF)
+    jobs = [(d1, w1, (0, 2, 3, 1), (), None), (d2, w1, (1, 2, 3, 0), (2, 3), None), (d3, w2, (2, 3, 1, 0), (), None),
+            (d4, w3, (1, 0, 2, 3), (), (32, 1, 1, 1))]
+    c = [torch.full((), 5, device=dev(), dtype=torch.int64) for _ in range(3)]
+
+    def fn(b):
+        b.pack_weights(jobs)
+        b.add_i64(c, 2)
+    run(fn)
+    assert torch.equal(d1, w1.permute(0, 2, 3, 1).reshape(96, -1).to(BF))
+    assert torch.equal(d2, w1.flip(2, 3).permute(1, 2, 3, 0).reshape(64, -1).to(BF))
+    assert torch.equal(d3, w2.permute(2, 3, 1, 0).reshape(-1, 128).to(BF))
+    assert torch.equal(d4[:, :24], w3.reshape(24, 64).t().to(BF)) and d4[:, 24:].abs().max().item() == 0
+    assert all(int(t.item()) == 7 for t in c)

@@ -11,6 +11,8 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+
+#include "launch.cuh"
 #include <stdlib.h>
 
 #include "ptx.cuh"
@@ -62,6 +64,7 @@ __device__ __forceinline__ void load_tile(uint32_t smem_base, const __nv_bfloat1
 
 __global__ void __launch_bounds__(128) attention_fwd_kernel(const __nv_bfloat16* __restrict__ qkv,
                                                             __nv_bfloat16* __restrict__ ctx, int T, int D, float scale_log2) {
+  pdl_grid_sync();
   __shared__ __align__(128) uint8_t smem[kBQ * 128 + 2 * kBK * 128 + 2 * kBK * 128];
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sK = sQ + kBQ * 128;
@@ -221,7 +224,7 @@ cudaError_t launch_attention_fwd(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, i
   }
   const int D = heads * kDH;
   dim3 grid((T + kBQ - 1) / kBQ, heads, B);
-  attention_fwd_kernel<<<grid, 128, 0, s>>>(qkv, ctx, T, D, scale * 1.4426950408889634f);
+  launch_k<attention_fwd_kernel>(grid, 128, 0, s, qkv, ctx, T, D, scale * 1.4426950408889634f);
   return cudaGetLastError();
 }
 

@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+
+#include "launch.cuh"
 #include <stdio.h>
 #include <stdlib.h>
 
@@ -79,6 +81,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_grid_sync();   // programmatic dependent launch: no global-memory access above this line
 
   if (warp == 0) {
     if (elect_one()) {
@@ -312,6 +315,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc257_kernel(const __gr
     mbar_init(p_ready, 4);
     mbar_init(o_full, 1);
     fence_barrier_init();
+    pdl_grid_sync();   // programmatic dependent launch: every thread passes this before its first global-memory access
     // loads are issued before the CTA-wide sync: their latency overlaps the TMEM allocation and the extra-row loads
     mbar_arrive_expect_tx(ld_full, 5 * kTileBytes);
     tma_load_2d(sQ, &p.tm, ld_full, h * kDh, row0 + qt * kTile);
@@ -319,10 +323,13 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc257_kernel(const __gr
     tma_load_2d(sK + kTileBytes, &p.tm, ld_full, p.D + h * kDh, row0 + kTile);
     tma_load_2d(sV, &p.tm, ld_full, 2 * p.D + h * kDh, row0);
     tma_load_2d(sV + kTileBytes, &p.tm, ld_full, 2 * p.D + h * kDh, row0 + kTile);
+  } else if (warp != 1) {
+    pdl_grid_sync();
   }
   if (warp == 1) {
     tmem_alloc(tmem_holder, 256);
     tmem_relinquish();
+    pdl_grid_sync();
     // the 257th token's k / v / q rows of this head (plain loads: 3 x 128 bytes)
     const __nv_bfloat16* xrow = p.qkv + (long long)(row0 + 256) * ld + h * kDh;
     for (int i = lane; i < 64; i += 32) {
@@ -622,7 +629,7 @@ cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, in
       if (e != cudaSuccess) return e;
       attr2 = true;
     }
-    attention_tc257_kernel<<<B * heads * 2, kThreads, kSmem257, s>>>(q);
+    launch_k<attention_tc257_kernel>(B * heads * 2, kThreads, kSmem257, s, q);
     if (trace_on) {   // debug only: synchronises
       long long h[16];
       cudaStreamSynchronize(s);
@@ -653,7 +660,7 @@ cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, in
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  attention_tc_kernel<<<B * heads, kThreads, kSmemBytes, s>>>(p);
+  launch_k<attention_tc_kernel>(B * heads, kThreads, kSmemBytes, s, p);
   return cudaGetLastError();
 }
 

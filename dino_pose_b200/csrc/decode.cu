@@ -9,6 +9,8 @@
 #include <math.h>
 #include <stdint.h>
 
+#include "launch.cuh"
+
 namespace dp {
 
 struct Best {
@@ -35,6 +37,7 @@ __device__ __forceinline__ void consider(Best& best, float v, int i) {
 __global__ void __launch_bounds__(128) decode_kernel(const float* __restrict__ hm, int maps, int H, int W, double tw,
                                                      double th, int* __restrict__ idx_out, double* __restrict__ xy_out,
                                                      float* __restrict__ conf_out) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int map = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (map >= maps) return;
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(128) decode_kernel(const float* __restrict__ h
 cudaError_t launch_decode(const float* hm, int maps, int H, int W, double tw, double th, int* idx, double* xy,
                           float* conf, cudaStream_t s) {
   const int wpb = 4;
-  decode_kernel<<<(maps + wpb - 1) / wpb, wpb * 32, 0, s>>>(hm, maps, H, W, tw, th, idx, xy, conf);
+  launch_k<decode_kernel>((maps + wpb - 1) / wpb, wpb * 32, 0, s, hm, maps, H, W, tw, th, idx, xy, conf);
   return cudaGetLastError();
 }
 

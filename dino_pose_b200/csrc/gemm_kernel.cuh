@@ -18,6 +18,7 @@
 // picks the smallest compiled superset, and a run-time-everything variant exists for each tile width.
 #pragma once
 #include "gemm_tc.cuh"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace dp {
@@ -409,6 +410,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // everything above touches only shared memory / TMEM / the parameter bank: it overlaps the tail of the previous
+  // launch (programmatic dependent launch); global memory is read or written only below this line
+  pdl_grid_sync();
 
   const int num_tiles = p.m_tiles * p.n_tiles;
   // tile order: n fastest (A tile shared by neighbouring CTAs through L2) unless column statistics are
@@ -536,7 +540,7 @@ cudaError_t launch_gemm_variant(const GemmParams& p, int grid, cudaStream_t s) {
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_fwd_kernel<BN, OUT, ACT, MAP, OPT><<<grid, kGemmThreads, GCfg<BN>::kSmemBytes, s>>>(p);
+  launch_k<gemm_fwd_kernel<BN, OUT, ACT, MAP, OPT>>(grid, kGemmThreads, GCfg<BN>::kSmemBytes, s, p);
   return cudaGetLastError();
 }
 

@@ -75,6 +75,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   cluster_sync_all();   // peer barriers initialised, peer TMEM allocated
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_grid_sync();   // see gemm_kernel.cuh: no global-memory access above this line
 
   const int pm_tiles = (p.m_tiles + 1) >> 1;           // 256-row pair tiles
   const int num_tiles = pm_tiles * p.n_tiles;
@@ -200,7 +201,7 @@ cudaError_t launch_gemm_pair_variant(const GemmParams& p, int grid, cudaStream_t
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_fwd_pair_kernel<BN, OUT, ACT, MAP, OPT><<<grid, kGemmThreads, PCfg<BN>::kSmemBytes, s>>>(p);
+  launch_k<gemm_fwd_pair_kernel<BN, OUT, ACT, MAP, OPT>>(grid, kGemmThreads, PCfg<BN>::kSmemBytes, s, p);
   return cudaGetLastError();
 }
 

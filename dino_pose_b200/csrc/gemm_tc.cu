@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const __grid_co
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  pdl_grid_sync();   // prologue above overlaps the previous launch; no global-memory access before this line
 
   // work item = (split, tap, m_blk, n_blk)
   const int num_items = p.splits * p.taps * p.m_tiles * p.n_tiles;
@@ -223,6 +224,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
                                                            int taps, int Mpad, int ld, int Mc, int Nc, long long so_m,
                                                            long long so_mo, long long so_n, long long so_no, long long so_t,
                                                            int m_inner, int n_inner) {
+  pdl_grid_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)Mc * Nc) return;
   const int m = int(idx / Nc), n = int(idx - (long long)m * Nc);
@@ -245,7 +247,7 @@ template <int BN> cudaError_t launch_wgrad_t(const WgradParams& p, int grid, cud
     if (e != cudaSuccess) return e;
     attr_set = true;
   }
-  gemm_wgrad_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmemBytes, s>>>(p);
+  launch_k<gemm_wgrad_kernel<BN>>(grid, kThreads, Cfg<BN>::kSmemBytes, s, p);
   return cudaGetLastError();
 }
 
@@ -296,7 +298,7 @@ cudaError_t launch_wgrad(const WgradParams& p, int block_n, int grid, cudaStream
   }
   if (e != cudaSuccess || p.ws == nullptr) return e;
   const long long total = (long long)p.Mc * p.Nc;
-  wgrad_reduce_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(p.ws, p.out, p.splits, p.taps, p.m_tiles * kBlockM, p.ws_ld,
+  launch_k<wgrad_reduce_kernel>(unsigned((total + 255) / 256), 256, 0, s, p.ws, p.out, p.splits, p.taps, p.m_tiles * kBlockM, p.ws_ld,
                                                                     p.Mc, p.Nc, p.so_m, p.so_mo, p.so_n, p.so_no, p.so_t,
                                                                     p.m_inner, p.n_inner);
   return cudaGetLastError();

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "launch.cuh"
+
 #include "ptx.cuh"
 
 namespace dp {
@@ -42,6 +44,7 @@ inline unsigned grid_for(long long n, int block, int max_blocks = 148 * 16) {
 // im2col: in NHWC [NB,IH,IW,C] -> col [NB*OH*OW, KH*KW*C], column = (ky*KW + kx)*C + c, zero padding.
 __global__ void __launch_bounds__(256) im2col_kernel(const uint4* __restrict__ in, uint4* __restrict__ col, int NB, int IH,
                                                      int IW, int C8, int OH, int OW, int KH, int KW, int stride, int pad) {
+  pdl_grid_sync();
   const long long total = (long long)NB * OH * OW * KH * KW * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = int(i % C8);
@@ -65,6 +68,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) col2im_kernel(const uint4* __restrict__ col, const float* __restrict__ bias,
                                                      OutT* __restrict__ big, int NB, int SH, int SW, int C8, int BH, int BW,
                                                      int KH, int KW, int stride, int pad) {
+  pdl_grid_sync();
   const long long total = (long long)NB * BH * BW * C8;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = int(i % C8);
@@ -104,6 +108,7 @@ template <typename OutT>
 __global__ void __launch_bounds__(256) dwconv3x3_kernel(const uint4* __restrict__ in, const float* __restrict__ w,
                                                         const float* __restrict__ bias, const uint4* __restrict__ add,
                                                         OutT* __restrict__ out, int NB, int H, int W, int C8, int flip) {
+  pdl_grid_sync();
   const int c = threadIdx.x % C8;
   const int ppb = blockDim.x / C8;          // pixels per block iteration
   const int pl = threadIdx.x / C8;
@@ -153,6 +158,7 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const uint4* __restrict_
 // block's pixel lanes and fp32 atomics (grid = a few hundred blocks, so <= a few hundred atomics per address).
 __global__ void __launch_bounds__(256) dwconv3x3_wgrad_kernel(const uint4* __restrict__ in, const uint4* __restrict__ dout,
                                                               float* __restrict__ dw, int NB, int H, int W, int C8) {
+  pdl_grid_sync();
   const int c = threadIdx.x % C8;
   const int ppb = blockDim.x / C8;
   const int pl = threadIdx.x / C8;
@@ -260,6 +266,7 @@ __device__ __forceinline__ void bn_block_reduce_atomic(float (&s)[8], float (&q)
 template <typename RawT>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const RawT* __restrict__ raw, double* __restrict__ sums,
                                                               long long P, int C8) {
+  pdl_grid_sync();
   const int C = C8 * 8;
   const int c8 = threadIdx.x % C8;
   const int rpb = kBnThreads / C8;
@@ -284,6 +291,7 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, const float* __res
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
                                    float* __restrict__ invstd_out, int C, double count, float eps, float momentum) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const double mean = sums[c] / count;
@@ -309,6 +317,7 @@ __global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float
                                     const float* __restrict__ rm, const float* __restrict__ rv,
                                     const float* __restrict__ conv_bias, float* __restrict__ scale,
                                     float* __restrict__ shift, int C, float eps) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float sc = gamma[c] * rsqrtf(rv[c] + eps);
@@ -325,6 +334,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const RawT* __rest
                                                               const __nv_bfloat16* __restrict__ add2,
                                                               __nv_bfloat16* __restrict__ out, long long P, int C8, int relu,
                                                               int mode) {
+  pdl_grid_sync();
   const int C = C8 * 8;
   const int c8 = threadIdx.x % C8;
   const int rpb = kBnThreads / C8;
@@ -393,6 +403,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
     const __nv_bfloat16* __restrict__ dout, const RawT* __restrict__ raw, const __nv_bfloat16* __restrict__ add1,
     const float* __restrict__ scale, const float* __restrict__ shift, double* __restrict__ sums, long long P, int C4,
     int relu, int mode) {
+  pdl_grid_sync();
   const int C = C4 * 4;
   const int c4 = threadIdx.x % C4;
   const int rpb = kBnThreads / C4;
@@ -461,6 +472,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_reduce_kernel(
 __global__ void bn_bwd_coeffs_kernel(double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ scale,
                                      const float* __restrict__ mean, const float* __restrict__ invstd, float* __restrict__ coef,
                                      float* __restrict__ dgamma, float* __restrict__ dbeta, int C, double invP, int eval_mode) {
+  pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   double S1 = 0.0, Q = 0.0;
@@ -499,6 +511,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
     __nv_bfloat16* __restrict__ draw, __nv_bfloat16* __restrict__ dres, long long P, int C4, int relu, int mode,
     int shuffle_oh, int shuffle_ow) {
+  pdl_grid_sync();
   const int C = C4 * 4;
   const int c4 = threadIdx.x % C4;
   const int rpb = kBnThreads / C4;
@@ -555,6 +568,7 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
 }
 
 __global__ void zero_f64_kernel(double* p, int n) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = 0.0;
 }
@@ -562,6 +576,7 @@ __global__ void zero_f64_kernel(double* p, int n) {
 // ------------------------------------------------------------------------------------------------
 // 2x2 mean (bilinear align_corners=False at exact scale 1/2, pose_heads.py:353-359) fp32 NCHW; and its adjoint.
 __global__ void avgpool2_kernel(const float* __restrict__ in, float* __restrict__ out, long long planes, int OH, int OW) {
+  pdl_grid_sync();
   const long long total = planes * OH * OW;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = int(i % OW);
@@ -579,6 +594,7 @@ __global__ void avgpool2_kernel(const float* __restrict__ in, float* __restrict_
 // up = 2 additionally applies the adjoint of avgpool2 (each fine pixel gets 0.25 * coarse gradient).
 __global__ void hm_grad_to_nhwc_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ out, int NB, int K, int Kp,
                                        int OH, int OW, int up) {
+  pdl_grid_sync();
   const long long total = (long long)NB * OH * OW * Kp;
   const int GH = OH / up, GW = OW / up;
   const float w = up == 2 ? 0.25f : 1.0f;
@@ -596,6 +612,7 @@ __global__ void hm_grad_to_nhwc_kernel(const float* __restrict__ g, __nv_bfloat1
 
 // mean over the N patch tokens: feat bf16 [B, N, D] -> fp32 [B, D]   (pose_heads.py:397)
 __global__ void mean_tokens_kernel(const __nv_bfloat16* __restrict__ feat, float* __restrict__ out, int N, int D) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const int d = blockIdx.x * blockDim.x + threadIdx.x;
   if (d >= D) return;
@@ -606,6 +623,7 @@ __global__ void mean_tokens_kernel(const __nv_bfloat16* __restrict__ feat, float
 // adjoint: dfeat[b, n, :] += dmean[b, :] / N   (bf16 in place)
 __global__ void mean_tokens_bwd_kernel(__nv_bfloat16* __restrict__ dfeat, const float* __restrict__ dmean, int N, int D,
                                        long long total) {
+  pdl_grid_sync();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int d = int(i % D);
     const long long b = i / ((long long)N * D);
@@ -631,6 +649,7 @@ __global__ void __launch_bounds__(128) sgemm_small_kernel(const float* __restric
                                                           const float* __restrict__ mask_ref, long long ld_ref,
                                                           float p_drop, const unsigned long long* __restrict__ seed_ptr,
                                                           int accumulate, int k_per_split) {
+  pdl_grid_sync();
   // 32x32 output tile, 32-deep k-steps, 128 threads x (2 rows x 4 cols); loads are coalesced along whichever
   // operand dimension has unit stride.  gridDim.z > 1: split-K -- each z-slice adds its partial sums to C with
   // fp32 atomics (C pre-zeroed or accumulated onto) and the epilogue runs in sgemm_small_finish_kernel.
@@ -707,6 +726,7 @@ __global__ void __launch_bounds__(128) sgemm_small_kernel(const float* __restric
 __global__ void sgemm_small_finish_kernel(float* __restrict__ Cc, long long ldc, int M, int N, const float* __restrict__ bias,
                                           int relu, const float* __restrict__ mask_ref, long long ld_ref, float p_drop,
                                           const unsigned long long* __restrict__ seed_ptr) {
+  pdl_grid_sync();
   const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
   const uint32_t thresh = p_drop > 0.f ? uint32_t(fminf(p_drop, 0.999999f) * 4294967296.0f) : 0u;
   const float keep = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
@@ -724,6 +744,7 @@ __global__ void sgemm_small_finish_kernel(float* __restrict__ Cc, long long ldc,
 // out = (ref > 0) ? d * keep_scale : 0      (gradient through ReLU [+ inverted dropout] given the saved output)
 __global__ void relu_mask_kernel(const float* __restrict__ d, const float* __restrict__ ref, float* __restrict__ out,
                                  long long n, float keep_scale) {
+  pdl_grid_sync();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = ref[i] > 0.f ? d[i] * keep_scale : 0.f;
 }
@@ -732,6 +753,7 @@ __global__ void relu_mask_kernel(const float* __restrict__ d, const float* __res
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, long long P, int C, long long ld,
                               int rows_per_block) {
+  pdl_grid_sync();
   const int c = blockIdx.y * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const long long p0 = (long long)blockIdx.x * rows_per_block;
@@ -750,7 +772,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, float* __restrict__ out, 
 cudaError_t launch_im2col(const void* in, void* col, int NB, int IH, int IW, int C, int OH, int OW, int KH, int KW,
                           int stride, int pad, cudaStream_t s) {
   const long long total = (long long)NB * OH * OW * KH * KW * (C / 8);
-  im2col_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(col), NB,
+  launch_k<im2col_kernel>(grid_for(total, 256), 256, 0, s, reinterpret_cast<const uint4*>(in), reinterpret_cast<uint4*>(col), NB,
                                                      IH, IW, C / 8, OH, OW, KH, KW, stride, pad);
   return cudaGetLastError();
 }
@@ -758,11 +780,11 @@ cudaError_t launch_col2im(const void* col, const float* bias, void* big, int big
                           int BW, int KH, int KW, int stride, int pad, cudaStream_t s) {
   const long long total = (long long)NB * BH * BW * (C / 8);
   if (big_f32)
-    col2im_kernel<float><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(col), bias,
+    launch_k<col2im_kernel<float>>(grid_for(total, 256), 256, 0, s, reinterpret_cast<const uint4*>(col), bias,
                                                               reinterpret_cast<float*>(big), NB, SH, SW, C / 8, BH, BW, KH,
                                                               KW, stride, pad);
   else
-    col2im_kernel<__nv_bfloat16><<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<const uint4*>(col), bias,
+    launch_k<col2im_kernel<__nv_bfloat16>>(grid_for(total, 256), 256, 0, s, reinterpret_cast<const uint4*>(col), bias,
                                                                       reinterpret_cast<__nv_bfloat16*>(big), NB, SH, SW,
                                                                       C / 8, BH, BW, KH, KW, stride, pad);
   return cudaGetLastError();
@@ -776,11 +798,11 @@ cudaError_t launch_dwconv3x3(const void* in, const float* w, const float* bias, 
   long long g = (P + ppb - 1) / ppb;
   if (g > 148 * 8) g = 148 * 8;
   if (out_f32)
-    dwconv3x3_kernel<float><<<unsigned(g), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), w, bias,
+    launch_k<dwconv3x3_kernel<float>>(unsigned(g), 256, 0, s, reinterpret_cast<const uint4*>(in), w, bias,
                                                         reinterpret_cast<const uint4*>(add), reinterpret_cast<float*>(out),
                                                         NB, H, W, C8, flip);
   else
-    dwconv3x3_kernel<__nv_bfloat16><<<unsigned(g), 256, 0, s>>>(reinterpret_cast<const uint4*>(in), w, bias,
+    launch_k<dwconv3x3_kernel<__nv_bfloat16>>(unsigned(g), 256, 0, s, reinterpret_cast<const uint4*>(in), w, bias,
                                                                 reinterpret_cast<const uint4*>(add),
                                                                 reinterpret_cast<__nv_bfloat16*>(out), NB, H, W, C8, flip);
   return cudaGetLastError();
@@ -800,7 +822,7 @@ cudaError_t launch_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, 
     if (e != cudaSuccess) return e;
     attr = true;
   }
-  dwconv3x3_wgrad_kernel<<<unsigned(g), 256, smem, s>>>(reinterpret_cast<const uint4*>(in), reinterpret_cast<const uint4*>(dout),
+  launch_k<dwconv3x3_wgrad_kernel>(unsigned(g), 256, smem, s, reinterpret_cast<const uint4*>(in), reinterpret_cast<const uint4*>(dout),
                                                         dw, NB, H, W, C8);
   return cudaGetLastError();
 }
@@ -824,21 +846,21 @@ static bool bn_c_ok(int C) { return C % 8 == 0 && kBnThreads % (C / 8) == 0 && C
 cudaError_t launch_bn_stats(const void* raw, int raw_f32, double* sums, long long P, int C, cudaStream_t s) {
   if (!bn_c_ok(C)) return cudaErrorInvalidValue;
   if (raw_f32)
-    bn_stats_kernel<float><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(reinterpret_cast<const float*>(raw), sums, P, C / 8);
+    launch_k<bn_stats_kernel<float>>(bn_grid(P, C / 8), kBnThreads, 0, s, reinterpret_cast<const float*>(raw), sums, P, C / 8);
   else
-    bn_stats_kernel<__nv_bfloat16><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(raw), sums, P, C / 8);
+    launch_k<bn_stats_kernel<__nv_bfloat16>>(bn_grid(P, C / 8), kBnThreads, 0, s, reinterpret_cast<const __nv_bfloat16*>(raw), sums, P, C / 8);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_finalize(double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,
                                float* shift, float* mean, float* invstd, int C, double count, float eps, float momentum,
                                cudaStream_t s) {
-  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, gamma, beta, rm, rv, scale, shift, mean, invstd, C, count, eps,
+  launch_k<bn_finalize_kernel>((C + 127) / 128, 128, 0, s, sums, gamma, beta, rm, rv, scale, shift, mean, invstd, C, count, eps,
                                                      momentum);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
                                 const float* conv_bias, float* scale, float* shift, int C, float eps, cudaStream_t s) {
-  bn_fold_eval_kernel<<<(C + 127) / 128, 128, 0, s>>>(gamma, beta, rm, rv, conv_bias, scale, shift, C, eps);
+  launch_k<bn_fold_eval_kernel>((C + 127) / 128, 128, 0, s, gamma, beta, rm, rv, conv_bias, scale, shift, C, eps);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_apply(const void* raw, int raw_f32, const float* scale, const float* shift, const void* add1,
@@ -848,9 +870,9 @@ cudaError_t launch_bn_apply(const void* raw, int raw_f32, const float* scale, co
   auto a2 = reinterpret_cast<const __nv_bfloat16*>(add2);
   auto o = reinterpret_cast<__nv_bfloat16*>(out);
   if (raw_f32)
-    bn_apply_kernel<float><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(reinterpret_cast<const float*>(raw), scale, shift, a1, a2, o, P, C / 8, relu, mode);
+    launch_k<bn_apply_kernel<float>>(bn_grid(P, C / 8), kBnThreads, 0, s, reinterpret_cast<const float*>(raw), scale, shift, a1, a2, o, P, C / 8, relu, mode);
   else
-    bn_apply_kernel<__nv_bfloat16><<<bn_grid(P, C / 8), kBnThreads, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(raw), scale, shift, a1, a2, o, P, C / 8, relu, mode);
+    launch_k<bn_apply_kernel<__nv_bfloat16>>(bn_grid(P, C / 8), kBnThreads, 0, s, reinterpret_cast<const __nv_bfloat16*>(raw), scale, shift, a1, a2, o, P, C / 8, relu, mode);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_bwd_reduce(const void* dout, const void* raw, int raw_f32, const void* add1, const float* scale,
@@ -860,9 +882,9 @@ cudaError_t launch_bn_bwd_reduce(const void* dout, const void* raw, int raw_f32,
   auto d = reinterpret_cast<const __nv_bfloat16*>(dout);
   auto a1 = reinterpret_cast<const __nv_bfloat16*>(add1);
   if (raw_f32)
-    bn_bwd_reduce_kernel<float><<<bn_grid4(P, C / 4), kBnThreads, 0, s>>>(d, reinterpret_cast<const float*>(raw), a1, scale, shift, sums, P, C / 4, relu, mode);
+    launch_k<bn_bwd_reduce_kernel<float>>(bn_grid4(P, C / 4), kBnThreads, 0, s, d, reinterpret_cast<const float*>(raw), a1, scale, shift, sums, P, C / 4, relu, mode);
   else
-    bn_bwd_reduce_kernel<__nv_bfloat16><<<bn_grid4(P, C / 4), kBnThreads, 0, s>>>(d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, sums, P, C / 4, relu, mode);
+    launch_k<bn_bwd_reduce_kernel<__nv_bfloat16>>(bn_grid4(P, C / 4), kBnThreads, 0, s, d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, sums, P, C / 4, relu, mode);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_bwd_apply(const void* dout, const void* raw, int raw_f32, const void* add1, const float* gamma,
@@ -876,36 +898,36 @@ cudaError_t launch_bn_bwd_apply(const void* dout, const void* raw, int raw_f32, 
   auto ds = reinterpret_cast<__nv_bfloat16*>(dres);
   // coefficient scratch: the (DP_BN_BWD_REPLICAS + 1)-th 2*C block of `sums` (16*C bytes >= 3*C floats)
   float* coef = reinterpret_cast<float*>(sums + (long long)kBnBwdReplicas * 2 * C);
-  bn_bwd_coeffs_kernel<<<(C + 127) / 128, 128, 0, s>>>(sums, gamma, scale, mean, invstd, coef, dgamma, dbeta, C, 1.0 / double(P),
+  launch_k<bn_bwd_coeffs_kernel>((C + 127) / 128, 128, 0, s, sums, gamma, scale, mean, invstd, coef, dgamma, dbeta, C, 1.0 / double(P),
                                                       eval_mode);
   if (raw_f32)
-    bn_bwd_apply_kernel<float><<<bn_grid4(P, C / 4), kBnThreads, 0, s>>>(d, reinterpret_cast<const float*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow);
+    launch_k<bn_bwd_apply_kernel<float>>(bn_grid4(P, C / 4), kBnThreads, 0, s, d, reinterpret_cast<const float*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow);
   else
-    bn_bwd_apply_kernel<__nv_bfloat16><<<bn_grid4(P, C / 4), kBnThreads, 0, s>>>(d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow);
+    launch_k<bn_bwd_apply_kernel<__nv_bfloat16>>(bn_grid4(P, C / 4), kBnThreads, 0, s, d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow);
   return cudaGetLastError();
 }
 cudaError_t launch_zero_f64(double* p, int n, cudaStream_t s) {
-  zero_f64_kernel<<<(n + 255) / 256, 256, 0, s>>>(p, n);
+  launch_k<zero_f64_kernel>((n + 255) / 256, 256, 0, s, p, n);
   return cudaGetLastError();
 }
 cudaError_t launch_avgpool2(const float* in, float* out, long long planes, int OH, int OW, cudaStream_t s) {
-  avgpool2_kernel<<<grid_for(planes * OH * OW, 256), 256, 0, s>>>(in, out, planes, OH, OW);
+  launch_k<avgpool2_kernel>(grid_for(planes * OH * OW, 256), 256, 0, s, in, out, planes, OH, OW);
   return cudaGetLastError();
 }
 cudaError_t launch_hm_grad_to_nhwc(const float* g, void* out, int NB, int K, int Kp, int OH, int OW, int up,
                                    cudaStream_t s) {
-  hm_grad_to_nhwc_kernel<<<grid_for((long long)NB * OH * OW * Kp, 256), 256, 0, s>>>(
+  launch_k<hm_grad_to_nhwc_kernel>(grid_for((long long)NB * OH * OW * Kp, 256), 256, 0, s, 
       g, reinterpret_cast<__nv_bfloat16*>(out), NB, K, Kp, OH, OW, up);
   return cudaGetLastError();
 }
 cudaError_t launch_mean_tokens(const void* feat, float* out, int B, int N, int D, cudaStream_t s) {
   dim3 grid((D + 127) / 128, B);
-  mean_tokens_kernel<<<grid, 128, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(feat), out, N, D);
+  launch_k<mean_tokens_kernel>(grid, 128, 0, s, reinterpret_cast<const __nv_bfloat16*>(feat), out, N, D);
   return cudaGetLastError();
 }
 cudaError_t launch_mean_tokens_bwd(void* dfeat, const float* dmean, int B, int N, int D, cudaStream_t s) {
   const long long total = (long long)B * N * D;
-  mean_tokens_bwd_kernel<<<grid_for(total, 256), 256, 0, s>>>(reinterpret_cast<__nv_bfloat16*>(dfeat), dmean, N, D, total);
+  launch_k<mean_tokens_bwd_kernel>(grid_for(total, 256), 256, 0, s, reinterpret_cast<__nv_bfloat16*>(dfeat), dmean, N, D, total);
   return cudaGetLastError();
 }
 cudaError_t launch_sgemm_small(const float* A, long long sa_m, long long sa_k, const float* B, long long sb_k,
@@ -926,21 +948,21 @@ cudaError_t launch_sgemm_small(const float* A, long long sa_m, long long sa_k, c
       cudaError_t e = cudaMemset2DAsync(C, size_t(ldc) * sizeof(float), 0, size_t(N) * sizeof(float), size_t(M), s);
       if (e != cudaSuccess) return e;
     }
-    sgemm_small_kernel<<<grid, 128, 0, s>>>(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, nullptr, 0, nullptr, 0, 0.f, nullptr,
+    launch_k<sgemm_small_kernel>(grid, 128, 0, s, A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, nullptr, 0, nullptr, 0, 0.f, nullptr,
                                             1, k_per_split);
     if (bias != nullptr || relu || mask_ref != nullptr || p_drop > 0.f) {
       const long long total = (long long)M * N;
-      sgemm_small_finish_kernel<<<unsigned((total + 255) / 256), 256, 0, s>>>(C, ldc, M, N, bias, relu, mask_ref, ld_ref, p_drop,
+      launch_k<sgemm_small_finish_kernel>(unsigned((total + 255) / 256), 256, 0, s, C, ldc, M, N, bias, relu, mask_ref, ld_ref, p_drop,
                                                                              seed);
     }
     return cudaGetLastError();
   }
-  sgemm_small_kernel<<<grid, 128, 0, s>>>(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, bias, relu, mask_ref, ld_ref,
+  launch_k<sgemm_small_kernel>(grid, 128, 0, s, A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, bias, relu, mask_ref, ld_ref,
                                           p_drop, seed, accumulate, K);
   return cudaGetLastError();
 }
 cudaError_t launch_relu_mask(const float* d, const float* ref, float* out, long long n, float keep_scale, cudaStream_t s) {
-  relu_mask_kernel<<<unsigned((n + 255) / 256), 256, 0, s>>>(d, ref, out, n, keep_scale);
+  launch_k<relu_mask_kernel>(unsigned((n + 255) / 256), 256, 0, s, d, ref, out, n, keep_scale);
   return cudaGetLastError();
 }
 cudaError_t launch_colsum(const void* x, int is_bf16, float* out, long long P, int C, long long ld, cudaStream_t s) {
@@ -949,9 +971,9 @@ cudaError_t launch_colsum(const void* x, int is_bf16, float* out, long long P, i
   const int block = C >= 128 ? 128 : 32;
   dim3 grid(unsigned((P + rpb - 1) / rpb), unsigned((C + block - 1) / block));
   if (is_bf16)
-    colsum_kernel<__nv_bfloat16><<<grid, block, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(x), out, P, C, ld, rpb);
+    launch_k<colsum_kernel<__nv_bfloat16>>(grid, block, 0, s, reinterpret_cast<const __nv_bfloat16*>(x), out, P, C, ld, rpb);
   else
-    colsum_kernel<float><<<grid, block, 0, s>>>(reinterpret_cast<const float*>(x), out, P, C, ld, rpb);
+    launch_k<colsum_kernel<float>>(grid, block, 0, s, reinterpret_cast<const float*>(x), out, P, C, ld, rpb);
   return cudaGetLastError();
 }
 

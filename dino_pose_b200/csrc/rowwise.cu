@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "launch.cuh"
+
 #include <type_traits>
 
 #include "ptx.cuh"
@@ -25,6 +27,7 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
                                                             const float* __restrict__ beta, __nv_bfloat16* __restrict__ y,
                                                             float* __restrict__ y32, long long rows, int T, int drop_cls,
                                                             float eps) {
+  pdl_grid_sync();
   constexpr int D = V * 128;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -82,6 +85,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
                                                             const float* __restrict__ ls,
                                                             __nv_bfloat16* __restrict__ dx_scaled, long long rows, int T,
                                                             int drop_cls, float eps) {
+  pdl_grid_sync();
   constexpr int D = V * 128;
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -185,7 +189,7 @@ cudaError_t launch_layernorm_fwd(const float* x, const float* gamma, const float
   const int wpb = 8;
   const unsigned grid = unsigned((rows + wpb - 1) / wpb);
   return dispatch_v(D, [&](auto v) {
-    layernorm_fwd_kernel<decltype(v)::value><<<grid, wpb * 32, 0, s>>>(x, gamma, beta, y, y32, rows, T, drop_cls, eps);
+    launch_k<layernorm_fwd_kernel<decltype(v)::value>>(grid, wpb * 32, 0, s, x, gamma, beta, y, y32, rows, T, drop_cls, eps);
   });
 }
 
@@ -197,10 +201,10 @@ cudaError_t launch_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
   return dispatch_v(D, [&](auto v) {
     constexpr int V = decltype(v)::value;
     if (dy_is_bf16)
-      layernorm_bwd_kernel<V, __nv_bfloat16><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const __nv_bfloat16*>(dy), x,
+      launch_k<layernorm_bwd_kernel<V, __nv_bfloat16>>(grid, wpb * 32, 0, s, reinterpret_cast<const __nv_bfloat16*>(dy), x,
                                                                       gamma, add_in, dx, ls, dx_scaled, rows, T, drop_cls, eps);
     else
-      layernorm_bwd_kernel<V, float><<<grid, wpb * 32, 0, s>>>(reinterpret_cast<const float*>(dy), x, gamma, add_in, dx,
+      launch_k<layernorm_bwd_kernel<V, float>>(grid, wpb * 32, 0, s, reinterpret_cast<const float*>(dy), x, gamma, add_in, dx,
                                                              ls, dx_scaled, rows, T, drop_cls, eps);
   });
 }
@@ -211,6 +215,7 @@ cudaError_t launch_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
 // up to Kp (a multiple of 64, so the GEMM k-loop needs no tail).
 __global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ out,
                                                            int B, int H, int W, int gh, int gw, int Kp) {
+  pdl_grid_sync();
   // one block per (b, patch row); threads sweep (c, ky, x-pair) with x fastest: 8-byte coalesced reads, and an
   // even x never straddles a 14-wide patch, so each pair is one 4-byte bf16x2 store
   const int b = blockIdx.x / gh, py = blockIdx.x % gh;
@@ -237,19 +242,20 @@ __global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restri
 
 cudaError_t launch_patch_im2col(const float* px, __nv_bfloat16* out, int B, int H, int W, int Kp, cudaStream_t s) {
   const int gh = H / 14, gw = W / 14;
-  patch_im2col_kernel<<<B * gh, 256, 0, s>>>(px, out, B, H, W, gh, gw, Kp);
+  launch_k<patch_im2col_kernel>(B * gh, 256, 0, s, px, out, B, H, W, gh, gw, Kp);
   return cudaGetLastError();
 }
 
 // x[b*T + 0, :] = cls_row[:]   (cls token + its position embedding, HF:108-112)
 __global__ void fill_cls_kernel(float* __restrict__ x, const float* __restrict__ cls_row, int B, int T, int D) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * D) return;
   const int b = i / D, d = i % D;
   x[(long long)b * T * D + d] = __ldg(cls_row + d);
 }
 cudaError_t launch_fill_cls(float* x, const float* cls_row, int B, int T, int D, cudaStream_t s) {
-  fill_cls_kernel<<<(B * D + 255) / 256, 256, 0, s>>>(x, cls_row, B, T, D);
+  launch_k<fill_cls_kernel>((B * D + 255) / 256, 256, 0, s, x, cls_row, B, T, D);
   return cudaGetLastError();
 }
 
@@ -278,6 +284,7 @@ __global__ void __launch_bounds__(256) lora_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ x_in, float* __restrict__ x_out,
                                                        float* __restrict__ u_save, long long rows, int D, float scaling,
                                                        float p_drop, const unsigned long long* __restrict__ seed_ptr) {
+  pdl_grid_sync();
   const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
   extern __shared__ float sm[];
   float* sA = sm;           // [D][R]
@@ -332,6 +339,7 @@ __global__ void __launch_bounds__(256) lora_bwd_gu_kernel(const float* __restric
                                                           const float* __restrict__ lambda1, float* __restrict__ gu_out,
                                                           long long rows, int D, float scaling, float p_drop,
                                                           const unsigned long long* __restrict__ seed_ptr) {
+  pdl_grid_sync();
   const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
   extern __shared__ float sm[];
   float* sB = sm;  // [R][D]
@@ -370,6 +378,7 @@ __global__ void __launch_bounds__(256) lora_bwd_acc_kernel(const float* __restri
                                                            float* __restrict__ dB, long long rows, int D, float scaling,
                                                            float p_drop, const unsigned long long* __restrict__ seed_ptr,
                                                            int rows_per_block) {
+  pdl_grid_sync();
   const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
   const int d = blockIdx.y * blockDim.x + threadIdx.x;
   if (d >= D) return;
@@ -419,13 +428,13 @@ cudaError_t launch_lora_fwd(const float* y, const float* A, const float* Bm, con
   const int grid = sms * 6;
   if (R == 8) {
     cudaFuncSetAttribute(lora_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    lora_fwd_kernel<8><<<grid, 256, smem, s>>>(y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed);
+    launch_k<lora_fwd_kernel<8>>(grid, 256, smem, s, y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed);
   } else if (R == 4) {
     cudaFuncSetAttribute(lora_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    lora_fwd_kernel<4><<<grid, 256, smem, s>>>(y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed);
+    launch_k<lora_fwd_kernel<4>>(grid, 256, smem, s, y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed);
   } else if (R == 16) {
     cudaFuncSetAttribute(lora_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    lora_fwd_kernel<16><<<grid, 256, smem, s>>>(y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed);
+    launch_k<lora_fwd_kernel<16>>(grid, 256, smem, s, y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed);
   } else {
     return cudaErrorInvalidValue;
   }
@@ -438,7 +447,7 @@ static cudaError_t lora_bwd_t(const float* g, const float* y, const float* u_sav
                               const unsigned long long* seed, int sms, cudaStream_t s) {
   const size_t smem = size_t(D) * R * sizeof(float);
   cudaFuncSetAttribute(lora_bwd_gu_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  lora_bwd_gu_kernel<R><<<sms * 6, 256, smem, s>>>(g, Bm, lambda1, gu_ws, rows, D, scaling, p_drop, seed);
+  launch_k<lora_bwd_gu_kernel<R>>(sms * 6, 256, smem, s, g, Bm, lambda1, gu_ws, rows, D, scaling, p_drop, seed);
   const int bx = 128;
   const int gy = (D + bx - 1) / bx;
   int gx = (sms * 4) / gy;   // more blocks = more same-address atomics on the 2*D*R outputs (measured slower)
@@ -446,7 +455,7 @@ static cudaError_t lora_bwd_t(const float* g, const float* y, const float* u_sav
   int rpb = int((rows + gx - 1) / gx);
   if (rpb < 16) rpb = 16;
   gx = int((rows + rpb - 1) / rpb);
-  lora_bwd_acc_kernel<R><<<dim3(gx, gy), bx, 0, s>>>(g, y, u_saved, gu_ws, lambda1, dA, dB, rows, D, scaling, p_drop, seed, rpb);
+  launch_k<lora_bwd_acc_kernel<R>>(dim3(gx, gy), bx, 0, s, g, y, u_saved, gu_ws, lambda1, dA, dB, rows, D, scaling, p_drop, seed, rpb);
   return cudaGetLastError();
 }
 

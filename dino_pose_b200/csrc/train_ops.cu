@@ -11,6 +11,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "launch.cuh"
+
 namespace dp {
 namespace {
 
@@ -19,6 +21,7 @@ __global__ void __launch_bounds__(256) pose_loss_reduce_kernel(const float4* __r
                                                                const float* __restrict__ kps, int kp_stride,
                                                                const float* __restrict__ z, const float* __restrict__ tz,
                                                                double* __restrict__ sums, long long n4, int map4, int BK) {
+  pdl_grid_sync();
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int bk = int(i / map4);
@@ -60,6 +63,7 @@ __global__ void __launch_bounds__(256) pose_loss_reduce_kernel(const float4* __r
 __global__ void pose_loss_finalize_kernel(double* __restrict__ sums, float* __restrict__ state, float* __restrict__ out,
                                           float* __restrict__ scales, double numel_hm, double numel_z, float momentum,
                                           float rate) {
+  pdl_grid_sync();
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   const float kp = float(sums[0] / numel_hm), zl = float(sums[1] / numel_z);
   sums[0] = 0.0;
@@ -88,6 +92,7 @@ __global__ void __launch_bounds__(256) pose_loss_grad_kernel(const float4* __res
                                                              const float* __restrict__ z, const float* __restrict__ tz,
                                                              const float* __restrict__ scales, float4* __restrict__ dhm,
                                                              float* __restrict__ dz, long long n4, int map4, int BK) {
+  pdl_grid_sync();
   const float s0 = scales[0], s1 = scales[1];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const int bk = int(i / map4);
@@ -116,6 +121,7 @@ __global__ void __launch_bounds__(256) pose_loss_grad_kernel(const float4* __res
 __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                                                     float4* __restrict__ v, long long n4, float lr, float b1, float b2,
                                                     float eps, float wd, float grad_scale, const long long* __restrict__ step_dev) {
+  pdl_grid_sync();
   const float t = float(*step_dev + 1);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
@@ -134,7 +140,10 @@ __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, cons
     p[i] = pp; m[i] = mm; v[i] = vv;
   }
 }
-__global__ void bump_step_kernel(long long* step_dev) { *step_dev += 1; }
+__global__ void bump_step_kernel(long long* step_dev) {
+  pdl_grid_sync();
+  *step_dev += 1;
+}
 
 }  // namespace
 
@@ -146,10 +155,10 @@ cudaError_t launch_pose_loss(const float* hm, const float* thm, const float* kps
   int grid = int((n4 + 255) / 256);
   if (grid > sms * 8) grid = sms * 8;
   if (grid < 1) grid = 1;
-  pose_loss_reduce_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(hm), reinterpret_cast<const float4*>(thm), kps,
+  launch_k<pose_loss_reduce_kernel>(grid, 256, 0, s, reinterpret_cast<const float4*>(hm), reinterpret_cast<const float4*>(thm), kps,
                                                kp_stride, z, tz, sums, n4, map4, BK);
-  pose_loss_finalize_kernel<<<1, 32, 0, s>>>(sums, state, out, scales, double(B) * K * HW, double(BK), momentum, rate);
-  pose_loss_grad_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float4*>(hm), reinterpret_cast<const float4*>(thm), kps,
+  launch_k<pose_loss_finalize_kernel>(1, 32, 0, s, sums, state, out, scales, double(B) * K * HW, double(BK), momentum, rate);
+  launch_k<pose_loss_grad_kernel>(grid, 256, 0, s, reinterpret_cast<const float4*>(hm), reinterpret_cast<const float4*>(thm), kps,
                                              kp_stride, z, tz, scales, reinterpret_cast<float4*>(dhm), dz, n4, map4, BK);
   return cudaGetLastError();
 }
@@ -160,9 +169,9 @@ cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long
   int grid = int((n4 + 255) / 256);
   if (grid > sms * 8) grid = sms * 8;
   if (grid < 1) grid = 1;
-  adamw_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+  launch_k<adamw_kernel>(grid, 256, 0, s, reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
                                     reinterpret_cast<float4*>(v), n4, lr, b1, b2, eps, wd, grad_scale, step_dev);
-  bump_step_kernel<<<1, 1, 0, s>>>(step_dev);
+  launch_k<bump_step_kernel>(1, 1, 0, s, step_dev);
   return cudaGetLastError();
 }
 
@@ -178,6 +187,7 @@ cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long
 namespace dp {
 namespace {
 __global__ void __launch_bounds__(256) pack_weights_kernel(const long long* __restrict__ jobs) {
+  pdl_grid_sync();
   const long long* j = jobs + (long long)blockIdx.y * 16;
   const float* src = reinterpret_cast<const float*>(j[0]);
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(j[1]);
@@ -196,6 +206,7 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const long long* __re
   }
 }
 __global__ void add_i64_kernel(const long long* __restrict__ ptrs, int n, long long inc) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) *reinterpret_cast<long long*>(ptrs[i]) += inc;
 }
@@ -206,11 +217,11 @@ cudaError_t launch_pack_weights(const long long* jobs_dev, int njobs, long long 
   if (gx > 64) gx = 64;     // jobs run side by side: njobs x 64 blocks fill the GPU
   if (gx < 1) gx = 1;
   (void)sms;
-  pack_weights_kernel<<<dim3(unsigned(gx), unsigned(njobs)), 256, 0, s>>>(jobs_dev);
+  launch_k<pack_weights_kernel>(dim3(unsigned(gx), unsigned(njobs)), 256, 0, s, jobs_dev);
   return cudaGetLastError();
 }
 cudaError_t launch_add_i64(const long long* ptrs_dev, int n, long long inc, cudaStream_t s) {
-  add_i64_kernel<<<(n + 127) / 128, 128, 0, s>>>(ptrs_dev, n, inc);
+  launch_k<add_i64_kernel>((n + 127) / 128, 128, 0, s, ptrs_dev, n, inc);
   return cudaGetLastError();
 }
 }  // namespace dp

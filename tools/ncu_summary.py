@@ -25,8 +25,15 @@ def short(name):
     return re.sub(r"\(.*", "", name)[:80]
 
 
+def _raw(path):
+    """raw-page CSV of a report; `path` may already be that CSV (exported on the GPU box to stay under the size limit)"""
+    if path.endswith(".csv"):
+        return open(path).read()
+    return subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+
+
 def full(path):
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = _raw(path)
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -58,7 +65,7 @@ def launch(path):
 def traffic(path):
     """JSON for bench.py's roofline.traffic: DRAM bytes (read + write) per launch, averaged per kernel family."""
     import json
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    raw = _raw(path)
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     idx = {h: i for i, h in enumerate(hdr)}
@@ -83,5 +90,53 @@ def traffic(path):
     print(json.dumps(out, indent=1))
 
 
+def _family(name):
+    name = short(name)
+    if "gemm_fwd" in name:
+        return "gemm_kmajor_tcgen05"
+    if "gemm_wgrad" in name:
+        return "gemm_wgrad_tcgen05"
+    base = name.split("<")[0] if not name.startswith("void ") else name
+    base = re.sub(r"^.*::", "", name.split("(")[0].split("<")[0])
+    return re.sub(r"_kernel$", "", base)
+
+
+def steptraffic(path, last=261):
+    """Long-format CSV (`ncu --metrics ... --csv`, one row per launch and metric) of the whole program: keeps the LAST
+    `last` launches (one steady-state fine-tuning step), prints a per-family markdown table on stderr-free stdout and
+    writes the JSON bench.py reads (profiles/traffic.json) when a second argument names it."""
+    import json
+    txt = open(path).read()
+    rows = list(csv.reader(io.StringIO(txt[txt.index('"ID"'):])))
+    idx = {h: i for i, h in enumerate(rows[0])}
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "%": 1.0}
+    launches = collections.OrderedDict()
+    for r in rows[1:]:
+        d = launches.setdefault(r[idx["ID"]], {"name": r[idx["Kernel Name"]]})
+        d[r[idx["Metric Name"]]] = float(r[idx["Metric Value"]].replace(",", "")) * mult.get(r[idx["Metric Unit"]], 1.0)
+    step = list(launches.values())[-int(last):]
+    fam = collections.OrderedDict()
+    for d in step:
+        f = fam.setdefault(_family(d["name"]), {"launches": 0, "dram_bytes": 0.0, "us": 0.0, "tens": 0.0})
+        f["launches"] += 1
+        f["dram_bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
+        f["us"] += d.get("gpu__time_duration.sum", 0.0)
+        f["tens"] += d.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", 0.0) * d.get("gpu__time_duration.sum", 0.0)
+    tot = sum(f["us"] for f in fam.values())
+    print(f"# one fine-tuning step under ncu (`{path}`, last {len(step)} launches): {tot:.0f} us serialised, cold caches\n")
+    print("| kernel family | launches | us | share | DRAM MB / launch | DRAM GB/s | tensor pipe active % |")
+    print("|---|---|---|---|---|---|---|")
+    out = {}
+    for k, f in sorted(fam.items(), key=lambda kv: -kv[1]["us"]):
+        print(f"| `{k}` | {f['launches']} | {f['us']:.1f} | {100 * f['us'] / tot:.1f}% | {f['dram_bytes'] / f['launches'] / 1e6:.2f} | "
+              f"{f['dram_bytes'] / f['us'] / 1e3:.0f} | {f['tens'] / f['us'] if f['us'] else 0:.1f} |")
+        out[k] = {"launches": f["launches"], "dram_bytes_per_launch": f["dram_bytes"] / f["launches"],
+                  "ncu_us_per_launch": f["us"] / f["launches"], "tensor_pipe_active_pct": f["tens"] / f["us"] if f["us"] else 0.0,
+                  "source": path}
+    if len(sys.argv) > 3:
+        with open(sys.argv[3], "w") as fh:
+            json.dump(out, fh, indent=1)
+
+
 if __name__ == "__main__":
-    {"full": full, "launch": launch, "traffic": traffic}[sys.argv[1]](sys.argv[2])
+    {"full": full, "launch": launch, "traffic": traffic, "steptraffic": steptraffic}[sys.argv[1]](sys.argv[2])

@@ -88,6 +88,9 @@ class Program:
         dicts {name, kernel, ms, flops, bytes}.  Used by bench.py for the per-kernel roofline figures."""
         stream = torch.cuda.current_stream()
         evs = []
+        # keep the GPU busy while the host enqueues: an eager launch + two event records cost ~10 us of CPU time, more
+        # than many of the kernels last, and the idle gap would be counted inside the event interval
+        torch.cuda._sleep(int(30_000 * len(self.calls)))
         for (fn, args, name), meta in zip(self.calls, self.meta):
             if fn is None:
                 if name != "mark":

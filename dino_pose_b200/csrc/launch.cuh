@@ -1,16 +1,18 @@
 // Kernel launch helper shared by every launch site of the library.
 //
-// A fine-tuning step is ~260 dependent launches replayed as one CUDA graph, many of them 5-30 us long, so the
-// kernel-to-kernel hand-over (grid drain, launch latency, prologue of the next kernel) is a double-digit share of the
-// step.  Two measures, both applied here so that no launch site can forget them:
+// A fine-tuning step is ~260 dependent launches replayed as one CUDA graph, many of them 5-30 us long.  Two launch-level
+// measures were built here (one place, so that no launch site can forget them) and MEASURED on the benchmark step
+// (gpurun_out ab1, tools/gpu_job_pdl_ab.sh):
 //   * programmatic dependent launch: every kernel of the library starts with pdl_grid_sync() (griddepcontrol
-//     launch_dependents + wait, see below) and is launched with the programmatic-stream-serialization attribute, so
-//     the CTAs of launch i+1 are scheduled while launch i drains, run their prologue (barrier init, TMEM allocation,
-//     tensor-map prefetch, parameter loads from the constant bank) and block in griddepcontrol.wait until launch i has
-//     completed and its memory is visible.  Stream capture turns the attribute into programmatic graph edges.
-//   * one shared-memory carve-out for all kernels (the maximum): the GEMMs need 226 KB, the row-wise kernels none;
-//     alternating preferences forces an SM-wide L1/shared reconfiguration between launches, which needs an idle SM.
-// DP_PDL=0 / DP_CARVEOUT=0 switch either off (A/B measurements, debugging).
+//     launch_dependents + wait) and can be launched with the programmatic-stream-serialization attribute, so the CTAs
+//     of launch i+1 are scheduled while launch i drains, run their prologue (barrier init, TMEM allocation, tensor-map
+//     prefetch) and block in griddepcontrol.wait until launch i has completed.  Stream capture turns the attribute
+//     into programmatic graph edges.  Result: correct (GPU suite green) but SLOWER, 4.73 vs 4.59 ms per step: graph
+//     kernel nodes already hand over in ~1 us, and the early-resident CTAs of the next launch cost more than that.
+//   * one shared-memory carve-out (the maximum) for all kernels, to avoid L1/shared reconfiguration between the
+//     226 KB GEMMs and the row-wise kernels: 4.66 vs 4.59 ms, also slower (the row-wise kernels lose their L1).
+// Both therefore default to OFF; DP_PDL=1 / DP_CARVEOUT=1 switch them on (the device-side prologue is a no-op when
+// the kernel was launched without the attribute).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdlib.h>
@@ -30,11 +32,11 @@ inline int env_flag(const char* name, int dflt) {
   return v ? atoi(v) : dflt;
 }
 inline bool pdl_enabled() {
-  static const int v = env_flag("DP_PDL", 1);
+  static const int v = env_flag("DP_PDL", 0);
   return v != 0;
 }
 inline bool carveout_enabled() {
-  static const int v = env_flag("DP_CARVEOUT", 1);
+  static const int v = env_flag("DP_CARVEOUT", 0);
   return v != 0;
 }
 

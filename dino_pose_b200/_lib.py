@@ -91,6 +91,8 @@ SIGNATURES = {
     "dp_bn_finalize": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, d, f, f, c_vp],
     "dp_bn_fold_eval": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, f, c_vp],
     "dp_bn_apply": [c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, c_vp],
+    "dp_bn_finalize_apply": [c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i,
+                             f, f, c_vp],
     "dp_bn_bwd_reduce": [c_vp, c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, c_vp],
     "dp_bn_bwd_apply": [c_vp, c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i,
                         i, i, i, c_vp],

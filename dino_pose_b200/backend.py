@@ -275,6 +275,14 @@ class CudaBackend:
         self.prog.add("bn_apply", self.lib.dp_bn_apply, _p(raw), int(raw.dtype == torch.float32), _p(scale), _p(shift),
                       _p(add1), _p(add2), _p(out), P, C, int(relu), mode, keep=(raw, scale, shift, add1, add2, out))
 
+    def bn_finalize_apply(self, raw, sums, gamma, beta, rm, rv, scale, shift, mean, invstd, add1, add2, out, *, P, C,
+                          relu=True, mode=0, eps=1e-5, momentum=0.1):
+        """bn_finalize + bn_apply in one launch (count = P); `sums` is the [9][2*C] fp64 buffer of the layer."""
+        self.prog.add("bn_apply", self.lib.dp_bn_finalize_apply, _p(raw), int(raw.dtype == torch.float32), _p(sums), _p(gamma),
+                      _p(beta), _p(rm), _p(rv), _p(scale), _p(shift), _p(mean), _p(invstd), _p(add1), _p(add2), _p(out), P, C,
+                      int(relu), mode, eps, momentum,
+                      keep=(raw, sums, gamma, beta, rm, rv, scale, shift, mean, invstd, add1, add2, out))
+
     def bn_bwd_reduce(self, dout, raw, add1, scale, shift, mean, invstd, sums, *, P, C, relu=True, mode=0):
         self.prog.add("bn_bwd_reduce", self.lib.dp_bn_bwd_reduce, _p(dout), _p(raw), int(raw.dtype == torch.float32),
                       _p(add1), _p(scale), _p(shift),
@@ -287,7 +295,8 @@ class CudaBackend:
                       _p(add1), _p(gamma), _p(scale),
                       _p(shift), _p(mean), _p(invstd), _p(sums), _p(draw), _p(dres), _p(dgamma), _p(dbeta), P, C,
                       int(relu), mode, int(eval_mode), shuffle_oh, shuffle_ow,
-                      keep=(dout, raw, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta), launches=2)
+                      keep=(dout, raw, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta),
+                      launches=1 if C <= 512 else 2)
 
     def avgpool2(self, x, out, *, planes, OH, OW):
         self.prog.add("avgpool2", self.lib.dp_avgpool2, _p(x), _p(out), planes, OH, OW, keep=(x, out))

@@ -17,7 +17,7 @@ struct GemmVariant {
   int pair;
   cudaError_t (*launch)(const GemmParams&, int grid, cudaStream_t);
 };
-const GemmVariant* select_gemm_variant(const Epilogue& e, int a_mode, int block_n, int pair);
+const GemmVariant* select_gemm_variant(const Epilogue& e, int a_mode, int block_n, int pair, bool tma_out_ok);
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, int grid, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
@@ -63,7 +63,7 @@ static EncodeTiledFn encode_fn() {
 
 // bf16 tensor map, 128B swizzle, zero OOB fill.  dims/box innermost first; strides (bytes) for dims 1..rank-1.
 static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides,
-                     const uint32_t* box) {
+                     const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) return set_error(-10, "cuTensorMapEncodeTiled entry point unavailable");
   if (reinterpret_cast<uintptr_t>(ptr) & 15) return set_error(-11, "TMA base pointer %p not 16-byte aligned", ptr);
@@ -81,7 +81,7 @@ static int make_tmap(CUtensorMap* m, const void* ptr, int rank, const uint64_t* 
                                           (unsigned long long)strides[i]);
   }
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), d, st, b, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_error(-14, "cuTensorMapEncodeTiled failed with CUresult %d", int(r));
   return 0;
@@ -154,19 +154,25 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   }
   // ---- tile shape: CTA-pair 256 x {192, 256, 128} tiles when a variant is compiled for this epilogue and N divides,
   // else single-CTA 128 x {128, 64, 32}.  block_n fixes the width, cta_pair (1 pair / 2 single) the kind.
+  // plain bf16 outputs (QKV, fc1) are written with TMA tile stores when the output qualifies (DP_GEMM_TMA_OUT=0: off)
+  static int allow_tma_out = -1;
+  if (allow_tma_out < 0) { const char* v = getenv("DP_GEMM_TMA_OUT"); allow_tma_out = v ? atoi(v) : 1; }
+  const bool tma_out_ok = allow_tma_out && a->a_mode == 0 && e.row_map == DP_ROWMAP_IDENTITY && e.out_dtype == DP_OUT_BF16 &&
+                          !e.scale && !e.ls && !e.residual && !e.aux_out && !e.aux_in && !e.stats && a->act != DP_ACT_RELU &&
+                          (e.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && dbg == 0;
   const GemmVariant* var = nullptr;
   const bool may_pair = (allow_pair || a->cta_pair == 1) && a->cta_pair != 2 && a->M > 128;
   const bool may_single = a->cta_pair != 1;
   if (a->block_n != 0) {
-    if (may_pair) var = select_gemm_variant(e, a->a_mode, a->block_n, 1);
-    if (!var && may_single) var = select_gemm_variant(e, a->a_mode, a->block_n, 0);
+    if (may_pair) var = select_gemm_variant(e, a->a_mode, a->block_n, 1, false);
+    if (!var && may_single) var = select_gemm_variant(e, a->a_mode, a->block_n, 0, tma_out_ok);
   } else {
     if (may_pair) {
       const int cand[3] = {192, 256, 128};
       for (int i = 0; i < 3 && !var; ++i)
-        if (a->N % cand[i] == 0 && a->N >= 2 * cand[i] - 128) var = select_gemm_variant(e, a->a_mode, cand[i], 1);
+        if (a->N % cand[i] == 0 && a->N >= 2 * cand[i] - 128) var = select_gemm_variant(e, a->a_mode, cand[i], 1, false);
     }
-    if (!var && may_single) var = select_gemm_variant(e, a->a_mode, a->N >= 128 ? 128 : (a->N > 32 ? 64 : 32), 0);
+    if (!var && may_single) var = select_gemm_variant(e, a->a_mode, a->N >= 128 ? 128 : (a->N > 32 ? 64 : 32), 0, tma_out_ok);
   }
   if (!var) return set_error(-3, "dp_gemm_bf16: no kernel variant for block_n %d (cta_pair %d)", a->block_n, a->cta_pair);
   const int bn = var->bn;
@@ -211,6 +217,12 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
     const uint64_t st[1] = {uint64_t(a->ldw) * 2};
     const uint32_t box[2] = {64, uint32_t(var->pair ? bn / 2 : bn)};   // a pair CTA stages half of the weight rows
     if ((rc = make_tmap(&p.tmB, a->W, 2, dims, st, box))) return rc;
+  }
+  if (var->opt & 128) {   // OP_TMA_OUT: 32 x 32 bf16 boxes, 64-byte rows, 64B swizzle; columns >= n_valid and rows >= M are clipped
+    const uint64_t dims[2] = {uint64_t(e.n_valid), uint64_t(a->M)};
+    const uint64_t st[1] = {uint64_t(e.ldo) * 2};
+    const uint32_t box[2] = {32, 32};
+    if ((rc = make_tmap(&p.tmC, e.out, 2, dims, st, box, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
   int grid;
   if (var->pair) {

@@ -30,6 +30,8 @@ cudaError_t launch_bn_finalize(double*, const float*, const float*, float*, floa
                                double, float, float, cudaStream_t);
 cudaError_t launch_bn_fold_eval(const float*, const float*, const float*, const float*, const float*, float*, float*, int,
                                 float, cudaStream_t);
+cudaError_t launch_bn_finalize_apply(const void*, int, double*, const float*, const float*, float*, float*, float*, float*, float*,
+                                     float*, const void*, const void*, void*, long long, int, int, int, float, float, cudaStream_t);
 cudaError_t launch_bn_apply(const void*, int, const float*, const float*, const void*, const void*, void*, long long, int,
                             int, int, cudaStream_t);
 cudaError_t launch_bn_bwd_reduce(const void*, const void*, int, const void*, const float*, const float*, const float*,
@@ -150,6 +152,17 @@ extern "C" int dp_bn_apply(const void* raw, int raw_f32, const float* scale, con
   if (!raw || !scale || !shift || !out || C % 8) return set_error(-1, "dp_bn_apply: bad args");
   if (mode == 1 && !add1) return set_error(-2, "dp_bn_apply: mode 1 needs add1");
   return cuda_error(launch_bn_apply(raw, raw_f32, scale, shift, add1, add2, out, P, C, relu, mode, ST), "dp_bn_apply");
+}
+extern "C" int dp_bn_finalize_apply(const void* raw, int raw_f32, double* sums, const float* gamma, const float* beta, float* rm,
+                                    float* rv, float* scale, float* shift, float* mean, float* invstd, const void* add1,
+                                    const void* add2, void* out, long long P, int C, int relu, int mode, float eps,
+                                    float momentum, void* stream) {
+  if (!raw || !sums || !gamma || !beta || !scale || !shift || !mean || !invstd || !out || C % 8 || C > 512)
+    return set_error(-1, "dp_bn_finalize_apply: bad args");
+  if (mode == 1 && !add1) return set_error(-2, "dp_bn_finalize_apply: mode 1 needs add1");
+  return cuda_error(launch_bn_finalize_apply(raw, raw_f32, sums, gamma, beta, rm, rv, scale, shift, mean, invstd, add1, add2, out,
+                                             P, C, relu, mode, eps, momentum, ST),
+                    "dp_bn_finalize_apply");
 }
 extern "C" int dp_bn_bwd_reduce(const void* dout, const void* raw, int raw_f32, const void* add1, const float* scale,
                                 const float* shift, const float* mean, const float* invstd, double* sums, long long P,

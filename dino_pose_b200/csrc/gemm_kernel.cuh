@@ -35,7 +35,8 @@ enum : int {
   OP_AUX_IN = 16,    // multiply by gelu'(aux_in)
   OP_STATS = 32,     // fused BatchNorm statistics
   OP_CONV = 64,      // implicit-conv row decoding (a_mode = 1)
-  OP_ALL = 127
+  OP_ALL = 127,
+  OP_TMA_OUT = 128   // bf16 identity-map output written with TMA tile stores (epilogue_tile_tma); not part of OP_ALL
 };
 
 struct GemmVariant {
@@ -104,7 +105,8 @@ constexpr int kRowBatch = 4;   // rows (x4 row groups) whose loads are in flight
 template <int BN, int OUT, int ACT, int MAP, int OPT>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int q, int half, int lane,
                                               int m_blk, int n_blk, float* __restrict__ stg,
-                                              float* __restrict__ colstats, long long* __restrict__ tr = nullptr) {
+                                              float* __restrict__ colstats, uint64_t* tfull, uint32_t tfull_phase,
+                                              long long* __restrict__ tr = nullptr) {
   const Epilogue& e = p.epi;
   const int map = (MAP == EM_RUNTIME) ? e.row_map : MAP;
   const bool conv = (OPT & OP_CONV) && p.a_mode == 1;
@@ -150,6 +152,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
     float* o = reinterpret_cast<float*>(e.out);
     const long long hw = (long long)p.OH * p.OW;
     const int act = (ACT == EA_RUNTIME) ? e.act : ACT;
+    mbar_wait(tfull, tfull_phase);
+    tc_fence_after();
 #pragma unroll 1
     for (int c = half; c < BN / 32; c += kEpiGroups) {
       uint32_t v[32];
@@ -196,12 +200,15 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
   //  16-byte pieces in phase 2 halves the staging traffic but needs 16 broadcast parameter loads per chunk and thread
   //  and serialises the GELU per row: qkv 20.4 -> 23.0 us, fc1 32.2 -> 45.0 us.)
   const int rr = lane >> 3, cg = lane & 7;
+  // The accumulator-ready wait sits INSIDE the chunk loop, after every global load of the first chunk (per-column
+  // parameters, residual / aux rows) has been issued: those loads do not depend on the accumulator, and an L2 round
+  // trip under load (1-1.5 k cycles) is as long as the whole main loop of a K = 384 tile.
+  bool waited = false;
 #pragma unroll 1
   for (int c = half; c < BN / 32; c += kEpiGroups) {
     if (e.debug & 8) continue;
     const int col0 = n_blk * BN + c * 32;
     if (col0 >= e.n_valid) continue;  // warp-uniform
-    // per-column parameters first: their global-load latency overlaps the TMEM load and the transpose
     const int ccol = col0 + cg * 4;
     const bool cvalid = ccol < e.n_valid;  // n_valid % 4 == 0 (checked by the launcher)
     float4 sc = make_float4(1.f, 1.f, 1.f, 1.f), bi = make_float4(0.f, 0.f, 0.f, 0.f), lsv = sc;
@@ -209,6 +216,42 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       if (has_scale) sc = ldg4(e.scale + ccol);
       if (e.bias != nullptr) bi = ldg4(e.bias + ccol);
       if (has_ls) lsv = ldg4(e.ls + ccol);
+    }
+    // row offsets (one shuffle each) and every global LOAD of the chunk, all 8 row groups back to back.  The residual
+    // may alias the output (in-place residual stream), which stops the compiler from hoisting loads above the stores
+    // of earlier rows by itself -- each element is read before it is written by the same thread, so this is safe.
+    float4 res32[(OPT & OP_LSRES) ? 8 : 1];
+    uint2 res16[(OPT & OP_RES_BF16) ? 8 : 1];
+    uint2 auxin[(OPT & OP_AUX_IN) ? 8 : 1];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + rr;
+      const bool ok = __shfl_sync(kFull, off_out, row) != kInvalidRow && cvalid;
+      if constexpr ((OPT & (OP_LSRES | OP_RES_BF16)) != 0) {
+        const uint32_t r_off = __shfl_sync(kFull, off_res, row);
+        if constexpr ((OPT & OP_LSRES) != 0) {
+          res32[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has_res32 && ok) res32[it] = ldg4(e.residual + r_off + ccol);
+        }
+        if constexpr ((OPT & OP_RES_BF16) != 0) {
+          res16[it] = make_uint2(0u, 0u);
+          if (has_res16 && ok)
+            res16[it] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.residual) + r_off + ccol));
+        }
+      }
+      if constexpr ((OPT & (OP_AUX_OUT | OP_AUX_IN)) != 0) {
+        const uint32_t ao = __shfl_sync(kFull, off_aux, row);
+        if constexpr ((OPT & OP_AUX_IN) != 0) {
+          auxin[it] = make_uint2(0u, 0u);
+          if (has_aux_in && ok)
+            auxin[it] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.aux_in) + ao + ccol));
+        }
+      }
+    }
+    if (!waited) {
+      mbar_wait(tfull, tfull_phase);
+      tc_fence_after();
+      waited = true;
     }
     uint32_t v[32];
     if (tr) tr[0] = clock64();
@@ -232,51 +275,13 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       tap_off = uint32_t((tap >> 1) * (2 * p.OW) + (tap & 1)) * uint32_t(e.ldo);
     }
     float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-    // pass A: row offsets (one shuffle each), staged accumulators, and every global LOAD of the chunk issued
-    // back to back.  The residual may alias the output (in-place residual stream), which stops the compiler
-    // from hoisting loads above the stores of earlier rows by itself -- each element is read before it is
-    // written by the same thread, so hoisting by hand is safe.
+    // branch-free math for all 8 row groups (the compiler interleaves the rows), predicated stores only
 #pragma unroll
-    for (int ib = 0; ib < 8; ib += kRowBatch) {
-    uint32_t o_off[kRowBatch];
-    float4 xs[kRowBatch];
-    float4 res32[(OPT & OP_LSRES) ? kRowBatch : 1];
-    uint2 res16[(OPT & OP_RES_BF16) ? kRowBatch : 1];
-    uint2 auxin[(OPT & OP_AUX_IN) ? kRowBatch : 1];
-    uint32_t a_off[(OPT & OP_AUX_OUT) ? kRowBatch : 1];
-#pragma unroll
-    for (int it = 0; it < kRowBatch; ++it) {
-      const int row = (ib + it) * 4 + rr;
-      o_off[it] = __shfl_sync(kFull, off_out, row);
-      const bool ok = o_off[it] != kInvalidRow && cvalid;
-      if constexpr ((OPT & (OP_LSRES | OP_RES_BF16)) != 0) {
-        const uint32_t r_off = __shfl_sync(kFull, off_res, row);
-        if constexpr ((OPT & OP_LSRES) != 0) {
-          res32[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (has_res32 && ok) res32[it] = ldg4(e.residual + r_off + ccol);
-        }
-        if constexpr ((OPT & OP_RES_BF16) != 0) {
-          res16[it] = make_uint2(0u, 0u);
-          if (has_res16 && ok)
-            res16[it] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.residual) + r_off + ccol));
-        }
-      }
-      if constexpr ((OPT & (OP_AUX_OUT | OP_AUX_IN)) != 0) {
-        const uint32_t ao = __shfl_sync(kFull, off_aux, row);
-        if constexpr ((OPT & OP_AUX_OUT) != 0) a_off[it] = ao;
-        if constexpr ((OPT & OP_AUX_IN) != 0) {
-          auxin[it] = make_uint2(0u, 0u);
-          if (has_aux_in && ok)
-            auxin[it] = __ldg(reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(e.aux_in) + ao + ccol));
-        }
-      }
-      xs[it] = *reinterpret_cast<const float4*>(stg + row * 32 + ((cg ^ (row & 7)) << 2));
-    }
-    // pass B: branch-free math for all 8 rows (the compiler interleaves the rows), predicated stores only
-#pragma unroll
-    for (int it = 0; it < kRowBatch; ++it) {
-      const float4 x = xs[it];
-      const bool ok = o_off[it] != kInvalidRow && cvalid;
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + rr;
+      const float4 x = *reinterpret_cast<const float4*>(stg + row * 32 + ((cg ^ (row & 7)) << 2));
+      const uint32_t o_off = __shfl_sync(kFull, off_out, row);   // re-fetched instead of kept live across the TMEM load
+      const bool ok = o_off != kInvalidRow && cvalid;
       float f[4];
       if constexpr ((OPT & OP_SCALE) != 0) {
         f[0] = fmaf(x.x, sc.x, bi.x); f[1] = fmaf(x.y, sc.y, bi.y); f[2] = fmaf(x.z, sc.z, bi.z); f[3] = fmaf(x.w, sc.w, bi.w);
@@ -292,11 +297,12 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         }
       }
       if constexpr ((OPT & OP_AUX_OUT) != 0) {
+        const uint32_t a_off = __shfl_sync(kFull, off_aux, row);   // all lanes take part
         if (has_aux_out && ok) {
           uint2 t;
           t.x = pack_bf16x2(f[0], f[1]);
           t.y = pack_bf16x2(f[2], f[3]);
-          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux_out) + a_off[it] + ccol) = t;
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux_out) + a_off + ccol) = t;
         }
       }
       if constexpr (ACT == EA_RELU) {
@@ -332,7 +338,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
 #pragma unroll
         for (int k = 0; k < 4; ++k) f[k] += t[k];
       }
-      const uint32_t off = o_off[it] + tap_off + ocol;
+      const uint32_t off = o_off + tap_off + ocol;
       if (ok) {
         if (out_f32) {
           *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + off) = make_float4(f[0], f[1], f[2], f[3]);
@@ -343,9 +349,8 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
           *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.out) + off) = t;
         }
       }
+      if (tr && (it & 3) == 3) tr[3 + it / 4] = clock64();
     }
-    if (tr) tr[3 + ib / kRowBatch] = clock64();
-    }  // row batch
     if constexpr ((OPT & OP_STATS) != 0) {
       if (has_stats) {
 #pragma unroll
@@ -365,6 +370,83 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
       }
     }
     __syncwarp();  // staging buffer is rewritten by the next chunk
+  }
+  if (!waited) {   // every chunk of this warp skipped: still consume the phase before releasing the accumulator
+    mbar_wait(tfull, tfull_phase);
+    tc_fence_after();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Epilogue for plain bf16 outputs (QKV, fc1): bias / GELU applied with thread = row straight out of TMEM, the
+// 32 x 32 bf16 chunk staged in shared memory in the 64B-swizzled layout of a TMA box and written with ONE
+// cp.async.bulk.tensor store per chunk (rows / columns outside the tensor are clipped by the tensor map).
+// Against epilogue_tile this removes the fp32 transpose round trip through shared memory, the per-row offset
+// shuffles and the 8 predicated global stores per lane and chunk: ~70 instead of ~340 instructions per chunk
+// and warp before the activation, and the store latency is off the warp's critical path (two staging buffers per
+// warp, bulk_wait_read before a buffer is reused).
+template <int BN>
+struct TmaEpiBias {
+  float v[(BN / 32 + kEpiGroups - 1) / kEpiGroups];   // lane l holds bias[col0 + l] of every chunk this warp handles
+};
+// Issued BEFORE the wait for the accumulator: the bias segment of a tile is new to the SM (L1 is invalidated per launch,
+// n_blk changes every tile), i.e. an L2 round trip of 1-1.5 k cycles under load that would otherwise sit on the
+// epilogue's critical path (in-kernel timeline, DP_GEMM_TRACE=1: 1.8-2.3 k cycles per chunk before).
+template <int BN>
+__device__ __forceinline__ void epilogue_tma_prefetch(const GemmParams& p, int half, int lane, int n_blk, TmaEpiBias<BN>& pre) {
+  const Epilogue& e = p.epi;
+  int i = 0;
+#pragma unroll
+  for (int c = half; c < BN / 32; c += kEpiGroups, ++i) {
+    const int col = n_blk * BN + c * 32 + lane;
+    pre.v[i] = (e.bias != nullptr && col < e.n_valid) ? __ldg(e.bias + col) : 0.f;
+  }
+}
+template <int BN, int ACT>
+__device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, uint32_t tmem_acc, int q, int half, int lane,
+                                                  int m_blk, int n_blk, uint8_t* __restrict__ stg, uint32_t& nstore,
+                                                  const TmaEpiBias<BN>& pre) {
+  const Epilogue& e = p.epi;
+  constexpr uint32_t kFull = 0xffffffffu;
+  int i = 0;
+#pragma unroll
+  for (int c = half; c < BN / 32; c += kEpiGroups, ++i) {
+    const int col0 = n_blk * BN + c * 32;
+    if (col0 >= e.n_valid) continue;  // warp-uniform
+    uint32_t v[32];
+    tmem_ld_32x32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
+    tmem_ld_wait();
+    const float bl = pre.v[i];
+    uint32_t pk[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float f0 = __uint_as_float(v[2 * j]) + __shfl_sync(kFull, bl, 2 * j);
+      float f1 = __uint_as_float(v[2 * j + 1]) + __shfl_sync(kFull, bl, 2 * j + 1);
+      if constexpr (ACT == EA_GELU) {
+        f0 = gelu_fast(f0); f1 = gelu_fast(f1);
+      } else if constexpr (ACT == EA_RELU) {
+        f0 = fmaxf(f0, 0.f); f1 = fmaxf(f1, 0.f);
+      }
+      pk[j] = pack_bf16x2(f0, f1);
+    }
+    uint8_t* buf = stg + (nstore & 1u) * 2048u;
+    if (nstore >= 2) {   // the store issued two chunks ago has to be done reading this buffer
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+    }
+    // row = lane, 64 bytes per row; 16-byte piece j lands at j ^ ((row >> 1) & 3) (CU_TENSOR_MAP_SWIZZLE_64B)
+    uint8_t* rowp = buf + lane * 64;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_2d(&p.tmC, buf, col0, m_blk * kBlockM + q * 32);
+      bulk_commit();
+    }
+    ++nstore;
   }
 }
 
@@ -388,6 +470,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    if constexpr ((OPT & OP_TMA_OUT) != 0) tma_prefetch_desc(&p.tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -489,13 +572,22 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
     float* stg = staging + (warp - 2) * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t nstore = 0;   // OP_TMA_OUT: tile stores issued by this warp so far (selects the staging buffer)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       DP_TILE_COORDS(tile, m_blk, n_blk)
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       if (p.epi.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64) p.epi.trace[(tile / gridDim.x) * 4 + 2] = clock64();
       long long* tr = (p.epi.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64) ? p.epi.trace + 2048 + (tile / gridDim.x) * 8 : nullptr;
-      epilogue_tile<BN, OUT, ACT, MAP, OPT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk, stg, colstats, tr);
+      if constexpr ((OPT & OP_TMA_OUT) != 0) {
+        TmaEpiBias<BN> pre;
+        epilogue_tma_prefetch<BN>(p, half, lane, n_blk, pre);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        epilogue_tile_tma<BN, ACT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk,
+                                   reinterpret_cast<uint8_t*>(stg), nstore, pre);
+      } else {
+        epilogue_tile<BN, OUT, ACT, MAP, OPT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk, stg, colstats,
+                                              &tfull_bar[acc], acc_phase, tr);
+      }
       tc_fence_before();
       __syncwarp();
       if (tr) tr[5] = clock64();
@@ -523,6 +615,9 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
           }
         }
       }
+    }
+    if constexpr ((OPT & OP_TMA_OUT) != 0) {
+      if (lane == 0) bulk_wait_read<0>();   // shared memory must stay allocated until the last tile store has read it
     }
   }
 #undef DP_TILE_COORDS

@@ -152,9 +152,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     uint32_t acc_phase = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       DP_PAIR_COORDS(tile, m_blk, n_blk)
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
-      epilogue_tile<BN, OUT, ACT, MAP, OPT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk, stg, colstats);
+      epilogue_tile<BN, OUT, ACT, MAP, OPT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk, stg, colstats,
+                                            &tfull_bar[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {

@@ -260,7 +260,7 @@ extern const int kNumGemmVariantsA, kNumGemmVariantsB, kNumGemmVariantsC, kNumGe
 
 // Pick the cheapest compiled variant (single-CTA or CTA-pair, as requested) whose compile-time feature set covers
 // what this launch needs; nullptr if none is compiled for this tile width.
-const GemmVariant* select_gemm_variant(const Epilogue& e, int a_mode, int block_n, int pair) {
+const GemmVariant* select_gemm_variant(const Epilogue& e, int a_mode, int block_n, int pair, bool tma_out_ok) {
   int need = 0;
   if (e.scale) need |= OP_SCALE;
   if (e.ls || (e.residual && !e.res_is_bf16)) need |= OP_LSRES;
@@ -283,7 +283,9 @@ const GemmVariant* select_gemm_variant(const Epilogue& e, int a_mode, int block_
       if (v.act != EA_RUNTIME && v.act != e.act) continue;
       if (v.map != EM_RUNTIME && v.map != e.row_map) continue;
       if ((v.opt & need) != need) continue;
-      const int cost = __builtin_popcount(v.opt) + 8 * ((v.out == EO_RUNTIME) + (v.act == EA_RUNTIME) + (v.map == EM_RUNTIME));
+      if ((v.opt & OP_TMA_OUT) && !tma_out_ok) continue;
+      const int cost = __builtin_popcount(v.opt & OP_ALL) + 8 * ((v.out == EO_RUNTIME) + (v.act == EA_RUNTIME) + (v.map == EM_RUNTIME)) -
+                       ((v.opt & OP_TMA_OUT) ? 64 : 0);   // a qualifying output prefers the TMA-store epilogue
       if (cost < best_cost) { best_cost = cost; best = &v; }
     }
   return best;

@@ -41,6 +41,7 @@ struct Epilogue {
 struct alignas(64) GemmParams {
   CUtensorMap tmA;  // plain: 2D {K, M} box {64,128}; conv: 4D {C, W, H, B} box {64, bw, bh, bb}
   CUtensorMap tmB;  // 2D {Ktotal, N} box {64, BN}
+  CUtensorMap tmC;  // OP_TMA_OUT variants only: bf16 output, 2D {n_valid, M} box {32, 32}, 64B swizzle
   Epilogue epi;
   int M, N, num_k_blocks;
   int m_tiles, n_tiles;

@@ -87,6 +87,20 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// shared -> global tile store (bulk async-group completion): the issuing thread commits a group per store and waits
+// with bulk_wait_read<N>() until all but the N most recent groups have finished READING shared memory.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+
 // ----------------------------------------------------------------------------- tcgen05 / TMEM
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_holder, uint32_t ncols) {  // whole warp
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_holder)),
@@ -198,10 +212,23 @@ __device__ __forceinline__ float gelu_fast(float x) {
   const float hx = 0.5f * x;
   return fmaf(hx, th, hx);
 }
-__device__ __forceinline__ float gelu_fast_grad(float x) {
+__device__ __forceinline__ float gelu_as_grad(float x) {
   float e;
   const float phi = gelu_phi_parts(x, e);
   return fmaf(x * 0.3989422804014327f, e, phi);
+}
+// derivative of gelu_fast (same fit, same single MUFU.TANH): 0.5 (1 + th) + 0.5 x (1 - th^2) (a + 3 b x^2 + 5 c x^4);
+// |error| vs the exact erf-GELU derivative <= 3e-4 before the MUFU error
+__device__ __forceinline__ float gelu_fast_grad(float x) {
+  const float x2 = fminf(x * x, 64.f);
+  float p = fmaf(-0.00035190239f, x2, 0.03700802f);
+  p = fmaf(p, x2, 0.79750528f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(p * x));
+  float q = fmaf(5.f * -0.00035190239f, x2, 3.f * 0.03700802f);
+  q = fmaf(q, x2, 0.79750528f);
+  const float r = (0.5f * x) * fmaf(-th, th, 1.f);
+  return fmaf(r, q, fmaf(0.5f, th, 0.5f));
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

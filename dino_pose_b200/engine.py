@@ -488,10 +488,15 @@ class PoseEngine:
         bn = L.bn
         if not L.t.get("stats_fused"):
             be.bn_stats(raw, L.t["sums"], P=P, C=L.cout)
+        out = out if out is not None else self.new((P, L.cout), self.adt)
+        if L.cout <= 512:
+            be.bn_finalize_apply(raw, L.t["sums"], self.p(bn + ".weight"), self.p(bn + ".bias"), self.p(bn + ".running_mean"),
+                                 self.p(bn + ".running_var"), L.t["scale"], L.t["shift"], L.t["mean"], L.t["invstd"],
+                                 add1, add2, out, P=P, C=L.cout, relu=L.relu, mode=mode)
+            return out
         be.bn_finalize(L.t["sums"], self.p(bn + ".weight"), self.p(bn + ".bias"), self.p(bn + ".running_mean"),
                        self.p(bn + ".running_var"), L.t["scale"], L.t["shift"], L.t["mean"], L.t["invstd"], C=L.cout,
                        count=P)
-        out = out if out is not None else self.new((P, L.cout), self.adt)
         be.bn_apply(raw, L.t["scale"], L.t["shift"], add1, add2, out, P=P, C=L.cout, relu=L.relu, mode=mode)
         return out
 

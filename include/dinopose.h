@@ -156,6 +156,15 @@ int dp_bn_fold_eval(const float* gamma, const float* beta, const float* running_
                     const float* conv_bias, float* scale, float* shift, int C, float eps, void* stream);
 int dp_bn_apply(const void* raw, int raw_is_f32, const float* scale, const float* shift, const void* add1,
                 const void* add2, void* out, long long P, int C, int relu, int mode, void* stream);
+/* dp_bn_finalize + dp_bn_apply in ONE launch (pose_heads.py train-mode nn.BatchNorm2d + ReLU / adds): every thread
+ * block derives scale / shift from `sums` itself, block 0 writes scale / shift / mean / invstd (kept for the backward)
+ * and updates the running statistics, the last block to finish re-zeroes sums[0 .. 2*C).  count = P.  C <= 512.
+ * `sums` must be the [DP_BN_BWD_REPLICAS + 1][2*C] buffer described below (its last 4 bytes hold a ticket counter,
+ * zero on first use). */
+int dp_bn_finalize_apply(const void* raw, int raw_is_f32, double* sums, const float* gamma, const float* beta,
+                         float* running_mean, float* running_var, float* scale, float* shift, float* mean,
+                         float* invstd, const void* add1, const void* add2, void* out, long long P, int C, int relu,
+                         int mode, float eps, float momentum, void* stream);
 /* BatchNorm backward.  `sums` here is fp64 [DP_BN_BWD_REPLICAS + 1][2*C]: the first DP_BN_BWD_REPLICAS blocks are
  * accumulators, zero on entry of dp_bn_bwd_reduce (the thread blocks spread their atomics over the replicas);
  * dp_bn_bwd_apply first adds the replicas up, forms the per-channel coefficients (scratch = the last block), writes

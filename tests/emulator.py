@@ -329,6 +329,11 @@ class TorchEmulator:
             sums.zero_()
         self.prog.calls.append(fn)
 
+    def bn_finalize_apply(self, raw, sums, gamma, beta, rm, rv, scale, shift, mean, invstd, add1, add2, out, *, P, C,
+                          relu=True, mode=0, eps=1e-5, momentum=0.1):
+        self.bn_finalize(sums, gamma, beta, rm, rv, scale, shift, mean, invstd, C=C, count=P, eps=eps, momentum=momentum)
+        self.bn_apply(raw, scale, shift, add1, add2, out, P=P, C=C, relu=relu, mode=mode)
+
     def bn_fold_eval(self, gamma, beta, rm, rv, conv_bias, scale, shift, *, C, eps=1e-5):
         def fn():
             sc = gamma.detach() * torch.rsqrt(rv + eps)

@@ -477,8 +477,9 @@ def test_dwconv_and_wgrad():
     assert rel(dw, wr.grad) < 1e-3
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("mode,rawdt,C", [(0, BF, 128), (1, BF, 128), (0, torch.float32, 512), (1, torch.float32, 64)])
-def test_batchnorm_train_fwd_bwd(mode, rawdt, C):
+def test_batchnorm_train_fwd_bwd(mode, rawdt, C, fused):
     P = 3 * 16 * 16
     raw = (rnd(P, C) * 1.5 + 0.2).to(rawdt)
     gamma, beta = rnd(C, seed=1) * 0.1 + 1, rnd(C, seed=2) * 0.1
@@ -492,8 +493,12 @@ def test_batchnorm_train_fwd_bwd(mode, rawdt, C):
 
     def fwd(b):
         b.bn_stats(raw, sums, P=P, C=C)
-        b.bn_finalize(sums, gamma, beta, rm2, rv2, scale, shift, mean, invstd, C=C, count=P)
-        b.bn_apply(raw, scale, shift, add1, add2, out, P=P, C=C, relu=True, mode=mode)
+        if fused:   # one launch: per-block finalize, last block re-zeroes the sums
+            b.bn_finalize_apply(raw, sums, gamma, beta, rm2, rv2, scale, shift, mean, invstd, add1, add2, out, P=P, C=C,
+                                relu=True, mode=mode)
+        else:
+            b.bn_finalize(sums, gamma, beta, rm2, rv2, scale, shift, mean, invstd, C=C, count=P)
+            b.bn_apply(raw, scale, shift, add1, add2, out, P=P, C=C, relu=True, mode=mode)
     run(fwd)
     rr = raw.float().requires_grad_(True)
     gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
@@ -515,11 +520,13 @@ def test_batchnorm_train_fwd_bwd(mode, rawdt, C):
                         mode=mode)
         b.bn_bwd_apply(dout, raw, add1 if mode == 1 else None, gamma, scale, shift, mean, invstd, sums, draw, dres, dg,
                        db, P=P, C=C, relu=True, mode=mode)
-    run(bwd)
-    assert rel(draw.float(), rr.grad) < 2e-2
-    assert rel(dg, gr.grad) < 1e-2 and rel(db, br.grad) < 1e-2
-    if mode == 1:
-        assert rel(dres.float(), a1.grad) < 1e-2
+    for _ in range(2):   # the second pass checks that the accumulators were re-zeroed by the first
+        run(bwd)
+        assert sums.abs().max().item() == 0
+        assert rel(draw.float(), rr.grad) < 2e-2
+        assert rel(dg, gr.grad) < 1e-2 and rel(db, br.grad) < 1e-2
+        if mode == 1:
+            assert rel(dres.float(), a1.grad) < 1e-2
 
 
 def test_small_ops():

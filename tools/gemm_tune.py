@@ -18,6 +18,7 @@ SHAPES = {
     "proj": (M, 384, 384, "res_f32"),
     "fc1": (M, 1536, 384, "gelu_bf16"),
     "fc2": (M, 384, 1536, "res_f32"),
+    "fc2dg": (M, 1536, 384, "auxin_bf16"),     # last block's fc2 input gradient: x gelu'(pre-activation)
     "fc1_B": (M, 3072, 768, "gelu_bf16"),
     "fc2_B": (M, 768, 3072, "res_f32"),
 }
@@ -35,6 +36,10 @@ def bench(name, bn, reps=20, nbuf=6, pair=2):
         if epi == "bias_bf16":
             out = torch.empty(m, n, device=dev, dtype=BF)
             be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, block_n=bn, cta_pair=pair)
+        elif epi == "auxin_bf16":
+            out = torch.empty(m, n, device=dev, dtype=BF)
+            aux = torch.randn(m, n, device=dev).to(BF)
+            be.gemm(A, W, out, M=m, N=n, K=k, aux_in=aux, ld_aux=n, block_n=bn, cta_pair=pair)
         elif epi == "gelu_bf16":
             out = torch.empty(m, n, device=dev, dtype=BF)
             be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, act="gelu", block_n=bn, cta_pair=pair)

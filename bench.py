@@ -265,7 +265,37 @@ def run_ours(args):
         top = max(agg.items(), key=lambda kv: kv[1]["ms"])
         name, a = top
         total_ms = sum(v["ms"] for v in agg.values())
-        achieved = a["flops"] / (a["ms"] * 1e-3) / 1e12 if a["ms"] > 0 else 0.0
+        achieved_events = a["flops"] / (a["ms"] * 1e-3) / 1e12 if a["ms"] > 0 else 0.0
+        # The event pair around a single eager launch also contains the launch hand-over (measured ~5 us per pair:
+        # the event table sums to ~1.3 ms more than the graph-replayed step).  The figure reported as `achieved` is
+        # therefore taken from a CUDA graph that holds ONLY this family's launches of one step, in step order, on the
+        # buffers of the last real step, replayed back to back: GPU time / launches, timed with events on the
+        # launching stream.  (Done last: the stray BatchNorm statistics it accumulates are re-zeroed below.)
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        fam_graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            for p in progs:
+                p.run_family(name)
+            torch.cuda.synchronize()
+            with torch.cuda.graph(fam_graph, stream=side):
+                fam_launches = sum(p.run_family(name) for p in progs)
+            fam_graph.replay()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            fam_reps = 5
+            f0.record(side)
+            for _ in range(fam_reps):
+                fam_graph.replay()
+            f1.record(side)
+            torch.cuda.synchronize()
+        fam_ms = f0.elapsed_time(f1) / fam_reps
+        torch.cuda.current_stream().wait_stream(side)
+        for L in plan["layers"].values():
+            if "sums" in L.t:
+                L.t["sums"].zero_()
+        fam_flops = a["flops"] / reps
+        achieved = fam_flops / (fam_ms * 1e-3) / 1e12
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "traffic.json")   # ncu --set full of one step, tools/ncu_summary.py traffic
         if os.path.exists(tpath):
@@ -280,8 +310,13 @@ def run_ours(args):
                                   "the launches of this kernel family in one step)" if traffic is not None else None,
                 "algorithmic_flops_per_launch": a["flops"] / a["n"],
                 "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-                "share_of_step": a["ms"] / total_ms, "launches_per_step": a["n"] // reps,
-                "avg_launch_ms": a["ms"] / a["n"],
+                "timing": "CUDA graph of this family's launches of one step (step order, buffers of the last step), "
+                          "replayed 5x, events on the launching stream",
+                "share_of_step": fam_ms / ms_step, "launches_per_step": fam_launches,
+                "avg_launch_ms": fam_ms / max(1, fam_launches),
+                "achieved_single_launch_events": achieved_events,
+                "single_launch_events_note": "event pair around each eager launch; includes ~5 us of launch hand-over per pair",
+                "avg_launch_ms_events": a["ms"] / a["n"],
                 "per_kernel_ms_per_step": {k: round(v["ms"] / reps, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:12]},
                 "step_tflops": FLOPS_PER_IMAGE_STEP * B / (ms_step * 1e-3) / 1e12,
                 "step_frac_of_peak": FLOPS_PER_IMAGE_STEP * B / (ms_step * 1e-3) / 1e12 / peaks["tf_sustained"]}

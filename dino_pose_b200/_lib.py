@@ -91,6 +91,8 @@ SIGNATURES = {
     "dp_bn_finalize": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, d, f, f, c_vp],
     "dp_bn_fold_eval": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, f, c_vp],
     "dp_bn_apply": [c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, c_vp],
+    "dp_preprocess_workspace_bytes": [i, i, i, i, i],
+    "dp_preprocess_u8": [c_vp, i, i, i, i, i, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp],
     "dp_bn_finalize_apply": [c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i,
                              f, f, c_vp],
     "dp_bn_bwd_reduce": [c_vp, c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, c_vp],
@@ -108,7 +110,7 @@ SIGNATURES = {
     "dp_pack_weights_bf16": [c_vp, i, c_ll, c_vp],
     "dp_add_i64": [c_vp, i, c_ll, c_vp],
 }
-_RESTYPES = {"dp_last_error": C.c_char_p}
+_RESTYPES = {"dp_last_error": C.c_char_p, "dp_preprocess_workspace_bytes": C.c_longlong}
 
 _lib = None
 

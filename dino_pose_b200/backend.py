@@ -69,6 +69,20 @@ class Program:
         """number of kernel launches of this library per run"""
         return sum(m.get("launches", 1) for (fn, _a, _n), m in zip(self.calls, self.meta) if fn is not None)
 
+    def run_family(self, kernel):
+        """Launch only the calls of one kernel family (``meta['kernel']``), host steps and marks skipped: timing aid for
+        bench.py (the launches run on whatever the buffers hold; results are garbage by design)."""
+        stream = torch.cuda.current_stream().cuda_stream
+        n = 0
+        for (fn, args, name), meta in zip(self.calls, self.meta):
+            if fn is None or meta["kernel"] != kernel:
+                continue
+            rc = fn(*args, stream)
+            if rc != 0:
+                _lib.check(rc, name)
+            n += meta.get("launches", 1)
+        return n
+
     def run(self, on_mark=None):
         stream = torch.cuda.current_stream().cuda_stream
         for fn, args, name in self.calls:

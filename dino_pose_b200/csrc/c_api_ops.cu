@@ -30,6 +30,9 @@ cudaError_t launch_bn_finalize(double*, const float*, const float*, float*, floa
                                double, float, float, cudaStream_t);
 cudaError_t launch_bn_fold_eval(const float*, const float*, const float*, const float*, const float*, float*, float*, int,
                                 float, cudaStream_t);
+long long preprocess_workspace_bytes(int, int, int, int, int);
+cudaError_t launch_preprocess(const void*, int, int, int, int, int, const float*, const float*, float*, void*, long long, int*,
+                              cudaStream_t);
 cudaError_t launch_bn_finalize_apply(const void*, int, double*, const float*, const float*, float*, float*, float*, float*, float*,
                                      float*, const void*, const void*, void*, long long, int, int, int, float, float, cudaStream_t);
 cudaError_t launch_bn_apply(const void*, int, const float*, const float*, const void*, const void*, void*, long long, int,
@@ -152,6 +155,19 @@ extern "C" int dp_bn_apply(const void* raw, int raw_f32, const float* scale, con
   if (!raw || !scale || !shift || !out || C % 8) return set_error(-1, "dp_bn_apply: bad args");
   if (mode == 1 && !add1) return set_error(-2, "dp_bn_apply: mode 1 needs add1");
   return cuda_error(launch_bn_apply(raw, raw_f32, scale, shift, add1, add2, out, P, C, relu, mode, ST), "dp_bn_apply");
+}
+extern "C" long long dp_preprocess_workspace_bytes(int B, int H, int W, int short_edge, int crop) {
+  return preprocess_workspace_bytes(B, H, W, short_edge, crop);
+}
+extern "C" int dp_preprocess_u8(const void* images, int B, int H, int W, int short_edge, int crop, const float* mean255,
+                                const float* std255, float* out, void* workspace, long long workspace_bytes, void* stream) {
+  if (!images || !mean255 || !std255 || !out || !workspace) return set_error(-1, "dp_preprocess_u8: null pointer");
+  int status = 0;
+  cudaError_t e = launch_preprocess(images, B, H, W, short_edge, crop, mean255, std255, out, workspace, workspace_bytes, &status, ST);
+  if (status == -1) return set_error(-2, "dp_preprocess_u8: bad geometry B=%d H=%d W=%d short_edge=%d crop=%d (crop <= short_edge, crop <= 1024)", B, H, W, short_edge, crop);
+  if (status == -2) return set_error(-3, "dp_preprocess_u8: down-scaling factor too large (more than 160 filter taps)");
+  if (status == -3) return set_error(-4, "dp_preprocess_u8: workspace too small (%lld bytes given)", workspace_bytes);
+  return cuda_error(e, "dp_preprocess_u8");
 }
 extern "C" int dp_bn_finalize_apply(const void* raw, int raw_f32, double* sums, const float* gamma, const float* beta, float* rm,
                                     float* rv, float* scale, float* shift, float* mean, float* invstd, const void* add1,

@@ -18,14 +18,11 @@ _Z_CONFIG = {"hidden_dims": (1024, 512, 256), "dropout_rate": 0.1}   # reference
 
 
 def _image_processor(name):
-    """``AutoImageProcessor.from_pretrained`` needs the hub; callers only read ``crop_size`` / call it on PIL
-    images (demo.py:171,281).  Use the real one when it is cached locally, else a stub carrying the defaults."""
-    try:
-        from transformers import AutoImageProcessor
-        return AutoImageProcessor.from_pretrained(name, local_files_only=True)
-    except Exception:
-        return SimpleNamespace(crop_size={"height": 224, "width": 224}, size={"shortest_edge": 256},
-                               image_mean=[0.485, 0.456, 0.406], image_std=[0.229, 0.224, 0.225])
+    """The reference's ``AutoImageProcessor.from_pretrained`` (dinov2_pose.py:15,182) resolves to HF BitImageProcessor
+    with the DINOv2 preprocessor config; callers call it on PIL images / frames and read ``crop_size``
+    (demo.py:80,171,281; data_loader.py:52,137).  Same call form, same values, computed on the GPU."""
+    from ..preprocess import GpuBitImageProcessor
+    return GpuBitImageProcessor()
 
 
 class _PoseFunction(torch.autograd.Function):

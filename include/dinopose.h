@@ -213,6 +213,20 @@ int dp_pack_weights_bf16(const long long* jobs_dev, int njobs, long long max_tot
 /* *ptrs[i] += inc for n device int64 scalars (BatchNorm num_batches_tracked, torch bookkeeping). */
 int dp_add_i64(const long long* ptrs_dev, int n, long long inc, void* stream);
 
+/* ---- image pre-processing: replaces `self.image_processor(image, return_tensors="pt")`
+ * (reference model/dinov2_pose.py:15,182; demo.py:80,171; benchmark_model.py:35,45; data_loader/data_loader.py:52) =
+ * HF BitImageProcessor with the DINOv2 preprocessor config (transformers/image_processing_backends.py
+ * TorchvisionBackend.resize / center_crop / rescale_and_normalize over ATen's uint8 anti-aliased bicubic kernel).
+ * images: DEVICE uint8 [B, H, W, 3] RGB, interleaved, contiguous.  out: DEVICE fp32 [B, 3, crop, crop].
+ * Shortest edge -> short_edge (long edge int(short_edge * long / short)), bicubic + antialias in the CPU kernel's
+ * uint8 / int16-weight arithmetic (horizontal pass, uint8 rounding, vertical pass), center crop, then
+ * (float(u8) - mean255[c]) / std255[c] in fp32 with IEEE division.  mean255 / std255: HOST arrays of 3 floats
+ * (= float32(mean) * float32(1 / rescale_factor), as the reference fuses them).  Bit-identical to the reference.
+ * workspace: DEVICE, >= dp_preprocess_workspace_bytes(...) (returns -1 for an unsupported geometry). */
+long long dp_preprocess_workspace_bytes(int B, int H, int W, int short_edge, int crop);
+int dp_preprocess_u8(const void* images, int B, int H, int W, int short_edge, int crop, const float* mean255,
+                     const float* std255, float* out, void* workspace, long long workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,8 +51,27 @@ class Program:
     def add(self, name, fn, *args, keep=(), kernel=None, flops=0.0, bytes=0.0, launches=1):
         self.calls.append((fn, args, name))
         self.meta.append({"name": name, "kernel": kernel or name, "flops": float(flops), "bytes": float(bytes),
-                          "launches": launches})
+                          "launches": launches, "side": self._side})
         self.keep.extend(keep)
+
+    # ---- fork / join: launches recorded between ``fork()`` ... ``side(False)`` go to a second stream and run
+    # concurrently with what follows on the main stream until ``join()`` (small-grid chains such as the z-head MLP or
+    # the weight re-packing overlap the tensor-core kernels).  Program order stays a valid serial order: ``run_timed``
+    # and ``run_family`` simply ignore the fork.
+    _side = False
+
+    def fork(self):
+        self.calls.append((None, "fork", "stream"))
+        self.meta.append({"name": "fork", "kernel": "host:stream", "flops": 0.0, "bytes": 0.0})
+        self._side = True
+
+    def side(self, flag):
+        self._side = bool(flag)
+
+    def join(self):
+        self._side = False
+        self.calls.append((None, "join", "stream"))
+        self.meta.append({"name": "join", "kernel": "host:stream", "flops": 0.0, "bytes": 0.0})
 
     def add_callable(self, name, fn):
         """Host-side step (e.g. a torch op on static tensors) recorded in order with the launches."""
@@ -84,18 +103,33 @@ class Program:
         return n
 
     def run(self, on_mark=None):
-        stream = torch.cuda.current_stream().cuda_stream
-        for fn, args, name in self.calls:
+        main = torch.cuda.current_stream()
+        stream = main.cuda_stream
+        side = None
+        for (fn, args, name), meta in zip(self.calls, self.meta):
             if fn is None:
                 if name == "mark":
                     if on_mark is not None:
                         on_mark(args)
+                elif name == "stream":
+                    if self._side_stream is None or self._side_stream.device != main.device:
+                        self._side_stream = torch.cuda.Stream(device=main.device)
+                    if args == "fork":
+                        side = self._side_stream
+                        side.wait_stream(main)
+                    elif side is not None:
+                        main.wait_stream(side)
+                        side = None
                 else:
                     args()
                 continue
-            rc = fn(*args, stream)
+            rc = fn(*args, side.cuda_stream if (side is not None and meta.get("side")) else stream)
             if rc != 0:
                 _lib.check(rc, name)
+        if side is not None:     # a fork without a join: never leave work dangling on the second stream
+            main.wait_stream(side)
+
+    _side_stream = None
 
     def run_timed(self):
         """Replay with a CUDA event pair around every launch (on the launching stream); returns a list of
@@ -107,7 +141,7 @@ class Program:
         torch.cuda._sleep(int(30_000 * len(self.calls)))
         for (fn, args, name), meta in zip(self.calls, self.meta):
             if fn is None:
-                if name != "mark":
+                if name not in ("mark", "stream"):
                     args()
                 continue
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -356,6 +390,15 @@ class CudaBackend:
 
     def mark(self, tag):
         self.prog.add_mark(tag)
+
+    def fork(self):
+        self.prog.fork()
+
+    def side(self, flag):
+        self.prog.side(flag)
+
+    def join(self):
+        self.prog.join()
 
     def pack_weights(self, jobs):
         """jobs: list of (dst bf16 tensor, w fp32 [d0,d1,kh,kw] parameter, order, flips, dst_strides|None): dst (viewed in

@@ -79,14 +79,17 @@ __global__ void __launch_bounds__(256) col2im_kernel(const uint4* __restrict__ c
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = bias ? __ldg(bias + c * 8 + j) : 0.f;
-    for (int ky = 0; ky < KH; ++ky) {
+    // only the taps with (y + pad - ky) % stride == 0 contribute: start at ky0 = (y + pad) % stride and step by the
+    // stride (1-2 taps per axis for k4 s3) instead of testing all KH x KW taps with a division each
+    const int ky0 = (y + pad) % stride, kx0 = (x + pad) % stride;
+    for (int ky = ky0; ky < KH; ky += stride) {
       const int ty = y + pad - ky;
-      if (ty < 0 || ty % stride) continue;
+      if (ty < 0) break;
       const int sy = ty / stride;
       if (sy >= SH) continue;
-      for (int kx = 0; kx < KW; ++kx) {
+      for (int kx = kx0; kx < KW; kx += stride) {
         const int tx = x + pad - kx;
-        if (tx < 0 || tx % stride) continue;
+        if (tx < 0) break;
         const int sx = tx / stride;
         if (sx >= SW) continue;
         const uint4 t = __ldg(col + ((((long long)b * SH + sy) * SW + sx) * (KH * KW) + (ky * KW + kx)) * C8 + c);
@@ -112,13 +115,19 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const uint4* __restrict_
   const int c = threadIdx.x % C8;
   const int ppb = blockDim.x / C8;          // pixels per block iteration
   const int pl = threadIdx.x / C8;
+  // the filter [C, 9] goes through shared memory: read coalesced once per block (the per-thread gather of 72 taps at a
+  // 36-byte stride touched 32 sectors per load instruction and cost more than the pixel loop; with ~1200 short-lived
+  // blocks it was paid 8 times per SM -- the kernel ran at 60 us for 50 MB of traffic)
+  extern __shared__ float s_w[];
+  for (int i = threadIdx.x; i < C8 * 72; i += blockDim.x) s_w[i] = __ldg(w + i);
+  __syncthreads();
   if (pl >= ppb) return;
   float wt[9][8], bs[8];
 #pragma unroll
   for (int t = 0; t < 9; ++t) {
     const int tap = flip ? 8 - t : t;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) wt[t][j] = __ldg(w + (c * 8 + j) * 9 + tap);
+    for (int j = 0; j < 8; ++j) wt[t][j] = s_w[(c * 8 + j) * 9 + tap];
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) bs[j] = bias ? __ldg(bias + c * 8 + j) : 0.f;
@@ -150,6 +159,142 @@ __global__ void __launch_bounds__(256) dwconv3x3_kernel(const uint4* __restrict_
       for (int j = 0; j < 8; ++j) acc[j] += f[j];
     }
     store8(out + (p * C8 + c) * 8, acc);
+  }
+}
+
+// Tiled versions (C % 64 == 0): a block owns (image, slab of 64 channels, band of rows), stages the band + one halo row
+// above / below in shared memory with 16-byte loads and computes from there, so every input element is read from global
+// memory ONCE.  The untiled kernels above re-read each element 9 times from L2 (151 MB instead of 17 MB for the
+// hourglass layer) and ran at 50-70 us, 5-7x their HBM time (tools/op_bench.py).
+// thread = (channel group g = tid % 8, pixel lane = tid / 8); smem tile [rows + 2][W][8] uint4, conflict free.
+constexpr int kDwSlab = 8;   // channel groups (of 8 channels) per block
+template <typename OutT>
+__global__ void __launch_bounds__(256) dwconv3x3_tiled_kernel(const uint4* __restrict__ in, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, const uint4* __restrict__ add,
+                                                              OutT* __restrict__ out, int H, int W, int C8, int flip, int TH) {
+  pdl_grid_sync();
+  extern __shared__ uint4 s_tile[];                                   // [(TH + 2) * W * 8]
+  float* s_wt = reinterpret_cast<float*>(s_tile + (TH + 2) * W * kDwSlab);   // [64 * 9]
+  const int y0 = blockIdx.x * TH, slab = blockIdx.y, b = blockIdx.z;
+  const int rows = min(TH, H - y0);
+  const int g = threadIdx.x % kDwSlab, lane = threadIdx.x / kDwSlab;
+  const int cg = slab * kDwSlab + g;                                  // channel group of this thread
+  for (int i = threadIdx.x; i < kDwSlab * 72; i += 256) s_wt[i] = __ldg(w + slab * kDwSlab * 72 + i);
+  const uint4* src = in + (long long)b * H * W * C8;
+  for (int i = threadIdx.x; i < (rows + 2) * W * kDwSlab; i += 256) {
+    const int gg = i % kDwSlab, px = i / kDwSlab;
+    const int ty = px / W, x = px - ty * W;
+    const int y = y0 + ty - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H) v = __ldg(src + ((long long)y * W + x) * C8 + slab * kDwSlab + gg);
+    s_tile[i] = v;
+  }
+  __syncthreads();
+  float wt[9][8], bs[8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) {
+    const int tap = flip ? 8 - t : t;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) wt[t][j] = s_wt[(g * 8 + j) * 9 + tap];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) bs[j] = bias ? __ldg(bias + cg * 8 + j) : 0.f;
+  for (int px = lane; px < rows * W; px += 256 / kDwSlab) {
+    const int ty = px / W, x = px - ty * W;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bs[j];
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = x + kx - 1;
+        if (ix < 0 || ix >= W) continue;       // rows outside the image are zero in the tile
+        float f[8];
+        unpack8(s_tile[((ty + ky) * W + ix) * kDwSlab + g], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], wt[ky * 3 + kx][j], acc[j]);
+      }
+    const long long p = ((long long)b * H + y0 + ty) * W + x;
+    if (add != nullptr) {
+      float f[8];
+      unpack8(__ldg(add + p * C8 + cg), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    store8(out + (p * C8 + cg) * 8, acc);
+  }
+}
+
+// weight gradient, same tiling; 72 accumulators per thread, reduced over the 32 pixel lanes (shuffles inside a warp, shared
+// memory across the 8 warps), then one fp32 atomic per (channel, tap) and block.
+__global__ void __launch_bounds__(256) dwconv3x3_wgrad_tiled_kernel(const uint4* __restrict__ in, const uint4* __restrict__ dout,
+                                                                    float* __restrict__ dw, int H, int W, int C8, int TH) {
+  pdl_grid_sync();
+  extern __shared__ uint4 s_tile[];                                   // in: [(TH + 2) * W * 8], then dout: [TH * W * 8]
+  uint4* s_d = s_tile + (TH + 2) * W * kDwSlab;
+  const int y0 = blockIdx.x * TH, slab = blockIdx.y, b = blockIdx.z;
+  const int rows = min(TH, H - y0);
+  const int g = threadIdx.x % kDwSlab, lane = threadIdx.x / kDwSlab;
+  const uint4* src = in + (long long)b * H * W * C8;
+  const uint4* dsrc = dout + (long long)b * H * W * C8;
+  for (int i = threadIdx.x; i < (rows + 2) * W * kDwSlab; i += 256) {
+    const int gg = i % kDwSlab, px = i / kDwSlab;
+    const int ty = px / W, x = px - ty * W;
+    const int y = y0 + ty - 1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (y >= 0 && y < H) v = __ldg(src + ((long long)y * W + x) * C8 + slab * kDwSlab + gg);
+    s_tile[i] = v;
+  }
+  for (int i = threadIdx.x; i < rows * W * kDwSlab; i += 256) {
+    const int gg = i % kDwSlab, px = i / kDwSlab;
+    s_d[i] = __ldg(dsrc + ((long long)y0 * W + px) * C8 + slab * kDwSlab + gg);
+  }
+  __syncthreads();
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[t][j] = 0.f;
+  for (int px = lane; px < rows * W; px += 256 / kDwSlab) {
+    const int ty = px / W, x = px - ty * W;
+    float gd[8];
+    unpack8(s_d[px * kDwSlab + g], gd);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ix = x + kx - 1;
+        if (ix < 0 || ix >= W) continue;
+        float f[8];
+        unpack8(s_tile[((ty + ky) * W + ix) * kDwSlab + g], f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[ky * 3 + kx][j] = fmaf(gd[j], f[j], acc[ky * 3 + kx][j]);
+      }
+  }
+  // lanes of one group inside a warp differ in bits 3 and 4 of the thread index
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      acc[t][j] += __shfl_xor_sync(0xffffffffu, acc[t][j], 8);
+      acc[t][j] += __shfl_xor_sync(0xffffffffu, acc[t][j], 16);
+    }
+  __syncthreads();                                                    // the tiles are dead: reuse the memory
+  float* red = reinterpret_cast<float*>(s_tile);                      // [8 warps][8 groups][72]
+  const int wrp = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) < kDwSlab) {
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[(wrp * kDwSlab + g) * 72 + j * 9 + t] = acc[t][j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kDwSlab * 72; i += 256) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k * kDwSlab * 72 + i];
+    atomicAdd(dw + (long long)slab * kDwSlab * 72 + i, t);   // i = (g * 8 + j) * 9 + tap = the [C, 9] weight layout
   }
 }
 
@@ -726,42 +871,96 @@ __global__ void avgpool2_kernel(const float* __restrict__ in, float* __restrict_
 
 // heat-map gradient fp32 NCHW [NB,K,GH,GW] -> bf16 NHWC [NB*OH*OW, Kp] (zero padded channels);
 // up = 2 additionally applies the adjoint of avgpool2 (each fine pixel gets 0.25 * coarse gradient).
-__global__ void hm_grad_to_nhwc_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ out, int NB, int K, int Kp,
-                                       int OH, int OW, int up) {
+// A block transposes 128 consecutive pixels of one image through shared memory: NCHW reads are coalesced along the
+// pixels of each channel plane (4 loads in flight per lane), NHWC writes are 16-byte pieces of the padded channel rows.
+constexpr int kHmPix = 128;
+__global__ void __launch_bounds__(256) hm_grad_to_nhwc_kernel(const float* __restrict__ g, __nv_bfloat16* __restrict__ out,
+                                                              int NB, int K, int Kp, int OH, int OW, int up) {
   pdl_grid_sync();
-  const long long total = (long long)NB * OH * OW * Kp;
+  __shared__ float tile[64][kHmPix + 1];
   const int GH = OH / up, GW = OW / up;
   const float w = up == 2 ? 0.25f : 1.0f;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int k = int(i % Kp);
-    long long r = i / Kp;
-    const int x = int(r % OW); r /= OW;
-    const int y = int(r % OH);
-    const long long b = r / OH;
-    float v = 0.f;
-    if (k < K) v = w * __ldg(g + ((b * K + k) * GH + y / up) * GW + x / up);
-    out[i] = __float2bfloat16_rn(v);
+  const int hw = OH * OW;
+  const int chunks = (hw + kHmPix - 1) / kHmPix;
+  const int b = blockIdx.x / chunks, p0 = (blockIdx.x % chunks) * kHmPix;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  for (int k = wrp; k < Kp; k += 8) {
+    float v[kHmPix / 32];
+#pragma unroll
+    for (int i = 0; i < kHmPix / 32; ++i) {
+      const int pix = p0 + lane + 32 * i;
+      v[i] = 0.f;
+      if (k < K && pix < hw) {
+        const int y = pix / OW, x = pix - y * OW;
+        v[i] = w * __ldg(g + (((long long)b * K + k) * GH + y / up) * GW + x / up);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kHmPix / 32; ++i) tile[k][lane + 32 * i] = v[i];
+  }
+  __syncthreads();
+  const int kp8 = Kp / 8;   // Kp % 8 == 0 (checked by the launcher)
+  for (int i = threadIdx.x; i < kHmPix * kp8; i += 256) {
+    const int pl = i / kp8, k8 = i - pl * kp8;
+    if (p0 + pl < hw) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = tile[k8 * 8 + j][pl];
+      store8(out + ((long long)b * hw + p0 + pl) * Kp + k8 * 8, f);
+    }
   }
 }
 
-// mean over the N patch tokens: feat bf16 [B, N, D] -> fp32 [B, D]   (pose_heads.py:397)
-__global__ void mean_tokens_kernel(const __nv_bfloat16* __restrict__ feat, float* __restrict__ out, int N, int D) {
+// mean over the N patch tokens: feat bf16 [B, N, D] -> fp32 [B, D]   (pose_heads.py:397).  One block per image:
+// thread = (8-channel group, token lane), 16-byte loads, token lanes combined through shared memory.
+__global__ void __launch_bounds__(512) mean_tokens_kernel(const __nv_bfloat16* __restrict__ feat, float* __restrict__ out, int N, int D) {
   pdl_grid_sync();
-  const int b = blockIdx.y;
-  const int d = blockIdx.x * blockDim.x + threadIdx.x;
-  if (d >= D) return;
-  float s = 0.f;
-  for (int n = 0; n < N; ++n) s += __bfloat162float(feat[((long long)b * N + n) * D + d]);
-  out[(long long)b * D + d] = s / float(N);
+  extern __shared__ float s_part[];   // [lanes][D]
+  const int b = blockIdx.x;
+  const int C8 = D / 8;
+  const int lanes = blockDim.x / C8;
+  const int c = threadIdx.x % C8, l = threadIdx.x / C8;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (l < lanes) {
+    const uint4* src = reinterpret_cast<const uint4*>(feat + (long long)b * N * D) + c;
+    for (int n = l; n < N; n += lanes) {
+      float f[8];
+      unpack8(__ldg(src + (long long)n * C8), f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s_part[l * D + c * 8 + j] = acc[j];
+  }
+  __syncthreads();
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    float t = 0.f;
+    for (int k = 0; k < lanes; ++k) t += s_part[k * D + d];
+    out[(long long)b * D + d] = t / float(N);
+  }
 }
-// adjoint: dfeat[b, n, :] += dmean[b, :] / N   (bf16 in place)
-__global__ void mean_tokens_bwd_kernel(__nv_bfloat16* __restrict__ dfeat, const float* __restrict__ dmean, int N, int D,
-                                       long long total) {
+// adjoint: dfeat[b, n, :] += dmean[b, :] / N   (bf16 in place), 8 channels per thread
+__global__ void __launch_bounds__(256) mean_tokens_bwd_kernel(__nv_bfloat16* __restrict__ dfeat, const float* __restrict__ dmean,
+                                                              int N, int D, long long total) {
   pdl_grid_sync();
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int d = int(i % D);
-    const long long b = i / ((long long)N * D);
-    dfeat[i] = __float2bfloat16_rn(__bfloat162float(dfeat[i]) + __ldg(dmean + b * D + d) / float(N));
+  const int C8 = D / 8;
+  const long long total8 = total / 8;
+  const float inv = 1.f / float(N);
+  uint4* p = reinterpret_cast<uint4*>(dfeat);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % C8);
+    const long long b = i / ((long long)N * C8);
+    float f[8];
+    unpack8(p[i], f);
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(dmean + b * D + c * 8));
+    const float4 m1 = __ldg(reinterpret_cast<const float4*>(dmean + b * D + c * 8) + 1);
+    // same rounding as before: dmean / N (a division), added in fp32, one bf16 rounding
+    f[0] += m0.x / float(N); f[1] += m0.y / float(N); f[2] += m0.z / float(N); f[3] += m0.w / float(N);
+    f[4] += m1.x / float(N); f[5] += m1.y / float(N); f[6] += m1.z / float(N); f[7] += m1.w / float(N);
+    (void)inv;
+    p[i] = pack8(f);
   }
 }
 
@@ -927,16 +1126,32 @@ cudaError_t launch_dwconv3x3(const void* in, const float* w, const float* bias, 
                              int NB, int H, int W, int C, int flip, cudaStream_t s) {
   const int C8 = C / 8;
   if (C % 8 || C8 > 256) return cudaErrorInvalidValue;
+  if (C % 64 == 0 && W * 128 * 3 <= 44 * 1024) {   // tiled kernel: rows + 2 halo rows of W pixels x 128 bytes fit in 44 KB
+    int TH = (44 * 1024) / (W * 128) - 2;
+    if (TH > H) TH = H;
+    const size_t smem = size_t(TH + 2) * W * kDwSlab * sizeof(uint4) + kDwSlab * 72 * sizeof(float);
+    const dim3 grid((H + TH - 1) / TH, C8 / kDwSlab, NB);
+    if (out_f32)
+      launch_k<dwconv3x3_tiled_kernel<float>>(grid, 256, smem, s, reinterpret_cast<const uint4*>(in), w, bias,
+                                              reinterpret_cast<const uint4*>(add), reinterpret_cast<float*>(out), H, W, C8, flip, TH);
+    else
+      launch_k<dwconv3x3_tiled_kernel<__nv_bfloat16>>(grid, 256, smem, s, reinterpret_cast<const uint4*>(in), w, bias,
+                                                      reinterpret_cast<const uint4*>(add), reinterpret_cast<__nv_bfloat16*>(out),
+                                                      H, W, C8, flip, TH);
+    return cudaGetLastError();
+  }
   const int ppb = 256 / C8;
   const long long P = (long long)NB * H * W;
   long long g = (P + ppb - 1) / ppb;
-  if (g > 148 * 8) g = 148 * 8;
+  if (g > 148 * 2) g = 148 * 2;   // two resident blocks per SM (~110 registers per thread): one wave, the taps are loaded once
+  const size_t smem = size_t(C) * 9 * sizeof(float);   // <= 72 KB... C <= 2048 -> checked below
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
   if (out_f32)
-    launch_k<dwconv3x3_kernel<float>>(unsigned(g), 256, 0, s, reinterpret_cast<const uint4*>(in), w, bias,
+    launch_k<dwconv3x3_kernel<float>>(unsigned(g), 256, smem, s, reinterpret_cast<const uint4*>(in), w, bias,
                                                         reinterpret_cast<const uint4*>(add), reinterpret_cast<float*>(out),
                                                         NB, H, W, C8, flip);
   else
-    launch_k<dwconv3x3_kernel<__nv_bfloat16>>(unsigned(g), 256, 0, s, reinterpret_cast<const uint4*>(in), w, bias,
+    launch_k<dwconv3x3_kernel<__nv_bfloat16>>(unsigned(g), 256, smem, s, reinterpret_cast<const uint4*>(in), w, bias,
                                                                 reinterpret_cast<const uint4*>(add),
                                                                 reinterpret_cast<__nv_bfloat16*>(out), NB, H, W, C8, flip);
   return cudaGetLastError();
@@ -945,6 +1160,16 @@ cudaError_t launch_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, 
                                    cudaStream_t s) {
   const int C8 = C / 8;
   if (C % 8 || C8 > 256) return cudaErrorInvalidValue;
+  if (C % 64 == 0 && W * 128 * 4 <= 46 * 1024) {   // tiled kernel: (rows + 2) input rows + rows gradient rows in <= 46 KB
+    int TH = ((46 * 1024) / (W * 128) - 2) / 2;
+    if (TH > H) TH = H;
+    size_t smem = size_t(2 * TH + 2) * W * kDwSlab * sizeof(uint4);
+    if (smem < size_t(8) * kDwSlab * 72 * sizeof(float)) smem = size_t(8) * kDwSlab * 72 * sizeof(float);   // reduction scratch
+    const dim3 grid((H + TH - 1) / TH, C8 / kDwSlab, NB);
+    launch_k<dwconv3x3_wgrad_tiled_kernel>(grid, 256, smem, s, reinterpret_cast<const uint4*>(in), reinterpret_cast<const uint4*>(dout),
+                                           dw, H, W, C8, TH);
+    return cudaGetLastError();
+  }
   const int ppb = 256 / C8;
   const long long P = (long long)NB * H * W;
   long long g = (P + ppb - 1) / ppb;
@@ -1084,18 +1309,21 @@ cudaError_t launch_avgpool2(const float* in, float* out, long long planes, int O
 }
 cudaError_t launch_hm_grad_to_nhwc(const float* g, void* out, int NB, int K, int Kp, int OH, int OW, int up,
                                    cudaStream_t s) {
-  launch_k<hm_grad_to_nhwc_kernel>(grid_for((long long)NB * OH * OW * Kp, 256), 256, 0, s, 
-      g, reinterpret_cast<__nv_bfloat16*>(out), NB, K, Kp, OH, OW, up);
+  if (Kp > 64 || K > Kp || Kp % 8) return cudaErrorInvalidValue;
+  const int chunks = (OH * OW + kHmPix - 1) / kHmPix;
+  launch_k<hm_grad_to_nhwc_kernel>(unsigned(NB * chunks), 256, 0, s, g, reinterpret_cast<__nv_bfloat16*>(out), NB, K, Kp, OH, OW, up);
   return cudaGetLastError();
 }
 cudaError_t launch_mean_tokens(const void* feat, float* out, int B, int N, int D, cudaStream_t s) {
-  dim3 grid((D + 127) / 128, B);
-  launch_k<mean_tokens_kernel>(grid, 128, 0, s, reinterpret_cast<const __nv_bfloat16*>(feat), out, N, D);
+  if (D % 8 || D / 8 > 512) return cudaErrorInvalidValue;
+  const int lanes = 512 / (D / 8);
+  launch_k<mean_tokens_kernel>(B, 512, size_t(lanes) * D * sizeof(float), s, reinterpret_cast<const __nv_bfloat16*>(feat), out, N, D);
   return cudaGetLastError();
 }
 cudaError_t launch_mean_tokens_bwd(void* dfeat, const float* dmean, int B, int N, int D, cudaStream_t s) {
+  if (D % 8) return cudaErrorInvalidValue;
   const long long total = (long long)B * N * D;
-  launch_k<mean_tokens_bwd_kernel>(grid_for(total, 256), 256, 0, s, reinterpret_cast<__nv_bfloat16*>(dfeat), dmean, N, D, total);
+  launch_k<mean_tokens_bwd_kernel>(grid_for(total / 8, 256), 256, 0, s, reinterpret_cast<__nv_bfloat16*>(dfeat), dmean, N, D, total);
   return cudaGetLastError();
 }
 cudaError_t launch_sgemm_small(const float* A, long long sa_m, long long sa_k, const float* B, long long sb_k,

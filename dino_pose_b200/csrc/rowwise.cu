@@ -278,7 +278,7 @@ __device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32
 //   x_out = x_in + (y + v) * lambda1
 // y fp32 [rows, D] (output of the out-proj GEMM), A [D, r], Bm [r, D] fp32 (trainable, read directly).
 // One warp per row; A and B staged in shared memory.  Saves u (fp32 [rows, R]) for the backward.
-template <int R>
+template <int R, int NV>
 __global__ void __launch_bounds__(256) lora_fwd_kernel(const float* __restrict__ y, const float* __restrict__ A,
                                                        const float* __restrict__ Bm, const float* __restrict__ lambda1,
                                                        const float* __restrict__ x_in, float* __restrict__ x_out,
@@ -287,10 +287,10 @@ __global__ void __launch_bounds__(256) lora_fwd_kernel(const float* __restrict__
   pdl_grid_sync();
   const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
   extern __shared__ float sm[];
-  float* sA = sm;           // [D][R]
+  float* sAT = sm;          // [R][D]  (A transposed: a lane's float4 of columns is contiguous, conflict free)
   float* sB = sm + D * R;   // [R][D]
   for (int i = threadIdx.x; i < D * R; i += blockDim.x) {
-    sA[i] = A[i];
+    sAT[(i % R) * D + i / R] = A[i];
     sB[i] = Bm[i];
   }
   __syncthreads();
@@ -298,16 +298,33 @@ __global__ void __launch_bounds__(256) lora_fwd_kernel(const float* __restrict__
   const int wpb = blockDim.x >> 5;
   const uint32_t thresh = p_drop > 0.f ? uint32_t(fminf(p_drop, 0.999999f) * 4294967296.0f) : 0u;
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  // a lane owns the float4 column groups 4*lane + 128*i (D % 128 == 0, D <= 1024): every global access is a 16-byte
+  // load / store, and all of a row's loads (y and x_in) are issued before the first use -- with scalar loads and four
+  // of them in flight per lane the kernel ran at a third of the HBM rate
+  // NV = D / 128 is a template parameter: with run-time trip counts the compiler kept 8 float4 pairs per lane alive
+  // (139 registers, ONE resident block per SM, and 6 waves of blocks each re-staging A and B: 47 us for 76 MB)
+  constexpr int kMaxV = NV;
+  constexpr int nv = NV;
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+    float4 yv[kMaxV], xv[kMaxV];
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i)
+      if (i < nv) {
+        yv[i] = __ldg(reinterpret_cast<const float4*>(y + row * D) + lane + 32 * i);
+        xv[i] = __ldg(reinterpret_cast<const float4*>(x_in + row * D) + lane + 32 * i);
+      }
     float u[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) u[r] = 0.f;
-#pragma unroll 4
-    for (int d = lane; d < D; d += 32) {
-      const float yv = __ldg(y + row * D + d);
 #pragma unroll
-      for (int r = 0; r < R; ++r) u[r] += yv * sA[d * R + r];
-    }
+    for (int i = 0; i < kMaxV; ++i)
+      if (i < nv) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 a = *reinterpret_cast<const float4*>(sAT + r * D + 4 * lane + 128 * i);
+          u[r] = fmaf(yv[i].x, a.x, fmaf(yv[i].y, a.y, fmaf(yv[i].z, a.z, fmaf(yv[i].w, a.w, u[r]))));
+        }
+      }
 #pragma unroll
     for (int r = 0; r < R; ++r) u[r] = warp_sum(u[r]);
     if (u_save != nullptr && lane < R) {
@@ -316,15 +333,28 @@ __global__ void __launch_bounds__(256) lora_fwd_kernel(const float* __restrict__
       for (int r = 0; r < R; ++r) mine = (lane == r) ? u[r] : mine;
       u_save[row * R + lane] = mine;
     }
-#pragma unroll 4
-    for (int d = lane; d < D; d += 32) {
-      float v = 0.f;
 #pragma unroll
-      for (int r = 0; r < R; ++r) v += u[r] * sB[r * D + d];
-      if (p_drop > 0.f) v = dropout_keep(seed, uint64_t(row) * D + d, thresh) ? v * keep_scale : 0.f;
-      const float yv = y[row * D + d];
-      x_out[row * D + d] = x_in[row * D + d] + (yv + v * scaling) * lambda1[d];
-    }
+    for (int i = 0; i < kMaxV; ++i)
+      if (i < nv) {
+        const int d = 4 * lane + 128 * i;
+        float v[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 b = *reinterpret_cast<const float4*>(sB + r * D + d);
+          v[0] = fmaf(u[r], b.x, v[0]); v[1] = fmaf(u[r], b.y, v[1]); v[2] = fmaf(u[r], b.z, v[2]); v[3] = fmaf(u[r], b.w, v[3]);
+        }
+        if (p_drop > 0.f) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = dropout_keep(seed, uint64_t(row) * D + d + k, thresh) ? v[k] * keep_scale : 0.f;
+        }
+        const float4 l = __ldg(reinterpret_cast<const float4*>(lambda1 + d));
+        float4 o;
+        o.x = xv[i].x + (yv[i].x + v[0] * scaling) * l.x;
+        o.y = xv[i].y + (yv[i].y + v[1] * scaling) * l.y;
+        o.z = xv[i].z + (yv[i].z + v[2] * scaling) * l.z;
+        o.w = xv[i].w + (yv[i].w + v[3] * scaling) * l.w;
+        *(reinterpret_cast<float4*>(x_out + row * D) + lane + 32 * i) = o;
+      }
   }
 }
 
@@ -334,7 +364,7 @@ __global__ void __launch_bounds__(256) lora_fwd_kernel(const float* __restrict__
 //   dB[r, d]  += sum_rows u[row, r] * gv[row, d]                 (kernel 2, thread per column d)
 //   dA[d, r]  += sum_rows y[row, d] * gu[row, r]
 // (no gradient flows further: y is produced by frozen parameters from a frozen input.)
-template <int R>
+template <int R, int NV>
 __global__ void __launch_bounds__(256) lora_bwd_gu_kernel(const float* __restrict__ g, const float* __restrict__ Bm,
                                                           const float* __restrict__ lambda1, float* __restrict__ gu_out,
                                                           long long rows, int D, float scaling, float p_drop,
@@ -349,17 +379,32 @@ __global__ void __launch_bounds__(256) lora_bwd_gu_kernel(const float* __restric
   const int wpb = blockDim.x >> 5;
   const uint32_t thresh = p_drop > 0.f ? uint32_t(fminf(p_drop, 0.999999f) * 4294967296.0f) : 0u;
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
+  constexpr int kMaxV = NV;     // float4 column groups per lane (D = 128 * NV), all loads of a row in flight
+  constexpr int nv = NV;
   for (long long row = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * wpb) {
+    float4 gv4[kMaxV];
+#pragma unroll
+    for (int i = 0; i < kMaxV; ++i)
+      if (i < nv) gv4[i] = __ldg(reinterpret_cast<const float4*>(g + row * D) + lane + 32 * i);
     float gu[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) gu[r] = 0.f;
-#pragma unroll 4
-    for (int d = lane; d < D; d += 32) {
-      float gv = __ldg(g + row * D + d) * __ldg(lambda1 + d) * scaling;
-      if (p_drop > 0.f) gv = dropout_keep(seed, uint64_t(row) * D + d, thresh) ? gv * keep_scale : 0.f;
 #pragma unroll
-      for (int r = 0; r < R; ++r) gu[r] += gv * sB[r * D + d];
-    }
+    for (int i = 0; i < kMaxV; ++i)
+      if (i < nv) {
+        const int d = 4 * lane + 128 * i;
+        const float4 l = __ldg(reinterpret_cast<const float4*>(lambda1 + d));
+        float gv[4] = {gv4[i].x * l.x * scaling, gv4[i].y * l.y * scaling, gv4[i].z * l.z * scaling, gv4[i].w * l.w * scaling};
+        if (p_drop > 0.f) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) gv[k] = dropout_keep(seed, uint64_t(row) * D + d + k, thresh) ? gv[k] * keep_scale : 0.f;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float4 b = *reinterpret_cast<const float4*>(sB + r * D + d);
+          gu[r] = fmaf(gv[0], b.x, fmaf(gv[1], b.y, fmaf(gv[2], b.z, fmaf(gv[3], b.w, gu[r]))));
+        }
+      }
 #pragma unroll
     for (int r = 0; r < R; ++r) gu[r] = warp_sum(gu[r]);
     if (lane < R) {
@@ -371,101 +416,169 @@ __global__ void __launch_bounds__(256) lora_bwd_gu_kernel(const float* __restric
   }
 }
 
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+// A thread owns FOUR columns (one float4 of g and y per row) and walks over rows eight at a time: 16 loads of 16 bytes in
+// flight per thread.  blockDim.x = (D / 4) * row_lanes: the row lanes split the block's rows (the D / 4 = 96 threads of
+// ViT-S alone are 6 warps per SM -- issue bound) and are combined through shared memory before the atomics.
 template <int R>
-__global__ void __launch_bounds__(256) lora_bwd_acc_kernel(const float* __restrict__ g, const float* __restrict__ y,
+__global__ void __launch_bounds__(384) lora_bwd_acc_kernel(const float* __restrict__ g, const float* __restrict__ y,
                                                            const float* __restrict__ u_saved, const float* __restrict__ gu,
                                                            const float* __restrict__ lambda1, float* __restrict__ dA,
                                                            float* __restrict__ dB, long long rows, int D, float scaling,
                                                            float p_drop, const unsigned long long* __restrict__ seed_ptr,
-                                                           int rows_per_block) {
+                                                           int rows_per_block, int row_lanes) {
   pdl_grid_sync();
+  extern __shared__ float s_red[];   // [row_lanes - 1][D / 4][8 * R]
   const unsigned long long seed = seed_ptr ? *seed_ptr : 0ull;
-  const int d = blockIdx.y * blockDim.x + threadIdx.x;
-  if (d >= D) return;
+  const int cols = D >> 2;
+  const int ct = threadIdx.x % cols, rl = threadIdx.x / cols;
+  const int d = 4 * ct;
   const uint32_t thresh = p_drop > 0.f ? uint32_t(fminf(p_drop, 0.999999f) * 4294967296.0f) : 0u;
   const float keep_scale = p_drop > 0.f ? 1.0f / (1.0f - p_drop) : 1.0f;
-  const float ld = lambda1[d] * scaling;
+  const float4 l4 = __ldg(reinterpret_cast<const float4*>(lambda1 + d));
+  const float ld[4] = {l4.x * scaling, l4.y * scaling, l4.z * scaling, l4.w * scaling};
   const long long r0 = (long long)blockIdx.x * rows_per_block;
   const long long r1 = min(r0 + rows_per_block, rows);
-  float aB[R], aA[R];
+  float aB[R][4], aA[4][R];
 #pragma unroll
-  for (int r = 0; r < R; ++r) aB[r] = aA[r] = 0.f;
-  // 4 rows per iteration: the g / y loads of all four rows are in flight together (the loop is latency bound otherwise)
-  for (long long row = r0; row < r1; row += 4) {
-    float gv[4], yv[4];
+  for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long rr = row + k < r1 ? row + k : r1 - 1;
-      gv[k] = __ldg(g + rr * D + d);
-      yv[k] = __ldg(y + rr * D + d);
+    for (int k = 0; k < 4; ++k) aB[r][k] = aA[k][r] = 0.f;
+  constexpr int kRows = 8;
+  for (long long base = r0 + rl; base < r1; base += (long long)kRows * row_lanes) {
+    float4 gv[kRows], yv[kRows];
+#pragma unroll
+    for (int k = 0; k < kRows; ++k) {
+      long long rr = base + (long long)k * row_lanes;
+      if (rr >= r1) rr = base;
+      gv[k] = __ldg(reinterpret_cast<const float4*>(g + rr * D + d));
+      yv[k] = __ldg(reinterpret_cast<const float4*>(y + rr * D + d));
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (row + k >= r1) break;
-      float gk = gv[k] * ld;
-      if (p_drop > 0.f) gk = dropout_keep(seed, uint64_t(row + k) * D + d, thresh) ? gk * keep_scale : 0.f;
-      const float4* up = reinterpret_cast<const float4*>(u_saved + (row + k) * R);
-      const float4* gp = reinterpret_cast<const float4*>(gu + (row + k) * R);
+    for (int k = 0; k < kRows; ++k) {
+      const long long row = base + (long long)k * row_lanes;
+      if (row >= r1) break;
+      float gk[4] = {gv[k].x * ld[0], gv[k].y * ld[1], gv[k].z * ld[2], gv[k].w * ld[3]};
+      if (p_drop > 0.f) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) gk[c] = dropout_keep(seed, uint64_t(row) * D + d + c, thresh) ? gk[c] * keep_scale : 0.f;
+      }
+      const float yk[4] = {yv[k].x, yv[k].y, yv[k].z, yv[k].w};
+      const float4* up = reinterpret_cast<const float4*>(u_saved + row * R);   // same address in every thread of a lane: broadcast
+      const float4* gp = reinterpret_cast<const float4*>(gu + row * R);
 #pragma unroll
       for (int r4 = 0; r4 < R / 4; ++r4) {
         const float4 uu = __ldg(up + r4), gg = __ldg(gp + r4);
-        aB[4 * r4 + 0] += uu.x * gk; aB[4 * r4 + 1] += uu.y * gk; aB[4 * r4 + 2] += uu.z * gk; aB[4 * r4 + 3] += uu.w * gk;
-        aA[4 * r4 + 0] += yv[k] * gg.x; aA[4 * r4 + 1] += yv[k] * gg.y; aA[4 * r4 + 2] += yv[k] * gg.z; aA[4 * r4 + 3] += yv[k] * gg.w;
+        const float uv[4] = {uu.x, uu.y, uu.z, uu.w}, gq[4] = {gg.x, gg.y, gg.z, gg.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            aB[4 * r4 + q][c] = fmaf(uv[q], gk[c], aB[4 * r4 + q][c]);
+            aA[c][4 * r4 + q] = fmaf(yk[c], gq[q], aA[c][4 * r4 + q]);
+          }
       }
     }
   }
+  if (rl > 0) {
+    float* dst = s_red + ((long long)(rl - 1) * cols + ct) * (8 * R);
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    atomicAdd(dB + (long long)r * D + d, aB[r]);
-    atomicAdd(dA + (long long)d * R + r, aA[r]);
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        dst[r * 4 + c] = aB[r][c];
+        dst[4 * R + c * R + r] = aA[c][r];
+      }
+  }
+  __syncthreads();
+  if (rl == 0) {
+    for (int l = 1; l < row_lanes; ++l) {
+      const float* src = s_red + ((long long)(l - 1) * cols + ct) * (8 * R);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          aB[r][c] += src[r * 4 + c];
+          aA[c][r] += src[4 * R + c * R + r];
+        }
+    }
+    // 16-byte vector reductions (red.global.add.v4.f32): a quarter of the atomic operations -- with ~300 blocks adding
+    // into the same 2*D*R addresses the L2 atomic rate, not the 50 MB of loads, bounded this kernel
+#pragma unroll
+    for (int r = 0; r < R; ++r) red_add_v4(dB + (long long)r * D + d, aB[r][0], aB[r][1], aB[r][2], aB[r][3]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+      for (int r4 = 0; r4 < R / 4; ++r4)
+        red_add_v4(dA + (long long)(d + c) * R + 4 * r4, aA[c][4 * r4], aA[c][4 * r4 + 1], aA[c][4 * r4 + 2], aA[c][4 * r4 + 3]);
   }
 }
 
+template <int R, int NV>
+static cudaError_t lora_fwd_t(const float* y, const float* A, const float* Bm, const float* lambda1, const float* x_in,
+                              float* x_out, float* u_save, long long rows, int D, float scaling, float p_drop,
+                              const unsigned long long* seed, int sms, cudaStream_t s) {
+  const size_t smem = size_t(2) * D * R * sizeof(float);
+  cudaFuncSetAttribute(lora_fwd_kernel<R, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  // persistent blocks (3 per SM fit by registers and shared memory): A and B are staged once per block
+  launch_k<lora_fwd_kernel<R, NV>>(sms * 3, 256, smem, s, y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed);
+  return cudaGetLastError();
+}
+#define DP_LORA_DISPATCH(FN, ...)                                                     \
+  switch (R * 16 + D / 128) {                                                         \
+    case 4 * 16 + 1: return FN<4, 1>(__VA_ARGS__);                                    \
+    case 4 * 16 + 3: return FN<4, 3>(__VA_ARGS__);                                    \
+    case 4 * 16 + 6: return FN<4, 6>(__VA_ARGS__);                                    \
+    case 4 * 16 + 8: return FN<4, 8>(__VA_ARGS__);                                    \
+    case 8 * 16 + 1: return FN<8, 1>(__VA_ARGS__);                                    \
+    case 8 * 16 + 3: return FN<8, 3>(__VA_ARGS__);                                    \
+    case 8 * 16 + 6: return FN<8, 6>(__VA_ARGS__);                                    \
+    case 8 * 16 + 8: return FN<8, 8>(__VA_ARGS__);                                    \
+    case 16 * 16 + 1: return FN<16, 1>(__VA_ARGS__);                                  \
+    case 16 * 16 + 3: return FN<16, 3>(__VA_ARGS__);                                  \
+    case 16 * 16 + 6: return FN<16, 6>(__VA_ARGS__);                                  \
+    case 16 * 16 + 8: return FN<16, 8>(__VA_ARGS__);                                  \
+    default: return cudaErrorInvalidValue;                                            \
+  }
 cudaError_t launch_lora_fwd(const float* y, const float* A, const float* Bm, const float* lambda1, const float* x_in,
                             float* x_out, float* u_save, long long rows, int D, int R, float scaling, float p_drop,
                             const unsigned long long* seed, int sms, cudaStream_t s) {
-  const size_t smem = size_t(2) * D * R * sizeof(float);
-  const int grid = sms * 6;
-  if (R == 8) {
-    cudaFuncSetAttribute(lora_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    launch_k<lora_fwd_kernel<8>>(grid, 256, smem, s, y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed);
-  } else if (R == 4) {
-    cudaFuncSetAttribute(lora_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    launch_k<lora_fwd_kernel<4>>(grid, 256, smem, s, y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed);
-  } else if (R == 16) {
-    cudaFuncSetAttribute(lora_fwd_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-    launch_k<lora_fwd_kernel<16>>(grid, 256, smem, s, y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed);
-  } else {
-    return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
+  // float4 column groups per lane: D = 128 * {1, 3, 6, 8} (test / ViT-S / ViT-B / ViT-L), rank 4 / 8 / 16
+  if (D % 128) return cudaErrorInvalidValue;
+  DP_LORA_DISPATCH(lora_fwd_t, y, A, Bm, lambda1, x_in, x_out, u_save, rows, D, scaling, p_drop, seed, sms, s)
 }
 
-template <int R>
+template <int R, int NV>
 static cudaError_t lora_bwd_t(const float* g, const float* y, const float* u_saved, const float* Bm, const float* lambda1,
                               float* dA, float* dB, float* gu_ws, long long rows, int D, float scaling, float p_drop,
                               const unsigned long long* seed, int sms, cudaStream_t s) {
   const size_t smem = size_t(D) * R * sizeof(float);
-  cudaFuncSetAttribute(lora_bwd_gu_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
-  launch_k<lora_bwd_gu_kernel<R>>(sms * 6, 256, smem, s, g, Bm, lambda1, gu_ws, rows, D, scaling, p_drop, seed);
-  const int bx = 128;
-  const int gy = (D + bx - 1) / bx;
-  int gx = (sms * 4) / gy;   // more blocks = more same-address atomics on the 2*D*R outputs (measured slower)
-  if (gx < 1) gx = 1;
+  cudaFuncSetAttribute(lora_bwd_gu_kernel<R, NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+  launch_k<lora_bwd_gu_kernel<R, NV>>(sms * 3, 256, smem, s, g, Bm, lambda1, gu_ws, rows, D, scaling, p_drop, seed);
+  if (D % 128 || D > 1024) return cudaErrorInvalidValue;
+  const int cols = D / 4;          // one thread per float4 column group ...
+  int lanes = 384 / cols;          // ... times up to 4 row lanes (ViT-S: 4, ViT-B: 2, ViT-L: 1)
+  if (lanes < 1) lanes = 1;
+  if (lanes > 4) lanes = 4;
+  if (R == 16) lanes = 1;          // 250 registers per thread
+  int gx = sms * 2;                // more blocks = more same-address atomics on the 2*D*R outputs (measured slower)
   int rpb = int((rows + gx - 1) / gx);
   if (rpb < 16) rpb = 16;
   gx = int((rows + rpb - 1) / rpb);
-  launch_k<lora_bwd_acc_kernel<R>>(dim3(gx, gy), bx, 0, s, g, y, u_saved, gu_ws, lambda1, dA, dB, rows, D, scaling, p_drop, seed, rpb);
+  const size_t red = size_t(lanes - 1) * cols * 8 * R * sizeof(float);
+  cudaFuncSetAttribute(lora_bwd_acc_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+  launch_k<lora_bwd_acc_kernel<R>>(gx, cols * lanes, red, s, g, y, u_saved, gu_ws, lambda1, dA, dB, rows, D, scaling, p_drop, seed,
+                                   rpb, lanes);
   return cudaGetLastError();
 }
 
 cudaError_t launch_lora_bwd(const float* g, const float* y, const float* u_saved, const float* Bm, const float* lambda1,
                             float* dA, float* dB, float* gu_ws, long long rows, int D, int R, float scaling, float p_drop,
                             const unsigned long long* seed, int sms, cudaStream_t s) {
-  if (R == 8) return lora_bwd_t<8>(g, y, u_saved, Bm, lambda1, dA, dB, gu_ws, rows, D, scaling, p_drop, seed, sms, s);
-  if (R == 4) return lora_bwd_t<4>(g, y, u_saved, Bm, lambda1, dA, dB, gu_ws, rows, D, scaling, p_drop, seed, sms, s);
-  if (R == 16) return lora_bwd_t<16>(g, y, u_saved, Bm, lambda1, dA, dB, gu_ws, rows, D, scaling, p_drop, seed, sms, s);
-  return cudaErrorInvalidValue;
+  if (D % 128) return cudaErrorInvalidValue;
+  DP_LORA_DISPATCH(lora_bwd_t, g, y, u_saved, Bm, lambda1, dA, dB, gu_ws, rows, D, scaling, p_drop, seed, sms, s)
 }
 
 }  // namespace dp

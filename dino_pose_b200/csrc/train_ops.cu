@@ -186,23 +186,30 @@ cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long
 // and BatchNorm's num_batches_tracked counters (14 separate int64 buffers) are bumped by one launch too.
 namespace dp {
 namespace {
+constexpr int kPackChunk = 2048;   // consecutive destination elements per block
 __global__ void __launch_bounds__(256) pack_weights_kernel(const long long* __restrict__ jobs) {
   pdl_grid_sync();
   const long long* j = jobs + (long long)blockIdx.y * 16;
-  const float* src = reinterpret_cast<const float*>(j[0]);
+  const unsigned total = unsigned(j[15]);
+  const unsigned first = blockIdx.x * unsigned(kPackChunk);
+  if (first >= total) return;   // the grid is sized for the largest job
+  const float* src = reinterpret_cast<const float*>(j[0]) + j[14];
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(j[1]);
-  const long long n1 = j[3], n2 = j[4], n3 = j[5];
-  const long long s0 = j[6], s1 = j[7], s2 = j[8], s3 = j[9];
-  const long long t0 = j[10], t1 = j[11], t2 = j[12], t3 = j[13];
-  const long long off = j[14], total = j[15];
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const long long c3 = i % n3;
-    long long r = i / n3;
-    const long long c2 = r % n2;
+  // every tensor has < 2^31 elements (checked by the launcher): 32-bit index arithmetic, signed source strides
+  const unsigned n1 = unsigned(j[3]), n2 = unsigned(j[4]), n3 = unsigned(j[5]);
+  const int s0 = int(j[6]), s1 = int(j[7]), s2 = int(j[8]), s3 = int(j[9]);
+  const unsigned t0 = unsigned(j[10]), t1 = unsigned(j[11]), t2 = unsigned(j[12]), t3 = unsigned(j[13]);
+  const unsigned last = min(total, first + unsigned(kPackChunk));
+  // a block covers a contiguous destination range: its strided source reads stay inside a few KB that L1 keeps
+  for (unsigned i = first + threadIdx.x; i < last; i += 256) {
+    const unsigned c3 = i % n3;
+    unsigned r = i / n3;
+    const unsigned c2 = r % n2;
     r /= n2;
-    const long long c1 = r % n1;
-    const long long c0 = r / n1;
-    dst[c0 * t0 + c1 * t1 + c2 * t2 + c3 * t3] = __float2bfloat16_rn(__ldg(src + off + c0 * s0 + c1 * s1 + c2 * s2 + c3 * s3));
+    const unsigned c1 = r % n1;
+    const unsigned c0 = r / n1;
+    const long long so = (long long)int(c0) * s0 + (long long)int(c1) * s1 + (long long)int(c2) * s2 + (long long)int(c3) * s3;
+    dst[c0 * t0 + c1 * t1 + c2 * t2 + c3 * t3] = __float2bfloat16_rn(__ldg(src + so));
   }
 }
 __global__ void add_i64_kernel(const long long* __restrict__ ptrs, int n, long long inc) {
@@ -213,8 +220,8 @@ __global__ void add_i64_kernel(const long long* __restrict__ ptrs, int n, long l
 }  // namespace
 
 cudaError_t launch_pack_weights(const long long* jobs_dev, int njobs, long long max_total, int sms, cudaStream_t s) {
-  long long gx = (max_total + 255) / 256;
-  if (gx > 64) gx = 64;     // jobs run side by side: njobs x 64 blocks fill the GPU
+  if (max_total >= (1LL << 31)) return cudaErrorInvalidValue;
+  long long gx = (max_total + kPackChunk - 1) / kPackChunk;   // blocks beyond a job's size return immediately
   if (gx < 1) gx = 1;
   (void)sms;
   launch_k<pack_weights_kernel>(dim3(unsigned(gx), unsigned(njobs)), 256, 0, s, jobs_dev);

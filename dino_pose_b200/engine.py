@@ -327,6 +327,12 @@ class PoseEngine:
 
         # ---------------- forward program
         prog_f = be.begin()
+        # the bf16 re-packing of the trainable head weights only has to be done before the first head convolution: it
+        # runs on the second stream underneath the backbone (gather-bound, ~50 us, a fraction of the SMs)
+        plan["layers"] = self.build_head_layers(g)
+        be.fork()
+        self.record_pack_heads(plan)
+        be.side(False)
         be.patch_im2col(t["px"], t["acol"], B=B, H=H, W=W, Kp=PATCH_KP)
         be.fill_cls(t["x"], pos[0], B=B, T=T, D=D)
         be.gemm(t["acol"], fz["wpe"], t["x"], M=B * N, N=D, K=PATCH_KP, out_dtype="f32", residual=pos,
@@ -504,8 +510,8 @@ class PoseEngine:
         be = self.be
         B, g, training = plan["B"], plan["g"], plan["training"]
         t = plan["t"]
-        Ls = plan["layers"] = self.build_head_layers(g)
-        self.record_pack_heads(plan)
+        Ls = plan["layers"]
+        be.join()                # packed head weights (second stream, forked at the start of the program)
         for L in Ls.values():
             if L.bn is not None:
                 self._bn_tensors(L)
@@ -514,6 +520,30 @@ class PoseEngine:
                     be.bn_fold_eval(self.p(bn + ".weight"), self.p(bn + ".bias"), self.p(bn + ".running_mean"),
                                     self.p(bn + ".running_var"), self.p(L.name + ".bias"), L.t["scale"], L.t["shift"],
                                     C=L.cout)
+        K = self.K
+        # The z head (5 small launches on a [B, D] matrix) only needs the final LayerNorm output: it runs on the second
+        # stream underneath the heat-map head and is joined at the end of the program.
+        be.fork()
+        # z head: mean over patch tokens -> MLP (pose_heads.py:397-398, :148-159)
+        zh = self.cfg["z_hidden"]
+        dims = [self.D] + list(zh) + [K]
+        t["zin"] = self.new((B, self.D), F32)
+        be.mean_tokens(t["feat"], t["zin"], B=B, N=plan["N"], D=self.D)
+        zp = "pose_heads.z_head.mlp."
+        cur = t["zin"]
+        p_drop = float(self.cfg.get("z_dropout", 0.0)) if training else 0.0
+        t["zact"] = [cur]
+        for j in range(len(dims) - 1):
+            lastl = j == len(dims) - 2
+            out = self.new((B, dims[j + 1]), F32)
+            be.sgemm_small(cur, dims[j], 1, self.p(zp + f"{3 * j}.weight"), 1, dims[j], out, dims[j + 1], M=B,
+                           N=dims[j + 1], K=dims[j], bias=self.p(zp + f"{3 * j}.bias"), relu=not lastl,
+                           p_drop=0.0 if lastl else p_drop, seed=self.seed if (p_drop > 0 and not lastl) else None)
+            cur = out
+            t["zact"].append(cur)
+        t["z"] = cur
+        plan["zdims"] = dims
+        be.side(False)
         feat4 = t["feat"].view(B, g, g, self.D)
         a = plan["a"] = {}    # activations (bf16 [P, C])
         r = plan["raw"] = {}  # pre-BN conv outputs (training only)
@@ -582,25 +612,7 @@ class PoseEngine:
         else:
             raise NotImplementedError(f"heat-map resize {s48} -> {self.hm_size} (only 1x and 2x reductions occur "
                                       "for 224^2 / 448^2 inputs)")
-        # z head: mean over patch tokens -> MLP (pose_heads.py:397-398, :148-159)
-        zh = self.cfg["z_hidden"]
-        dims = [self.D] + list(zh) + [K]
-        t["zin"] = self.new((B, self.D), F32)
-        be.mean_tokens(t["feat"], t["zin"], B=B, N=plan["N"], D=self.D)
-        zp = "pose_heads.z_head.mlp."
-        cur = t["zin"]
-        p_drop = float(self.cfg.get("z_dropout", 0.0)) if training else 0.0
-        t["zact"] = [cur]
-        for j in range(len(dims) - 1):
-            lastl = j == len(dims) - 2
-            out = self.new((B, dims[j + 1]), F32)
-            be.sgemm_small(cur, dims[j], 1, self.p(zp + f"{3 * j}.weight"), 1, dims[j], out, dims[j + 1], M=B,
-                           N=dims[j + 1], K=dims[j], bias=self.p(zp + f"{3 * j}.bias"), relu=not lastl,
-                           p_drop=0.0 if lastl else p_drop, seed=self.seed if (p_drop > 0 and not lastl) else None)
-            cur = out
-            t["zact"].append(cur)
-        t["z"] = cur
-        plan["zdims"] = dims
+        be.join()                # z head (second stream)
         if training:
             # torch BatchNorm bookkeeping (momentum is fixed, the value is unused): one launch for the 14 counters
             counters = [self.Bufs[L.bn + ".num_batches_tracked"] for L in Ls.values() if L.bn is not None]
@@ -630,6 +642,28 @@ class PoseEngine:
         be.host("zero_grads", flat.zero_)
         s47, s48 = Ls["ups0"].oh, Ls["ups1"].oh
         P48 = B * s48 * s48
+        # the z-head backward (12 small launches, M = batch) depends only on dz: second stream, under the heat-map head
+        be.fork()
+        dims = plan["zdims"]
+        zp = "pose_heads.z_head.mlp."
+        p_drop = float(self.cfg.get("z_dropout", 0.0))
+        dcur = t["dz"]
+        nl = len(dims) - 1
+        for j in reversed(range(nl)):
+            xin, yout = t["zact"][j], t["zact"][j + 1]
+            if j < nl - 1:
+                # through dropout + relu of layer j: mask by the saved (post-dropout) activation
+                dm = self.new((B, dims[j + 1]), F32)
+                be.relu_mask(dcur, yout, dm, n=B * dims[j + 1], keep_scale=1.0 / (1.0 - p_drop) if p_drop > 0 else 1.0)
+                dcur = dm
+            be.sgemm_small(dcur, 1, dims[j + 1], xin, dims[j], 1, G[zp + f"{3 * j}.weight"], dims[j], M=dims[j + 1],
+                           N=dims[j], K=B)
+            be.colsum(dcur, G[zp + f"{3 * j}.bias"], P=B, C=dims[j + 1], ld=dims[j + 1])
+            dx = self.new((B, dims[j]), F32)
+            be.sgemm_small(dcur, dims[j + 1], 1, self.p(zp + f"{3 * j}.weight"), dims[j], 1, dx, dims[j], M=B, N=dims[j],
+                           K=dims[j + 1])
+            dcur = dx
+        be.side(False)
 
         def bn_bwd(key, dact, add1=None, mode=0, dres=None, shuffle=False):
             L = Ls[key]
@@ -750,26 +784,7 @@ class PoseEngine:
         d_a1c = conv_bwd("skip", bn_bwd("skip", d_hg), a["fr0"], dx_residual=d_a1b)
         dfeat = conv_bwd("fr0", bn_bwd("fr0", d_a1c), t["feat"].view(B, g, g, D))
         done("fr0")
-        # ---- z head
-        dims = plan["zdims"]
-        zp = "pose_heads.z_head.mlp."
-        p_drop = float(self.cfg.get("z_dropout", 0.0))
-        dcur = t["dz"]
-        nl = len(dims) - 1
-        for j in reversed(range(nl)):
-            xin, yout = t["zact"][j], t["zact"][j + 1]
-            if j < nl - 1:
-                # through dropout + relu of layer j: mask by the saved (post-dropout) activation
-                dm = self.new((B, dims[j + 1]), F32)
-                be.relu_mask(dcur, yout, dm, n=B * dims[j + 1], keep_scale=1.0 / (1.0 - p_drop) if p_drop > 0 else 1.0)
-                dcur = dm
-            be.sgemm_small(dcur, 1, dims[j + 1], xin, dims[j], 1, G[zp + f"{3 * j}.weight"], dims[j], M=dims[j + 1],
-                           N=dims[j], K=B)
-            be.colsum(dcur, G[zp + f"{3 * j}.bias"], P=B, C=dims[j + 1], ld=dims[j + 1])
-            dx = self.new((B, dims[j]), F32)
-            be.sgemm_small(dcur, dims[j + 1], 1, self.p(zp + f"{3 * j}.weight"), dims[j], 1, dx, dims[j], M=B, N=dims[j],
-                           K=dims[j + 1])
-            dcur = dx
+        be.join()                # z-head chain (second stream): its input gradient dcur is needed now
         be.mean_tokens_bwd(dfeat, dcur, B=B, N=N, D=D)
         done("z_head")
         if not self.lora:

@@ -43,6 +43,15 @@ class TorchEmulator:
     def host(self, name, fn):
         self.prog.calls.append(fn)
 
+    def fork(self):          # stream fork / join of the CUDA backend: the emulator runs everything in program order
+        pass
+
+    def side(self, flag):
+        pass
+
+    def join(self):
+        pass
+
     def mark(self, tag):
         self.prog.calls.append(("mark", tag))
 

@@ -284,6 +284,26 @@ class CudaBackend:
         _chk(qkv, torch.bfloat16, "attention.qkv")
         self.prog.add("attention_fwd", self.lib.dp_attention_fwd, _p(qkv), _p(ctx), B, T, heads, scale, keep=(qkv, ctx), flops=4.0 * B * T * T * heads * 64, bytes=B * T * heads * 64 * 8.0)
 
+    # ---- backward of an un-frozen encoder layer (Dinov2PoseModel(unfreeze_last_n_layers=n))
+    def attention_bwd(self, qkv, ctx, dctx, dqkv, stats, *, B, T, heads, scale):
+        for t, nm in ((qkv, "qkv"), (ctx, "ctx"), (dctx, "dctx"), (dqkv, "dqkv")):
+            _chk(t, torch.bfloat16, "attention_bwd." + nm)
+        _chk(stats, torch.float32, "attention_bwd.stats")
+        if stats.numel() < 2 * B * heads * T:
+            raise _lib.DinoPoseError("attention_bwd.stats: needs 2*B*heads*T floats")
+        self.prog.add("attention_bwd", self.lib.dp_attention_bwd, _p(qkv), _p(ctx), _p(dctx), _p(dqkv), _p(stats), B, T, heads,
+                      scale, keep=(qkv, ctx, dctx, dqkv, stats), flops=16.0 * B * T * T * heads * 64, launches=2)
+
+    def layernorm_bwd_params(self, dy, x, dgamma, dbeta, *, rows, D, eps=1e-6):
+        _chk(x, torch.float32, "ln_params.x", False)
+        self.prog.add("layernorm_bwd_params", self.lib.dp_layernorm_bwd_params, _p(dy), int(dy.dtype == torch.bfloat16), _p(x),
+                      _p(dgamma), _p(dbeta), rows, D, eps, keep=(dy, x, dgamma, dbeta))
+
+    def colsum_prod(self, g, a, out, *, P, C):
+        _chk(g, torch.float32, "colsum_prod.g")
+        _chk(a, torch.bfloat16, "colsum_prod.a")
+        self.prog.add("colsum_prod", self.lib.dp_colsum_prod, _p(g), _p(a), _p(out), P, C, keep=(g, a, out))
+
     def decode(self, hm, idx, xy, conf, *, maps, H, W, target_w, target_h):
         _chk(hm, torch.float32, "decode.heatmaps")
         self.prog.add("decode", self.lib.dp_decode, _p(hm), maps, H, W, float(target_w), float(target_h), _p(idx),

@@ -20,6 +20,10 @@ cudaError_t launch_lora_fwd(const float*, const float*, const float*, const floa
 cudaError_t launch_lora_bwd(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
                             long long, int, int, float, float, const unsigned long long*, int, cudaStream_t);
 cudaError_t launch_attention_fwd(const __nv_bfloat16*, __nv_bfloat16*, int, int, int, float, cudaStream_t);
+cudaError_t launch_attention_bwd(const __nv_bfloat16*, const __nv_bfloat16*, const __nv_bfloat16*, __nv_bfloat16*, float*, int,
+                                 int, int, float, cudaStream_t);
+cudaError_t launch_layernorm_bwd_params(const void*, int, const float*, float*, float*, long long, int, float, int, cudaStream_t);
+cudaError_t launch_colsum_prod(const float*, const __nv_bfloat16*, float*, long long, int, cudaStream_t);
 cudaError_t launch_decode(const float*, int, int, int, double, double, int*, double*, float*, cudaStream_t);
 cudaError_t launch_im2col(const void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_col2im(const void*, const float*, void*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -222,6 +226,26 @@ extern "C" int dp_sgemm_small(const float* A, long long sa_m, long long sa_k, co
   return cuda_error(launch_sgemm_small(A, sa_m, sa_k, B, sb_k, sb_n, C, ldc, M, N, K, bias, relu, mask_ref, ld_ref, p_drop,
                                        seed, accumulate, ST),
                     "dp_sgemm_small");
+}
+extern "C" int dp_attention_bwd(const void* qkv, const void* ctx, const void* dctx, void* dqkv, float* stats, int B, int T,
+                                int heads, float scale, void* stream) {
+  if (!qkv || !ctx || !dctx || !dqkv || !stats) return set_error(-1, "dp_attention_bwd: null pointer");
+  if (B <= 0 || T <= 0 || heads <= 0) return set_error(-2, "dp_attention_bwd: bad shape");
+  return cuda_error(launch_attention_bwd(static_cast<const __nv_bfloat16*>(qkv), static_cast<const __nv_bfloat16*>(ctx),
+                                         static_cast<const __nv_bfloat16*>(dctx), static_cast<__nv_bfloat16*>(dqkv), stats, B,
+                                         T, heads, scale, ST),
+                    "dp_attention_bwd");
+}
+extern "C" int dp_layernorm_bwd_params(const void* dy, int dy_is_bf16, const float* x, float* dgamma, float* dbeta,
+                                       long long rows, int D, float eps, void* stream) {
+  if (!dy || !x || !dgamma || !dbeta) return set_error(-1, "dp_layernorm_bwd_params: null pointer");
+  if (!ln_dim_ok(D)) return set_error(-2, "dp_layernorm_bwd_params: unsupported D=%d", D);
+  return cuda_error(launch_layernorm_bwd_params(dy, dy_is_bf16, x, dgamma, dbeta, rows, D, eps, sm_count(), ST),
+                    "dp_layernorm_bwd_params");
+}
+extern "C" int dp_colsum_prod(const float* g, const void* a, float* out, long long P, int C, void* stream) {
+  if (!g || !a || !out || P <= 0 || C <= 0) return set_error(-1, "dp_colsum_prod: bad args");
+  return cuda_error(launch_colsum_prod(g, static_cast<const __nv_bfloat16*>(a), out, P, C, ST), "dp_colsum_prod");
 }
 extern "C" int dp_colsum(const void* x, int is_bf16, float* out, long long P, int C, long long ld, void* stream) {
   if (!x || !out) return set_error(-1, "dp_colsum: bad args");

@@ -173,6 +173,99 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const TDY* __restric
   }
 }
 
+// LayerNorm parameter gradients of the un-frozen encoder layers (reference model/dinov2_pose.py:25-39 un-freezes
+// norm1 / norm2 of the last n blocks):  dgamma[c] += sum_rows dy[row,c] * xhat[row,c],  dbeta[c] += sum_rows dy[row,c].
+// Persistent blocks of 8 warps; a warp walks rows (statistics recomputed from x like the input-gradient kernel), a lane
+// keeps the partial sums of its 4*V columns in registers; one shared-memory reduction and 2*D atomics per block.
+template <int V, typename TDY>
+__global__ void __launch_bounds__(256) layernorm_bwd_params_kernel(const TDY* __restrict__ dy, const float* __restrict__ x,
+                                                                   float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                   long long rows, float eps) {
+  pdl_grid_sync();
+  constexpr int D = V * 128;
+  __shared__ float red[4][2 * D];   // two-step reduction over the 8 warps (32 KB at D = 1024)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float4 ag[V], ab[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) ag[i] = ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < rows; row += (long long)gridDim.x * 8) {
+    const float4* xr = reinterpret_cast<const float4*>(x + row * D);
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i] = __ldg(xr + lane + 32 * i);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float4 d;
+      if constexpr (sizeof(TDY) == 2) {
+        const uint2 pk = __ldg(reinterpret_cast<const uint2*>(dy + row * D) + lane + 32 * i);
+        const __nv_bfloat162 lo = *reinterpret_cast<const __nv_bfloat162*>(&pk.x);
+        const __nv_bfloat162 hi = *reinterpret_cast<const __nv_bfloat162*>(&pk.y);
+        d = make_float4(__low2float(lo), __high2float(lo), __low2float(hi), __high2float(hi));
+      } else {
+        d = __ldg(reinterpret_cast<const float4*>(dy + row * D) + lane + 32 * i);
+      }
+      ag[i].x = fmaf(d.x, v[i].x * rstd, ag[i].x); ag[i].y = fmaf(d.y, v[i].y * rstd, ag[i].y);
+      ag[i].z = fmaf(d.z, v[i].z * rstd, ag[i].z); ag[i].w = fmaf(d.w, v[i].w * rstd, ag[i].w);
+      ab[i].x += d.x; ab[i].y += d.y; ab[i].z += d.z; ab[i].w += d.w;
+    }
+  }
+  if (warp >= 4) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      *reinterpret_cast<float4*>(&red[warp - 4][4 * (lane + 32 * i)]) = ag[i];
+      *reinterpret_cast<float4*>(&red[warp - 4][D + 4 * (lane + 32 * i)]) = ab[i];
+    }
+  }
+  __syncthreads();
+  if (warp < 4) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float4 g2 = *reinterpret_cast<const float4*>(&red[warp][4 * (lane + 32 * i)]);
+      const float4 b2 = *reinterpret_cast<const float4*>(&red[warp][D + 4 * (lane + 32 * i)]);
+      ag[i].x += g2.x; ag[i].y += g2.y; ag[i].z += g2.z; ag[i].w += g2.w;
+      ab[i].x += b2.x; ab[i].y += b2.y; ab[i].z += b2.z; ab[i].w += b2.w;
+      *reinterpret_cast<float4*>(&red[warp][4 * (lane + 32 * i)]) = ag[i];
+      *reinterpret_cast<float4*>(&red[warp][D + 4 * (lane + 32 * i)]) = ab[i];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    const float t = (red[0][c] + red[1][c]) + (red[2][c] + red[3][c]);
+    atomicAdd((c < D ? dgamma + c : dbeta + (c - D)), t);
+  }
+}
+
+// out[c] += sum_rows g[row,c] * a[row,c]  (LayerScale gradient: g fp32 = gradient of the residual stream, a bf16 = the
+// branch output the scale multiplied; HF:272-278)
+__global__ void __launch_bounds__(128) colsum_prod_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ a,
+                                                          float* __restrict__ out, long long P, int C, int rows_per_block) {
+  pdl_grid_sync();
+  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long p0 = (long long)blockIdx.x * rows_per_block;
+  const long long p1 = min(p0 + rows_per_block, P);
+  float s0 = 0.f, s1 = 0.f;
+  long long p = p0;
+  for (; p + 1 < p1; p += 2) {
+    s0 = fmaf(__ldg(g + p * C + c), __bfloat162float(a[p * C + c]), s0);
+    s1 = fmaf(__ldg(g + (p + 1) * C + c), __bfloat162float(a[(p + 1) * C + c]), s1);
+  }
+  if (p < p1) s0 = fmaf(__ldg(g + p * C + c), __bfloat162float(a[p * C + c]), s0);
+  atomicAdd(out + c, s0 + s1);
+}
+
 template <typename F> static cudaError_t dispatch_v(int D, F&& f) {
   switch (D) {
     case 128: f(std::integral_constant<int, 1>{}); break;
@@ -207,6 +300,29 @@ cudaError_t launch_layernorm_bwd(const void* dy, int dy_is_bf16, const float* x,
       launch_k<layernorm_bwd_kernel<V, float>>(grid, wpb * 32, 0, s, reinterpret_cast<const float*>(dy), x, gamma, add_in, dx,
                                                              ls, dx_scaled, rows, T, drop_cls, eps);
   });
+}
+
+cudaError_t launch_layernorm_bwd_params(const void* dy, int dy_is_bf16, const float* x, float* dgamma, float* dbeta,
+                                        long long rows, int D, float eps, int sms, cudaStream_t s) {
+  long long want = (rows + 7) / 8;
+  const unsigned grid = unsigned(want < 2LL * sms ? (want < 1 ? 1 : want) : 2LL * sms);
+  return dispatch_v(D, [&](auto v) {
+    constexpr int V = decltype(v)::value;
+    if (dy_is_bf16)
+      launch_k<layernorm_bwd_params_kernel<V, __nv_bfloat16>>(grid, 256, 0, s, reinterpret_cast<const __nv_bfloat16*>(dy), x,
+                                                             dgamma, dbeta, rows, eps);
+    else
+      launch_k<layernorm_bwd_params_kernel<V, float>>(grid, 256, 0, s, reinterpret_cast<const float*>(dy), x, dgamma, dbeta,
+                                                     rows, eps);
+  });
+}
+
+cudaError_t launch_colsum_prod(const float* g, const __nv_bfloat16* a, float* out, long long P, int C, cudaStream_t s) {
+  int rpb = int((P + 295) / 296);
+  if (rpb < 32) rpb = 32;
+  dim3 grid(unsigned((P + rpb - 1) / rpb), unsigned((C + 127) / 128));
+  launch_k<colsum_prod_kernel>(grid, 128, 0, s, g, a, out, P, C, rpb);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------

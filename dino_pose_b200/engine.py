@@ -60,6 +60,9 @@ class PoseEngine:
         self.K = cfg["num_keypoints"]
         self.hm_size = cfg["heatmap_size"]
         self.lora = cfg.get("lora")
+        # Dinov2PoseModel(unfreeze_last_n_layers=n) (reference model/dinov2_pose.py:25-39): the last n encoder layers train
+        self.unfreeze = max(0, min(int(cfg.get("unfreeze", 0) or 0), cfg["L"]))
+        self.train_layers = list(range(cfg["L"] - self.unfreeze, cfg["L"]))
         # storage dtype of activations / packed weights.  The CUDA kernels are bf16-only; fp32 is accepted only by
         # the torch emulator (tests) to separate logic errors from bf16 rounding.
         self.adt = cfg.get("act_dtype", BF16)
@@ -124,6 +127,8 @@ class PoseEngine:
         order.append(("z_head", [n for n in zg if n in trainable]))
         lg = [self.lora_prefix + "lora_A", self.lora_prefix + "lora_B"] if self.lora else []
         order.append(("lora", [n for n in lg if n in trainable]))
+        for i in reversed(self.train_layers):
+            order.append((f"layer{i}", [n for n in self.layer_param_names(i) if n in trainable]))
         seen = {n for _k, g in order for n in g}
         rest = [n for n in self.trainable_names() if n not in seen]
         if rest:
@@ -137,6 +142,18 @@ class PoseEngine:
             ends[key] = off
         self._layout = {"names": [n for _k, g in order for n in g], "offsets": offsets, "group_end": ends, "total": off}
         return self._layout
+
+    def layer_param_names(self, i):
+        """Parameters of encoder layer i in the order the backward program finishes them.  The q/k/v biases and the q/k/v
+        weights are adjacent (and D, D*D are multiples of GRAD_ALIGN), so each triple is ONE contiguous slice of the flat
+        gradient buffer: the fused [3D, D] QKV weight gradient is written by a single launch."""
+        lp, ap = f"backbone.encoder.layer.{i}.", self.att_prefix[i]
+        return [lp + "layer_scale2.lambda1", lp + "mlp.fc2.bias", lp + "mlp.fc2.weight", lp + "mlp.fc1.bias",
+                lp + "mlp.fc1.weight", lp + "norm2.weight", lp + "norm2.bias", lp + "layer_scale1.lambda1",
+                ap + "output.dense.bias", ap + "output.dense.weight",
+                ap + "attention.query.bias", ap + "attention.key.bias", ap + "attention.value.bias",
+                ap + "attention.query.weight", ap + "attention.key.weight", ap + "attention.value.weight",
+                lp + "norm1.weight", lp + "norm1.bias"]
 
     # ------------------------------------------------------------------ frozen weight packing
     def pack_frozen(self):
@@ -282,6 +299,49 @@ class PoseEngine:
         be.pack_weights(jobs)
 
 
+    def record_pack_layers(self, plan, training):
+        """bf16 GEMM-layout copies of the UN-FROZEN encoder layers' weights (the optimizer changes them every step, so the
+        re-packing is part of the forward program): [3D, D] fused QKV, projection, fc1, fc2 and -- for the input-gradient
+        GEMMs of the backward -- their transposes; plus the concatenated fp32 QKV bias."""
+        D = self.D
+        lw = plan["lw"] = {}
+        jobs, cats = [], []
+        ident, transp = (0, 1, 2, 3), (1, 0, 2, 3)
+        for i in self.train_layers:
+            lp, ap = f"backbone.encoder.layer.{i}.", self.att_prefix[i]
+            w = lw[i] = {}
+            w["wqkv"] = self.new((3 * D, D), self.adt)
+            w["bqkv"] = self.new((3 * D,), F32)
+            w["wo"] = self.new((D, D), self.adt)
+            w["w1"] = self.new((4 * D, D), self.adt)
+            w["w2"] = self.new((D, 4 * D), self.adt)
+            if training:
+                w["wqkvT"] = self.new((D, 3 * D), self.adt)
+                w["woT"] = self.new((D, D), self.adt)
+                w["w1T"] = self.new((D, 4 * D), self.adt)
+                w["w2T"] = self.new((4 * D, D), self.adt)
+            qkv_w = [self.p(ap + f"attention.{n}.weight").detach() for n in ("query", "key", "value")]
+            for j, pw in enumerate(qkv_w):
+                jobs.append((w["wqkv"][j * D:(j + 1) * D], pw.view(D, D, 1, 1), ident, (), None))
+                if training:
+                    jobs.append((w["wqkvT"][:, j * D:(j + 1) * D], pw.view(D, D, 1, 1), transp, (), (3 * D, 1, 1, 1)))
+            for key, name, n_out, n_in in (("wo", ap + "output.dense.weight", D, D), ("w1", lp + "mlp.fc1.weight", 4 * D, D),
+                                           ("w2", lp + "mlp.fc2.weight", D, 4 * D)):
+                pw = self.p(name).detach().view(n_out, n_in, 1, 1)
+                jobs.append((w[key], pw, ident, (), None))
+                if training:
+                    jobs.append((w[key + "T"], pw, transp, (), None))
+            cats.append((w["bqkv"], [self.p(ap + f"attention.{n}.bias") for n in ("query", "key", "value")]))
+        if not jobs:
+            return
+
+        def cat_biases():
+            with torch.no_grad():
+                for dst, parts in cats:
+                    torch.cat([t.detach() for t in parts], out=dst)
+        self.be.pack_weights(jobs)
+        self.be.host("cat_qkv_bias", cat_biases)
+
     # ------------------------------------------------------------------ plans
     def get_plan(self, B, H, W, training):
         key = (B, H, W, bool(training))
@@ -327,6 +387,9 @@ class PoseEngine:
 
         # ---------------- forward program
         prog_f = be.begin()
+        # un-frozen encoder layers: their bf16 weight copies are refreshed by the program itself
+        self.record_pack_layers(plan, training)
+        lw = plan["lw"]
         # the bf16 re-packing of the trainable head weights only has to be done before the first head convolution: it
         # runs on the second stream underneath the backbone (gather-bound, ~50 us, a fraction of the SMs)
         plan["layers"] = self.build_head_layers(g)
@@ -338,9 +401,41 @@ class PoseEngine:
         be.gemm(t["acol"], fz["wpe"], t["x"], M=B * N, N=D, K=PATCH_KP, out_dtype="f32", residual=pos,
                 row_map="patch_tokens", map_a=N, map_b=T, name="patch_embed")
         scale = 1.0 / math.sqrt(D // heads)
+        sv = plan["saved"] = {}      # per un-frozen layer: everything its backward reads
+        x_cur = t["x"]               # residual stream entering the current layer
         for i in range(L):
             lp = f"backbone.encoder.layer.{i}."
             last = i == L - 1
+            if i in lw:
+                # ---- un-frozen layer (reference model/dinov2_pose.py:25-39): same arithmetic, weights from the per-step
+                # packed copies; in training every intermediate the backward needs gets its own buffer
+                w = lw[i]
+                if training:
+                    s_ = sv[i] = {"x_in": x_cur, "xn1": self.new((M, D), self.adt), "qkv": self.new((M, 3 * D), self.adt),
+                                  "ctx": self.new((M, D), self.adt), "a": self.new((M, D), self.adt),
+                                  "x_mid": self.new((M, D), F32), "xn2": self.new((M, D), self.adt),
+                                  "pre": self.new((M, 4 * D), self.adt), "h": self.new((M, 4 * D), self.adt),
+                                  "m": self.new((M, D), self.adt),
+                                  "x_out": t["x_last"] if last else self.new((M, D), F32)}
+                else:
+                    s_ = {"x_in": x_cur, "xn1": t["xn"], "qkv": t["qkv"], "ctx": t["ctx"], "a": None, "x_mid": x_cur,
+                          "xn2": t["xn"], "pre": None, "h": t["h"], "m": None, "x_out": x_cur}
+                be.layernorm_fwd(x_cur, self.p(lp + "norm1.weight"), self.p(lp + "norm1.bias"), s_["xn1"], None, rows=M, D=D,
+                                 eps=LN_EPS)
+                be.gemm(s_["xn1"], w["wqkv"], s_["qkv"], M=M, N=3 * D, K=D, bias=w["bqkv"], name=f"qkv{i}")
+                be.attention_fwd(s_["qkv"], s_["ctx"], B=B, T=T, heads=heads, scale=scale)
+                be.gemm(s_["ctx"], w["wo"], s_["x_mid"], M=M, N=D, K=D, bias=self.p(self.att_prefix[i] + "output.dense.bias"),
+                        out_dtype="f32", ls=self.p(lp + "layer_scale1.lambda1"), residual=x_cur, aux_out=s_["a"], ld_aux=D,
+                        name=f"proj{i}")
+                be.layernorm_fwd(s_["x_mid"], self.p(lp + "norm2.weight"), self.p(lp + "norm2.bias"), s_["xn2"], None, rows=M,
+                                 D=D, eps=LN_EPS)
+                be.gemm(s_["xn2"], w["w1"], s_["h"], M=M, N=4 * D, K=D, bias=self.p(lp + "mlp.fc1.bias"), act="gelu",
+                        aux_out=s_["pre"], ld_aux=4 * D, name=f"fc1_{i}", block_n=192 if (4 * D) % 192 == 0 else 0)
+                be.gemm(s_["h"], w["w2"], s_["x_out"], M=M, N=D, K=4 * D, bias=self.p(lp + "mlp.fc2.bias"), out_dtype="f32",
+                        ls=self.p(lp + "layer_scale2.lambda1"), residual=s_["x_mid"], aux_out=s_["m"], ld_aux=D,
+                        name=f"fc2_{i}")
+                x_cur = s_["x_out"]
+                continue
             be.layernorm_fwd(t["x"], self.p(lp + "norm1.weight"), self.p(lp + "norm1.bias"), t["xn"], None, rows=M, D=D,
                              eps=LN_EPS)
             be.gemm(t["xn"], fz[f"wqkv{i}"], t["qkv"], M=M, N=3 * D, K=D, bias=fz[f"bqkv{i}"], name=f"qkv{i}")
@@ -787,6 +882,9 @@ class PoseEngine:
         be.join()                # z-head chain (second stream): its input gradient dcur is needed now
         be.mean_tokens_bwd(dfeat, dcur, B=B, N=N, D=D)
         done("z_head")
+        if self.train_layers:
+            self.record_backward_layers(plan, dfeat, G, flat, ws, done)
+            return
         if not self.lora:
             return
         # ---- backbone: final LayerNorm, last block's MLP branch, LoRA adapter
@@ -807,6 +905,76 @@ class PoseEngine:
                     G[self.lora_prefix + "lora_A"], G[self.lora_prefix + "lora_B"], t["gu"], rows=M, D=D, R=self.lora["rank"],
                     scaling=self.lora["alpha"] / self.lora["rank"], p_drop=float(self.lora.get("dropout", 0.0)),
                     seed=self.seed)
+        be.mark(("grads_final", lay["total"]))
+
+    def record_backward_layers(self, plan, dfeat, G, flat, ws, done):
+        """Backward through the final LayerNorm and the un-frozen encoder layers (autograd of HF:367-386 for
+        Dinov2PoseModel(unfreeze_last_n_layers=n), reference model/dinov2_pose.py:25-39).  Per layer, with g = dL/dx_out:
+          MLP branch   x_out = x_mid + l2 * m,  m = fc2(gelu(fc1(LN2(x_mid))))
+          attention    x_mid = x_in  + l1 * a,  a = dense(attn(qkv(LN1(x_in))))
+        Linear weight gradients go through the MN-major tcgen05 wgrad kernel, input gradients through the K-major GEMM
+        with the transposed weight copies, bias / LayerScale / LayerNorm-parameter gradients through column reductions."""
+        be = self.be
+        B, T, M = plan["B"], plan["T"], plan["M"]
+        D, L, heads = self.D, self.L, self.heads
+        lay = self.layout()
+        sv, lw = plan["saved"], plan["lw"]
+        scale = 1.0 / math.sqrt(D // heads)
+        first = self.train_layers[0]
+
+        def gslice(names, shape):
+            # q / k / v gradients as ONE tensor: their flat-buffer slices are adjacent (layer_param_names)
+            off0, k0 = lay["offsets"][names[0]]
+            for j, n in enumerate(names):
+                assert lay["offsets"][n] == (off0 + j * k0, k0), "q/k/v gradient slices must be contiguous"
+            return flat[off0:off0 + len(names) * k0].view(shape)
+
+        g = self.new((M, D), F32)              # dL/dx_out of the current layer
+        gs = self.new((M, D), self.adt)        # bf16(g * layer_scale2)
+        top = f"backbone.encoder.layer.{L - 1}."
+        be.layernorm_bwd(dfeat, plan["x_final"], self.p("backbone.layernorm.weight"), None, g, rows=M, D=D, T=T,
+                         drop_cls=True, eps=LN_EPS, ls=self.p(top + "layer_scale2.lambda1"), dx_scaled=gs)
+        stats = self.new((2 * B * heads * T,), F32)
+        dpre = self.new((M, 4 * D), self.adt)
+        dxn = self.new((M, D), self.adt)
+        gmid = self.new((M, D), F32)
+        gmids = self.new((M, D), self.adt)
+        dctx = self.new((M, D), self.adt)
+        dqkv = self.new((M, 3 * D), self.adt)
+        for i in reversed(self.train_layers):
+            lp, ap = f"backbone.encoder.layer.{i}.", self.att_prefix[i]
+            s_, w = sv[i], lw[i]
+            # ---- MLP branch
+            be.colsum_prod(g, s_["m"], G[lp + "layer_scale2.lambda1"], P=M, C=D)
+            be.colsum(gs, G[lp + "mlp.fc2.bias"], P=M, C=D, ld=D)
+            be.wgrad(gs, s_["h"], G[lp + "mlp.fc2.weight"], Mc=D, Nc=4 * D, so_m=4 * D, so_n=1, P=M, name=f"fc2_{i}.wgrad",
+                     workspace=ws)
+            be.gemm(gs, w["w2T"], dpre, M=M, N=4 * D, K=D, aux_in=s_["pre"], ld_aux=4 * D, name=f"fc2_{i}.dgrad")
+            be.colsum(dpre, G[lp + "mlp.fc1.bias"], P=M, C=4 * D, ld=4 * D)
+            be.wgrad(dpre, s_["xn2"], G[lp + "mlp.fc1.weight"], Mc=4 * D, Nc=D, so_m=D, so_n=1, P=M, name=f"fc1_{i}.wgrad",
+                     workspace=ws)
+            be.gemm(dpre, w["w1T"], dxn, M=M, N=D, K=4 * D, name=f"fc1_{i}.dgrad")
+            be.layernorm_bwd_params(dxn, s_["x_mid"], G[lp + "norm2.weight"], G[lp + "norm2.bias"], rows=M, D=D, eps=LN_EPS)
+            be.layernorm_bwd(dxn, s_["x_mid"], self.p(lp + "norm2.weight"), g, gmid, rows=M, D=D, eps=LN_EPS,
+                             ls=self.p(lp + "layer_scale1.lambda1"), dx_scaled=gmids)
+            # ---- attention branch
+            be.colsum_prod(gmid, s_["a"], G[lp + "layer_scale1.lambda1"], P=M, C=D)
+            be.colsum(gmids, G[ap + "output.dense.bias"], P=M, C=D, ld=D)
+            be.wgrad(gmids, s_["ctx"], G[ap + "output.dense.weight"], Mc=D, Nc=D, so_m=D, so_n=1, P=M, name=f"proj{i}.wgrad",
+                     workspace=ws)
+            be.gemm(gmids, w["woT"], dctx, M=M, N=D, K=D, name=f"proj{i}.dgrad")
+            be.attention_bwd(s_["qkv"], s_["ctx"], dctx, dqkv, stats, B=B, T=T, heads=heads, scale=scale)
+            qkv_names = [ap + f"attention.{n}." for n in ("query", "key", "value")]
+            be.colsum(dqkv, gslice([n + "bias" for n in qkv_names], (3 * D,)), P=M, C=3 * D, ld=3 * D)
+            be.wgrad(dqkv, s_["xn1"], gslice([n + "weight" for n in qkv_names], (3 * D, D)), Mc=3 * D, Nc=D, so_m=D, so_n=1,
+                     P=M, name=f"qkv{i}.wgrad", workspace=ws)
+            be.gemm(dqkv, w["wqkvT"], dxn, M=M, N=D, K=3 * D, name=f"qkv{i}.dgrad")
+            be.layernorm_bwd_params(dxn, s_["x_in"], G[lp + "norm1.weight"], G[lp + "norm1.bias"], rows=M, D=D, eps=LN_EPS)
+            if i > first:
+                below = f"backbone.encoder.layer.{i - 1}."
+                be.layernorm_bwd(dxn, s_["x_in"], self.p(lp + "norm1.weight"), gmid, g, rows=M, D=D, eps=LN_EPS,
+                                 ls=self.p(below + "layer_scale2.lambda1"), dx_scaled=gs)
+            done(f"layer{i}")
         be.mark(("grads_final", lay["total"]))
 
     # ------------------------------------------------------------------ running

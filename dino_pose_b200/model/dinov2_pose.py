@@ -83,7 +83,7 @@ class _Dinov2PoseBase(BasePoseModel):
         zh = self.pose_heads.z_head
         ecfg = dict(D=cfg.hidden_size, L=cfg.num_hidden_layers, heads=cfg.num_attention_heads,
                     num_keypoints=self.num_keypoints, heatmap_size=self.heatmap_size, lora=lora,
-                    z_hidden=zh.hidden_dims, z_dropout=zh.mlp[2].p)
+                    z_hidden=zh.hidden_dims, z_dropout=zh.mlp[2].p, unfreeze=getattr(self, "unfreeze_last_n_layers", 0))
         if getattr(self, "_act_dtype", None) is not None:
             ecfg["act_dtype"] = self._act_dtype
         if getattr(self, "_raw_dtype", None) is not None:
@@ -164,11 +164,13 @@ class Dinov2PoseModel(_Dinov2PoseBase):
 
     def __init__(self, num_keypoints=24, backbone="facebook/dinov2-base", unfreeze_last_n_layers=0, heatmap_size=48):
         super().__init__()
-        if unfreeze_last_n_layers > 0:
-            raise NotImplementedError(
-                "unfreeze_last_n_layers > 0 needs the attention / QKV backward kernels (SURVEY 8f-4, next row); "
-                "the LoRA fine-tuning path (Dinov2PoseModelLoRA) is the one implemented")
         self._init_common(num_keypoints, backbone, heatmap_size)
+        # reference :25-39: every parameter of the last n encoder layers (attention, MLP, LayerScale, both LayerNorms)
+        layers = self.backbone.encoder.layer
+        self.unfreeze_last_n_layers = max(0, min(int(unfreeze_last_n_layers), len(layers)))
+        for i in range(1, self.unfreeze_last_n_layers + 1):
+            for p in layers[len(layers) - i].parameters():
+                p.requires_grad = True
         self._init_heads(num_keypoints, heatmap_size)
 
     @classmethod

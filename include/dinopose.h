@@ -131,6 +131,19 @@ int dp_lora_bwd(const float* g, const float* y, const float* u_saved, const floa
 /* Multi-head attention forward (HF:203-234), head dim 64.  qkv bf16 [B*T, 3*heads*64] -> ctx bf16 [B*T, heads*64]. */
 int dp_attention_fwd(const void* qkv_bf16, void* ctx_bf16, int B, int T, int heads, float scale, void* stream);
 
+/* ---- backward of an UN-FROZEN encoder layer: Dinov2PoseModel(unfreeze_last_n_layers = n), reference
+ * model/dinov2_pose.py:25-39 (autograd of HF:203-234, :371-384) */
+/* Attention backward.  qkv, dqkv bf16 [B*T, 3*heads*64] (q | k | v and dq | dk | dv); ctx = forward output, dctx =
+ * its gradient, bf16 [B*T, heads*64]; stats = fp32 scratch [2 * B*heads*T] (row log-sum-exp and rowsum(dO o O),
+ * recomputed here: the forward stores nothing).  Deterministic (no atomics). */
+int dp_attention_bwd(const void* qkv_bf16, const void* ctx_bf16, const void* dctx_bf16, void* dqkv_bf16, float* stats,
+                     int B, int T, int heads, float scale, void* stream);
+/* LayerNorm parameter gradients: dgamma[c] += sum_rows dy*xhat, dbeta[c] += sum_rows dy (atomics, caller zeroes). */
+int dp_layernorm_bwd_params(const void* dy, int dy_is_bf16, const float* x, float* dgamma, float* dbeta, long long rows,
+                            int D, float eps, void* stream);
+/* LayerScale gradient (HF:272-278): out[c] += sum_rows g[row,c] * a[row,c]; g fp32, a bf16, both [P, C] dense. */
+int dp_colsum_prod(const float* g, const void* a_bf16, float* out, long long P, int C, void* stream);
+
 /* ---------------------------------------------------------------- decode */
 /* Heat-map -> key-points (reference src/model_utils.py:10-51).  heatmaps fp32 [maps, H, W];
  * idx int32 [maps,2] = (row, col) of the first maximum; xy float64 [maps,2] = refined (x, y) scaled to

@@ -37,6 +37,13 @@ MODEL_CASES = [
     ("large_frozen_b1_224_eval", "facebook/dinov2-large", 0, 1, 224, "eval"),
 ]
 
+# Dinov2PoseModel(unfreeze_last_n_layers=n) (reference model/dinov2_pose.py:25-39):
+# name, arch, lora_rank (0), batch, res, mode, n
+UNFREEZE_CASES = [
+    ("tiny_unfreeze2_b3_224_train", "test/dinov2-tiny", 0, 3, 224, "train", 2),
+    ("small_unfreeze2_b2_224_train", "facebook/dinov2-small", 0, 2, 224, "train", 2),
+]
+
 
 def subsample(t):
     """Deterministic strided subsample of a tensor/array (<= MAX_KEEP values) as fp32 numpy."""
@@ -50,12 +57,12 @@ def l2(t):
     return np.float64(torch.as_tensor(t).double().norm().item())
 
 
-def build_reference_model(dp, arch, lora_rank, sd):
+def build_reference_model(dp, arch, lora_rank, sd, unfreeze=0):
     if lora_rank:
         m = dp.Dinov2PoseModelLoRA(num_keypoints=24, backbone=arch, heatmap_size=48,
                                    lora_rank=lora_rank, lora_alpha=16, lora_dropout=0.0)
     else:
-        m = dp.Dinov2PoseModel(num_keypoints=24, backbone=arch, heatmap_size=48)
+        m = dp.Dinov2PoseModel(num_keypoints=24, backbone=arch, heatmap_size=48, unfreeze_last_n_layers=unfreeze)
     ref_sd = m.state_dict()
     assert list(ref_sd.keys()) == list(sd.keys()) or set(ref_sd.keys()) == set(sd.keys()), \
         (set(ref_sd) ^ set(sd))
@@ -69,10 +76,10 @@ def build_reference_model(dp, arch, lora_rank, sd):
     return m
 
 
-def run_model_case(dp, losses, name, arch, lora_rank, batch, res, mode):
+def run_model_case(dp, losses, name, arch, lora_rank, batch, res, mode, unfreeze=0):
     torch.manual_seed(0)
     sd = make_state_dict(arch, seed=0, lora_rank=lora_rank)
-    m = build_reference_model(dp, arch, lora_rank, sd)
+    m = build_reference_model(dp, arch, lora_rank, sd, unfreeze)
     inp = make_inputs(batch, res, res, seed=0)
     out = {}
     hooks = {}
@@ -220,7 +227,7 @@ def main(argv):
     dp, _lora, _ph = ref_harness.import_reference()
     losses = ref_harness.import_reference_losses()
     only = set(argv[1:])
-    for case in MODEL_CASES:
+    for case in MODEL_CASES + UNFREEZE_CASES:
         if only and case[0] not in only:
             continue
         run_model_case(dp, losses, *case)

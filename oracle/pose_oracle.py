@@ -242,26 +242,31 @@ class DynamicLossWeighting:
         return kp_loss / (self.kp_avg + 1e-8) + zl / (self.z_avg + 1e-8)
 
 
-def trainable_names(sd, lora):
-    """Parameters that receive gradients in the LoRA model (reference
-    model/dinov2_pose.py:193-204: backbone frozen, lora_A/B + every head parameter)."""
+def trainable_names(sd, lora, unfreeze=0, arch=None):
+    """Parameters that receive gradients: every head parameter, plus lora_A/B in the LoRA model (reference
+    model/dinov2_pose.py:193-204: backbone frozen) or every parameter of the last ``unfreeze`` encoder layers in
+    ``Dinov2PoseModel(unfreeze_last_n_layers=unfreeze)`` (reference model/dinov2_pose.py:25-39)."""
     out = []
+    layers = ()
+    if unfreeze:
+        L = ARCHS[arch][1]
+        layers = tuple(f"backbone.encoder.layer.{i}." for i in range(L - unfreeze, L))
     for k, v in sd.items():
         if not v.dtype.is_floating_point:
             continue
         if "running_" in k:
             continue
-        if k.startswith("pose_heads.") or ".lora_output." in k:
+        if k.startswith("pose_heads.") or ".lora_output." in k or (layers and k.startswith(layers)):
             out.append(k)
     return out
 
 
-def loss_and_grads(sd, batch, arch, lora, training=True, z_dropout=0.0):
+def loss_and_grads(sd, batch, arch, lora, training=True, z_dropout=0.0, unfreeze=0):
     """One forward + reference losses + backward.  Loss = kp + 0.1 * z on the first step
     (``DynamicLossWeighting.get_balanced_loss`` falls back to ``kp + weight*z`` with
     weight 0.1 until averages exist -- but ``update`` is called first in train.py:154-163,
     so the first-step loss is the normalised form; both are exposed)."""
-    names = trainable_names(sd, lora)
+    names = trainable_names(sd, lora, unfreeze, arch)
     for n in names:
         sd[n].requires_grad_(True)
     hm, z = model_forward(sd, batch["pixel_values"], arch, lora, training, z_dropout=z_dropout)

@@ -271,6 +271,32 @@ class TorchEmulator:
             ctx.copy_((p.to(ctx.dtype).float() @ v).transpose(1, 2).reshape(B * T, D).to(ctx.dtype))
         self.prog.calls.append(fn)
 
+    def attention_bwd(self, qkv, ctx, dctx, dqkv, stats, *, B, T, heads, scale):
+        def fn():
+            D = heads * 64
+            q, k, v = [t.reshape(B, T, heads, 64).transpose(1, 2).detach().clone().requires_grad_(True)
+                       for t in qkv.float().view(B, T, 3 * D).split(D, -1)]
+            with torch.enable_grad():
+                o = (torch.softmax(q @ k.transpose(2, 3) * scale, -1) @ v).transpose(1, 2).reshape(B * T, D)
+                o.backward(dctx.float())
+            g = torch.cat([t.grad.transpose(1, 2).reshape(B * T, D) for t in (q, k, v)], -1)
+            dqkv.copy_(g.to(dqkv.dtype))
+        self.prog.calls.append(fn)
+
+    def layernorm_bwd_params(self, dy, x, dgamma, dbeta, *, rows, D, eps=1e-6):
+        def fn():
+            xf = x.float()[:rows]
+            xhat = (xf - xf.mean(-1, keepdim=True)) * torch.rsqrt(xf.var(-1, unbiased=False, keepdim=True) + eps)
+            g = dy.float()[:rows]
+            dgamma.add_((g * xhat).sum(0))
+            dbeta.add_(g.sum(0))
+        self.prog.calls.append(fn)
+
+    def colsum_prod(self, g, a, out, *, P, C):
+        def fn():
+            out.view(-1)[:C].add_((g.float().view(P, C) * a.float().view(P, C)).sum(0))
+        self.prog.calls.append(fn)
+
     # ------------------------------------------------------------------ heads
     def im2col(self, x, col, *, NB, IH, IW, C, OH, OW, KH, KW, stride, pad):
         def fn():

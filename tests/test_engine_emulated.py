@@ -19,11 +19,11 @@ def relmax(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
-def build(arch, lora_rank, seed=0, act_dtype=None):
+def build(arch, lora_rank, seed=0, act_dtype=None, unfreeze=0):
     if lora_rank:
         m = Dinov2PoseModelLoRA(backbone=arch, lora_rank=lora_rank, lora_alpha=16, lora_dropout=0.0)
     else:
-        m = Dinov2PoseModel(backbone=arch)
+        m = Dinov2PoseModel(backbone=arch, unfreeze_last_n_layers=unfreeze)
     m.load_state_dict(make_state_dict(arch, seed, lora_rank))
     for mod in m.modules():
         if isinstance(mod, torch.nn.Dropout):
@@ -56,10 +56,10 @@ def test_eval_forward_lora_merged_matches_oracle():
     assert relmax(z, rz) < 2e-2
 
 
-def _train_grads(golden_dir, act_dtype):
-    g = np.load(os.path.join(golden_dir, "tiny_lora_b3_224_train.npz"))
+def _train_grads(golden_dir, act_dtype, unfreeze=0):
+    g = np.load(os.path.join(golden_dir, "tiny_unfreeze2_b3_224_train.npz" if unfreeze else "tiny_lora_b3_224_train.npz"))
     arch = "test/dinov2-tiny"
-    m = build(arch, 8, act_dtype=act_dtype).train()
+    m = build(arch, 0 if unfreeze else 8, act_dtype=act_dtype, unfreeze=unfreeze).train()
     inp = make_inputs(3, 224, 224, 0)
     hm, z = m(inp["pixel_values"])
     tol = 2e-2 if act_dtype is None else 1e-4
@@ -110,6 +110,40 @@ def test_train_step_bf16_storage_vs_reference(golden_dir):
     stats = _train_grads(golden_dir, None)
     bad = {n: v for n, v in stats.items() if v[0] > 0.35 or v[1] < 0.95}
     assert not bad, bad
+
+
+def test_unfrozen_layers_logic_exact_in_fp32_storage(golden_dir):
+    """Dinov2PoseModel(unfreeze_last_n_layers=2) (reference model/dinov2_pose.py:25-39): the backward
+    through both encoder layers -- attention, QKV / projection / MLP weight and bias gradients, LayerScale and LayerNorm
+    parameter gradients -- reproduces the real reference's gradients through the engine's op graph."""
+    stats = _train_grads(golden_dir, torch.float32, unfreeze=2)
+    backbone = {n: v for n, v in stats.items() if n.startswith("backbone.")}
+    assert len(backbone) == 2 * 17, sorted(backbone)       # 18 tensors per layer minus the analytically-zero key bias
+    # fp32 noise floor of these cancelling sums at tiny / batch 3 is 7e-3 (tests/test_oracle_golden.py)
+    bad = {n: v for n, v in stats.items() if v[0] > 2e-2 or v[1] < 0.9995}
+    assert not bad, bad
+
+
+def test_unfrozen_layers_bf16_storage_vs_reference(golden_dir):
+    stats = _train_grads(golden_dir, None, unfreeze=2)
+    bad = {n: v for n, v in stats.items() if v[0] > 0.35 or v[1] < 0.95}
+    assert not bad, bad
+
+
+def test_unfrozen_layers_eval_uses_current_weights():
+    """eval forward of the un-frozen model reads the per-step packed weights: an in-place parameter update (what an
+    optimizer does) must show up in the next forward."""
+    arch = "test/dinov2-tiny"
+    m = build(arch, 0, unfreeze=1).eval()
+    inp = make_inputs(1, 224, 224, 3)
+    with torch.no_grad():
+        hm0, _ = m(inp["pixel_values"])
+        m.backbone.encoder.layer[-1].mlp.fc2.weight.mul_(0.5)
+        hm1, _ = m(inp["pixel_values"])
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        rhm, _ = pose_oracle.model_forward(sd, inp["pixel_values"], arch, None, False)
+    assert relmax(hm0, hm1) > 1e-3
+    assert relmax(hm1, rhm) < 2e-2
 
 
 def test_448_eval_matches_oracle():

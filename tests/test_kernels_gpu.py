@@ -388,6 +388,52 @@ def test_attention(B, T, heads):
     assert rel(ctx.float(), ref) < 1.5e-2
 
 
+@pytest.mark.parametrize("B,T,heads", [(2, 257, 6), (1, 1025, 2), (3, 65, 2), (2, 129, 12), (1, 64, 1)])
+def test_attention_bwd(B, T, heads):
+    """dq | dk | dv against autograd of softmax(q k^T * scale) v in fp32 on the same bf16 inputs (HF:203-234)."""
+    D = heads * 64
+    qkv = rnd(B * T, 3 * D, dtype=BF)
+    dctx = rnd(B * T, D, scale=0.5, seed=5, dtype=BF)
+    q, k, v = [t.reshape(B, T, heads, 64).transpose(1, 2).detach().clone().requires_grad_(True)
+               for t in qkv.float().view(B, T, 3 * D).split(D, dim=-1)]
+    o = (torch.softmax(q @ k.transpose(2, 3) * 0.125, -1) @ v).transpose(1, 2).reshape(B * T, D)
+    o.backward(dctx.float())
+    ref = torch.cat([t.grad.transpose(1, 2).reshape(B * T, D) for t in (q, k, v)], -1)
+    ctx = o.detach().to(BF)
+    dqkv = torch.full((B * T, 3 * D), 7.0, device=dev(), dtype=BF)
+    stats = torch.zeros(2 * B * heads * T, device=dev())
+    run(lambda b: b.attention_bwd(qkv, ctx, dctx, dqkv, stats, B=B, T=T, heads=heads, scale=0.125))
+    for j, name in enumerate("qkv"):
+        got, want = dqkv[:, j * D:(j + 1) * D].float(), ref[:, j * D:(j + 1) * D]
+        assert rel(got, want) < 2e-2, (name, rel(got, want))
+        l2 = ((got - want).norm() / want.norm()).item()
+        assert l2 < 1e-2, (name, l2)
+    # row statistics written for the dK / dV kernel: log2-domain log-sum-exp of the scaled scores
+    lse = torch.logsumexp(q.detach() @ k.detach().transpose(2, 3) * 0.125, -1) * 1.4426950408889634
+    assert rel(stats[:B * heads * T].view(B, heads, T), lse) < 1e-4
+    # deterministic: a second run gives the same bits
+    again = torch.zeros_like(dqkv)
+    run(lambda b: b.attention_bwd(qkv, ctx, dctx, again, stats, B=B, T=T, heads=heads, scale=0.125))
+    assert torch.equal(again, dqkv)
+
+
+@pytest.mark.parametrize("D,rows,dt", [(128, 700, BF), (384, 16448, BF), (768, 515, torch.float32), (1024, 1030, BF)])
+def test_layernorm_param_grads_and_colsum_prod(D, rows, dt):
+    x = rnd(rows, D, scale=2.0) + 0.3
+    dy = rnd(rows, D, seed=4, dtype=dt)
+    dg = torch.zeros(D, device=dev())
+    db = torch.zeros(D, device=dev())
+    run(lambda b: b.layernorm_bwd_params(dy, x, dg, db, rows=rows, D=D, eps=1e-6))
+    xr = x.double()
+    xhat = (xr - xr.mean(-1, keepdim=True)) * torch.rsqrt(xr.var(-1, unbiased=False, keepdim=True) + 1e-6)
+    assert rel(dg, (dy.double() * xhat).sum(0)) < 2e-4
+    assert rel(db, dy.double().sum(0)) < 2e-4
+    a = rnd(rows, D, seed=6, dtype=BF)
+    out = torch.zeros(D, device=dev())
+    run(lambda b: b.colsum_prod(x, a, out, P=rows, C=D))
+    assert rel(out, (x.double() * a.double()).sum(0)) < 2e-4
+
+
 def test_patch_im2col_and_cls():
     B, H, W, Kp, D = 2, 28, 42, 640, 128
     px = rnd(B, 3, H, W)

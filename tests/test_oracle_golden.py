@@ -7,7 +7,7 @@ import pytest
 import torch
 
 from oracle import decode_oracle, pose_oracle
-from oracle.make_golden import MODEL_CASES, subsample
+from oracle.make_golden import MODEL_CASES, UNFREEZE_CASES, subsample
 from oracle.weights import make_inputs, make_state_dict
 
 FAST = [c for c in MODEL_CASES if c[0].startswith(("tiny", "small"))]
@@ -24,9 +24,10 @@ def _relmax(a, b):
     return np.abs(a - b).max() / max(np.abs(b).max(), 1e-30)
 
 
-@pytest.mark.parametrize("case", FAST + SLOW, ids=lambda c: c[0])
+@pytest.mark.parametrize("case", FAST + SLOW + UNFREEZE_CASES, ids=lambda c: c[0])
 def test_model_oracle_matches_reference(golden_dir, case):
-    name, arch, lora_rank, batch, res, mode = case
+    name, arch, lora_rank, batch, res, mode = case[:6]
+    unfreeze = case[6] if len(case) > 6 else 0      # Dinov2PoseModel(unfreeze_last_n_layers=n), reference :25-39
     g = _load(golden_dir, name)
     torch.set_num_threads(os.cpu_count() or 1)
     sd = make_state_dict(arch, seed=0, lora_rank=lora_rank)
@@ -43,7 +44,7 @@ def test_model_oracle_matches_reference(golden_dir, case):
                          ("up0", aux["up0"]), ("up1", aux["up1"]), ("pred0", aux["pred0"])):
             assert _relmax(subsample(val), g["sub." + key]) < tol, key
     else:
-        out = pose_oracle.loss_and_grads(sd, inp, arch, lora, training=True)
+        out = pose_oracle.loss_and_grads(sd, inp, arch, lora, training=True, unfreeze=unfreeze)
         hm, z = out["heatmaps"], out["z"]
         assert abs(out["kp_loss"].item() - g["kp_loss"]) < 1e-6
         assert abs(out["z_loss"].item() - g["z_loss"]) < 1e-6
@@ -61,7 +62,10 @@ def test_model_oracle_matches_reference(golden_dir, case):
                 # differs by ~5e-4 relative L2, measured) -> relative-L2 tolerance, not element-wise
                 sub = subsample(grad)
                 rel = np.linalg.norm(sub - ref) / (np.linalg.norm(ref) + 1e-30)
-                assert rel < 5e-3, (pname, rel)
+                # un-frozen backbone layers sit one more cancelling stage upstream: at tiny / batch 3 the fp32 oracle, the
+                # fp32 reference and an fp64 run of the oracle differ pairwise by 3e-3 .. 7.5e-3 (measured); at ViT-S the
+                # same comparison gives <= 5e-4
+                assert rel < (1.5e-2 if unfreeze else 5e-3), (pname, rel)
             n += 1
         assert n == int(g["num_grad_tensors"])
         for k in g.files:

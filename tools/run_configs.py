@@ -23,6 +23,9 @@ CONFIGS = [
     ("cfg3 L frozen infer b256 224", "facebook/dinov2-large", False, 256, 224, "infer", 167.33),
     ("cfg4 S LoRA infer b64 448", "facebook/dinov2-small", True, 64, 448, "infer", 78.64),
     ("cfg4 S LoRA train b64 448", "facebook/dinov2-small", True, 64, 448, "train", 111.7),
+    # Dinov2PoseModel(unfreeze_last_n_layers=4) (reference config.py:48): fwd 16.04 + heads bwd 7.6 + 4 layers x
+    # (2 x 0.9095 GEMM + 2.5 x 0.1015 attention) GF
+    ("f4 S unfreeze4 train b64 224", "facebook/dinov2-small", False, 64, 224, "train", 31.9, 4),
 ]
 
 
@@ -39,12 +42,13 @@ def timed(fn, iters):
 
 def main():
     only = sys.argv[1:] or None
-    for name, arch, lora, B, res, mode, gflop in CONFIGS:
+    for name, arch, lora, B, res, mode, gflop, *rest in CONFIGS:
+        unfreeze = rest[0] if rest else 0
         if only and not any(o in name for o in only):
             continue
         torch.manual_seed(0)
         t0 = time.time()
-        m = (Dinov2PoseModelLoRA(backbone=arch) if lora else Dinov2PoseModel(backbone=arch)).to(dev)
+        m = (Dinov2PoseModelLoRA(backbone=arch) if lora else Dinov2PoseModel(backbone=arch, unfreeze_last_n_layers=unfreeze)).to(dev)
         batch = {k: v.to(dev) for k, v in make_inputs(B, res, res, 0).items()}
         if mode == "train":
             tr = PoseTrainer(m)

@@ -174,8 +174,8 @@ def test_unfrozen_layers_cuda_vs_emulated_op_graph():
         if not n.startswith("backbone."):
             continue
         a, b = grads[0][n].double(), grads[1][n].double()
-        if b.norm() < 1e-7:
-            assert a.norm() < 1e-5, n      # key bias: analytically zero
+        if n.endswith("attention.key.bias"):
+            assert a.norm() < 2e-5 and b.norm() < 2e-5, n      # analytically zero: bf16 rounding noise on both sides
             continue
         nb += 1
         rel = ((a - b).norm() / b.norm()).item()

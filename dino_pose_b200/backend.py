@@ -73,6 +73,14 @@ class Program:
         self.calls.append((None, "join", "stream"))
         self.meta.append({"name": "join", "kernel": "host:stream", "flops": 0.0, "bytes": 0.0})
 
+    def sync(self, which):
+        """Inside a fork: "side_wait" = the second stream waits for everything enqueued on the main stream so far (a
+        launch moved to the second stream depends on a main-stream producer); "main_wait" = the reverse (the fork stays
+        open).  No-ops outside a fork."""
+        assert which in ("side_wait", "main_wait")
+        self.calls.append((None, which, "stream"))
+        self.meta.append({"name": which, "kernel": "host:stream", "flops": 0.0, "bytes": 0.0})
+
     def add_callable(self, name, fn):
         """Host-side step (e.g. a torch op on static tensors) recorded in order with the launches."""
         self.calls.append((None, fn, name))
@@ -117,6 +125,12 @@ class Program:
                     if args == "fork":
                         side = self._side_stream
                         side.wait_stream(main)
+                    elif args == "side_wait":
+                        if side is not None:
+                            side.wait_stream(main)
+                    elif args == "main_wait":
+                        if side is not None:
+                            main.wait_stream(side)
                     elif side is not None:
                         main.wait_stream(side)
                         side = None
@@ -419,6 +433,9 @@ class CudaBackend:
 
     def join(self):
         self.prog.join()
+
+    def sync(self, which):
+        self.prog.sync(which)
 
     def pack_weights(self, jobs):
         """jobs: list of (dst bf16 tensor, w fp32 [d0,d1,kh,kw] parameter, order, flips, dst_strides|None): dst (viewed in

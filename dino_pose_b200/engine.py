@@ -19,6 +19,7 @@ block, LoRA adapter.  The backward program implements exactly that path; everyth
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -726,8 +727,25 @@ class PoseEngine:
             off, k = lay["offsets"][n]
             G[n] = flat[off:off + k].view(self.P[n].shape)
 
+        # Weight-gradient GEMMs depend only on (draw, saved activation) and nothing downstream needs them before the
+        # gradient buffer is handed over: they go to the second stream (opened below for the z head) and overlap the
+        # HBM-bound BatchNorm-backward / col2im kernels of the following layers on the main stream.  DP_BWD_OVERLAP=0
+        # keeps them in line (A/B switch).
+        overlap = bool(int(os.environ.get("DP_BWD_OVERLAP", "1")))
+
+        def wg(*a_, **k_):
+            if overlap:
+                be.sync("side_wait")
+                be.side(True)
+                be.wgrad(*a_, **k_)
+                be.side(False)
+            else:
+                be.wgrad(*a_, **k_)
+
         def done(key):
             # every gradient in flat[:group_end[key]] is final from here on
+            if overlap:
+                be.sync("main_wait")
             be.mark(("grads_final", lay["group_end"][key]))
         t["dhm"] = self.new(tuple(t["hm"].shape), F32)
         t["dz"] = self.new((B, K), F32)
@@ -782,7 +800,7 @@ class PoseEngine:
             P_in = B * L.ih * L.iw
             dx = None
             if L.kind == "conv" and k == 1:
-                be.wgrad(draw, x_in.reshape(P_in, ci), gw, Mc=co, Nc=ci, so_m=ci, so_n=1, P=P_out, name=L.name + ".wgrad",
+                wg(draw, x_in.reshape(P_in, ci), gw, Mc=co, Nc=ci, so_m=ci, so_n=1, P=P_out, name=L.name + ".wgrad",
                          workspace=ws)
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
@@ -795,10 +813,10 @@ class PoseEngine:
                     # few output channels (prediction.0: 128 -> 64): put the INPUT channels on the 128-row MMA side.
                     # dW[co,ci,ky,kx] = sum_q x[q,ci] * dRaw[q - (ky,kx) + pad, co]: the shift moves to the N operand
                     # with mirrored taps (tap' = kk-1-tap, pad' = k-1-pad), hence so_t = -1 from the last tap
-                    be.wgrad(x4, d4, gw.view(-1)[kk - 1:], Mc=ci, Nc=co, so_m=kk, so_n=ci * kk, so_t=-1,
+                    wg(x4, d4, gw.view(-1)[kk - 1:], Mc=ci, Nc=co, so_m=kk, so_n=ci * kk, so_t=-1,
                              conv=dict(KH=k, KW=k, pad=k - 1 - L.pad), block_n=64, name=L.name + ".wgrad", workspace=ws)
                 else:
-                    be.wgrad(d4, x4, gw, Mc=co, Nc=ci, so_m=ci * kk, so_n=kk, so_t=1, conv=dict(KH=k, KW=k, pad=L.pad),
+                    wg(d4, x4, gw, Mc=co, Nc=ci, so_m=ci * kk, so_n=kk, so_t=1, conv=dict(KH=k, KW=k, pad=L.pad),
                              name=L.name + ".wgrad", workspace=ws)
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
@@ -807,14 +825,14 @@ class PoseEngine:
             elif L.kind == "convT_s1":
                 x4 = x_in.view(B, L.ih, L.iw, ci)
                 d4 = draw.view(B, L.oh, L.ow, co)
-                be.wgrad(x4, d4, gw, Mc=ci, Nc=co, so_m=co * kk, so_n=kk, so_t=1, conv=dict(KH=k, KW=k, pad=L.pad),
+                wg(x4, d4, gw, Mc=ci, Nc=co, so_m=co * kk, so_n=kk, so_t=1, conv=dict(KH=k, KW=k, pad=L.pad),
                          name=L.name + ".wgrad", workspace=ws)
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
                     be.gemm(d4, L.t["wd"], dx, M=P_in, N=ci, K=kk * co, residual=dx_residual,
                             conv=dict(KH=k, KW=k, pad=L.pad, OH=L.ih, OW=L.iw), name=L.name + ".dgrad")
             elif L.kind == "conv_s2":
-                be.wgrad(draw, L.t["col"], gw, Mc=co, Nc=kk * ci, so_m=ci * kk, so_n=kk, so_no=1, n_inner=ci, P=P_out,
+                wg(draw, L.t["col"], gw, Mc=co, Nc=kk * ci, so_m=ci * kk, so_n=kk, so_no=1, n_inner=ci, P=P_out,
                          name=L.name + ".wgrad", workspace=ws)
                 if want_dx:
                     dcol = self.new((P_out, kk * ci), self.adt)
@@ -825,7 +843,7 @@ class PoseEngine:
             elif L.kind == "convT2":
                 # draw arrives in the un-shuffled [P_in, 4*Cout] layout (bn_bwd(..., shuffle=True))
                 dcol = draw.view(P_in, kk * co)
-                be.wgrad(x_in.reshape(P_in, ci), dcol, gw, Mc=ci, Nc=kk * co, so_m=co * kk, so_n=kk, so_no=1, n_inner=co,
+                wg(x_in.reshape(P_in, ci), dcol, gw, Mc=ci, Nc=kk * co, so_m=co * kk, so_n=kk, so_no=1, n_inner=co,
                          P=P_in, name=L.name + ".wgrad", workspace=ws)
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
@@ -834,7 +852,7 @@ class PoseEngine:
                 dcol = self.new((P_in, kk * co), self.adt)
                 be.im2col(draw, dcol, NB=B, IH=L.oh, IW=L.ow, C=co, OH=L.ih, OW=L.iw, KH=k, KW=k, stride=L.stride,
                           pad=L.pad)
-                be.wgrad(x_in.reshape(P_in, ci), dcol, gw, Mc=ci, Nc=kk * co, so_m=co * kk, so_n=kk, so_no=1, n_inner=co,
+                wg(x_in.reshape(P_in, ci), dcol, gw, Mc=ci, Nc=kk * co, so_m=co * kk, so_n=kk, so_no=1, n_inner=co,
                          P=P_in, name=L.name + ".wgrad", workspace=ws)
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
@@ -849,7 +867,7 @@ class PoseEngine:
         be.hm_grad_to_nhwc(t["dhm"], t["ghm"], NB=B, K=K, Kp=HM_PAD, OH=s48, OW=s48, up=up)
         L = Ls["pred3"]
         be.colsum(t["ghm"], G[L.name + ".bias"], P=P48, C=K, ld=HM_PAD)
-        be.wgrad(t["ghm"], a["pred0"], G[L.name + ".weight"], Mc=K, Nc=64, so_m=64, so_n=1, P=P48, block_n=64,
+        wg(t["ghm"], a["pred0"], G[L.name + ".weight"], Mc=K, Nc=64, so_m=64, so_n=1, P=P48, block_n=64,
                  name="pred3.wgrad", workspace=ws)
         d = self.new((P48, 64), self.adt)
         be.gemm(t["ghm"], L.t["wd"], d, M=P48, N=64, K=HM_PAD, name="pred3.dgrad")
@@ -929,6 +947,21 @@ class PoseEngine:
                 assert lay["offsets"][n] == (off0 + j * k0, k0), "q/k/v gradient slices must be contiguous"
             return flat[off0:off0 + len(names) * k0].view(shape)
 
+        # weight gradients on the second stream, the activation-gradient chain on the main one (see record_backward)
+        overlap = bool(int(os.environ.get("DP_BWD_OVERLAP", "1")))
+        if overlap:
+            be.fork()
+            be.side(False)
+
+        def wg(*a_, **k_):
+            if overlap:
+                be.sync("side_wait")
+                be.side(True)
+                be.wgrad(*a_, **k_)
+                be.side(False)
+            else:
+                be.wgrad(*a_, **k_)
+
         g = self.new((M, D), F32)              # dL/dx_out of the current layer
         gs = self.new((M, D), self.adt)        # bf16(g * layer_scale2)
         top = f"backbone.encoder.layer.{L - 1}."
@@ -947,11 +980,11 @@ class PoseEngine:
             # ---- MLP branch
             be.colsum_prod(g, s_["m"], G[lp + "layer_scale2.lambda1"], P=M, C=D)
             be.colsum(gs, G[lp + "mlp.fc2.bias"], P=M, C=D, ld=D)
-            be.wgrad(gs, s_["h"], G[lp + "mlp.fc2.weight"], Mc=D, Nc=4 * D, so_m=4 * D, so_n=1, P=M, name=f"fc2_{i}.wgrad",
+            wg(gs, s_["h"], G[lp + "mlp.fc2.weight"], Mc=D, Nc=4 * D, so_m=4 * D, so_n=1, P=M, name=f"fc2_{i}.wgrad",
                      workspace=ws)
             be.gemm(gs, w["w2T"], dpre, M=M, N=4 * D, K=D, aux_in=s_["pre"], ld_aux=4 * D, name=f"fc2_{i}.dgrad")
             be.colsum(dpre, G[lp + "mlp.fc1.bias"], P=M, C=4 * D, ld=4 * D)
-            be.wgrad(dpre, s_["xn2"], G[lp + "mlp.fc1.weight"], Mc=4 * D, Nc=D, so_m=D, so_n=1, P=M, name=f"fc1_{i}.wgrad",
+            wg(dpre, s_["xn2"], G[lp + "mlp.fc1.weight"], Mc=4 * D, Nc=D, so_m=D, so_n=1, P=M, name=f"fc1_{i}.wgrad",
                      workspace=ws)
             be.gemm(dpre, w["w1T"], dxn, M=M, N=D, K=4 * D, name=f"fc1_{i}.dgrad")
             be.layernorm_bwd_params(dxn, s_["x_mid"], G[lp + "norm2.weight"], G[lp + "norm2.bias"], rows=M, D=D, eps=LN_EPS)
@@ -960,13 +993,13 @@ class PoseEngine:
             # ---- attention branch
             be.colsum_prod(gmid, s_["a"], G[lp + "layer_scale1.lambda1"], P=M, C=D)
             be.colsum(gmids, G[ap + "output.dense.bias"], P=M, C=D, ld=D)
-            be.wgrad(gmids, s_["ctx"], G[ap + "output.dense.weight"], Mc=D, Nc=D, so_m=D, so_n=1, P=M, name=f"proj{i}.wgrad",
+            wg(gmids, s_["ctx"], G[ap + "output.dense.weight"], Mc=D, Nc=D, so_m=D, so_n=1, P=M, name=f"proj{i}.wgrad",
                      workspace=ws)
             be.gemm(gmids, w["woT"], dctx, M=M, N=D, K=D, name=f"proj{i}.dgrad")
             be.attention_bwd(s_["qkv"], s_["ctx"], dctx, dqkv, stats, B=B, T=T, heads=heads, scale=scale)
             qkv_names = [ap + f"attention.{n}." for n in ("query", "key", "value")]
             be.colsum(dqkv, gslice([n + "bias" for n in qkv_names], (3 * D,)), P=M, C=3 * D, ld=3 * D)
-            be.wgrad(dqkv, s_["xn1"], gslice([n + "weight" for n in qkv_names], (3 * D, D)), Mc=3 * D, Nc=D, so_m=D, so_n=1,
+            wg(dqkv, s_["xn1"], gslice([n + "weight" for n in qkv_names], (3 * D, D)), Mc=3 * D, Nc=D, so_m=D, so_n=1,
                      P=M, name=f"qkv{i}.wgrad", workspace=ws)
             be.gemm(dqkv, w["wqkvT"], dxn, M=M, N=D, K=3 * D, name=f"qkv{i}.dgrad")
             be.layernorm_bwd_params(dxn, s_["x_in"], G[lp + "norm1.weight"], G[lp + "norm1.bias"], rows=M, D=D, eps=LN_EPS)
@@ -974,7 +1007,11 @@ class PoseEngine:
                 below = f"backbone.encoder.layer.{i - 1}."
                 be.layernorm_bwd(dxn, s_["x_in"], self.p(lp + "norm1.weight"), gmid, g, rows=M, D=D, eps=LN_EPS,
                                  ls=self.p(below + "layer_scale2.lambda1"), dx_scaled=gs)
+            if overlap:
+                be.sync("main_wait")
             done(f"layer{i}")
+        if overlap:
+            be.join()
         be.mark(("grads_final", lay["total"]))
 
     # ------------------------------------------------------------------ running

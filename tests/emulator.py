@@ -52,6 +52,9 @@ class TorchEmulator:
     def join(self):
         pass
 
+    def sync(self, which):
+        pass
+
     def mark(self, tag):
         self.prog.calls.append(("mark", tag))
 

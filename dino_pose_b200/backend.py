@@ -54,37 +54,41 @@ class Program:
                           "launches": launches, "side": self._side})
         self.keep.extend(keep)
 
-    # ---- fork / join: launches recorded between ``fork()`` ... ``side(False)`` go to a second stream and run
-    # concurrently with what follows on the main stream until ``join()`` (small-grid chains such as the z-head MLP or
-    # the weight re-packing overlap the tensor-core kernels).  Program order stays a valid serial order: ``run_timed``
-    # and ``run_family`` simply ignore the fork.
+    # ---- fork / join: launches recorded between ``fork(k)`` ... ``side(False)`` go to side stream k (1 or 2) and run
+    # concurrently with what follows on the main stream until ``join(k)`` (small-grid chains such as the z-head MLP, the
+    # weight re-packing or the hourglass' 4x4 / 8x8 layers overlap the tensor-core kernels; weight-gradient GEMMs
+    # overlap the HBM-bound BatchNorm backward).  ``side(k)`` switches the recording stream while a fork is open and
+    # ``sync`` adds a one-way dependency without closing it.  Program order stays a valid serial order: ``run_timed``
+    # and ``run_family`` simply ignore the streams.
     _side = False
 
-    def fork(self):
-        self.calls.append((None, "fork", "stream"))
-        self.meta.append({"name": "fork", "kernel": "host:stream", "flops": 0.0, "bytes": 0.0})
-        self._side = True
+    def _stream_op(self, op, k, src=0):
+        self.calls.append((None, (op, int(k), int(src)), "stream"))
+        self.meta.append({"name": op, "kernel": "host:stream", "flops": 0.0, "bytes": 0.0})
+
+    def fork(self, k=1):
+        self._stream_op("fork", k)
+        self._side = int(k)
 
     def side(self, flag):
-        self._side = bool(flag)
+        """False / 0: record on the main stream; True / 1 / 2: on that (open) side stream."""
+        self._side = int(flag)
 
-    def join(self):
+    def join(self, k=1):
         self._side = False
-        self.calls.append((None, "join", "stream"))
-        self.meta.append({"name": "join", "kernel": "host:stream", "flops": 0.0, "bytes": 0.0})
+        self._stream_op("join", k)
 
-    def sync(self, which):
-        """Inside a fork: "side_wait" = the second stream waits for everything enqueued on the main stream so far (a
-        launch moved to the second stream depends on a main-stream producer); "main_wait" = the reverse (the fork stays
-        open).  No-ops outside a fork."""
+    def sync(self, which, k=1, src=0):
+        """Inside fork k: "side_wait" = side stream k waits for everything enqueued so far on the main stream (src = 0) or
+        on the open side stream `src` (a launch moved to stream k depends on a producer there); "main_wait" = the main
+        stream waits for side stream k (the fork stays open).  No-ops outside a fork."""
         assert which in ("side_wait", "main_wait")
-        self.calls.append((None, which, "stream"))
-        self.meta.append({"name": which, "kernel": "host:stream", "flops": 0.0, "bytes": 0.0})
+        self._stream_op(which, k, src)
 
     def add_callable(self, name, fn):
         """Host-side step (e.g. a torch op on static tensors) recorded in order with the launches."""
         self.calls.append((None, fn, name))
-        self.meta.append({"name": name, "kernel": "host:" + name, "flops": 0.0, "bytes": 0.0})
+        self.meta.append({"name": name, "kernel": "host:" + name, "flops": 0.0, "bytes": 0.0, "side": self._side})
 
     def add_mark(self, tag):
         """A named point in the program (e.g. "gradients up to offset N are final"); ``run(on_mark=f)`` calls
@@ -113,37 +117,44 @@ class Program:
     def run(self, on_mark=None):
         main = torch.cuda.current_stream()
         stream = main.cuda_stream
-        side = None
+        sides = {}            # open forks: k -> stream
         for (fn, args, name), meta in zip(self.calls, self.meta):
             if fn is None:
                 if name == "mark":
                     if on_mark is not None:
                         on_mark(args)
                 elif name == "stream":
-                    if self._side_stream is None or self._side_stream.device != main.device:
-                        self._side_stream = torch.cuda.Stream(device=main.device)
-                    if args == "fork":
-                        side = self._side_stream
-                        side.wait_stream(main)
-                    elif args == "side_wait":
-                        if side is not None:
-                            side.wait_stream(main)
-                    elif args == "main_wait":
-                        if side is not None:
-                            main.wait_stream(side)
-                    elif side is not None:
-                        main.wait_stream(side)
-                        side = None
+                    op, k, src = args
+                    if op == "fork":
+                        pool = self._side_streams.setdefault(main.device, {})
+                        if k not in pool:
+                            pool[k] = torch.cuda.Stream(device=main.device)
+                        sides[k] = pool[k]
+                        sides[k].wait_stream(main)
+                    elif k in sides:
+                        if op == "side_wait":
+                            sides[k].wait_stream(sides[src] if (src and src in sides) else main)
+                        elif op == "main_wait":
+                            main.wait_stream(sides[k])
+                        else:   # join
+                            main.wait_stream(sides.pop(k))
                 else:
-                    args()
+                    sk = meta.get("side")
+                    if sk and sk in sides:      # host-side torch step recorded inside a fork: same stream as its consumers
+                        with torch.cuda.stream(sides[sk]):
+                            args()
+                    else:
+                        args()
                 continue
-            rc = fn(*args, side.cuda_stream if (side is not None and meta.get("side")) else stream)
+            sk = meta.get("side")
+            rc = fn(*args, sides[sk].cuda_stream if (sk and sk in sides) else stream)
             if rc != 0:
                 _lib.check(rc, name)
-        if side is not None:     # a fork without a join: never leave work dangling on the second stream
-            main.wait_stream(side)
+        for st in sides.values():     # a fork without a join: never leave work dangling on a side stream
+            main.wait_stream(st)
 
-    _side_stream = None
+    _side_streams = {}
+
 
     def run_timed(self):
         """Replay with a CUDA event pair around every launch (on the launching stream); returns a list of
@@ -425,17 +436,17 @@ class CudaBackend:
     def mark(self, tag):
         self.prog.add_mark(tag)
 
-    def fork(self):
-        self.prog.fork()
+    def fork(self, k=1):
+        self.prog.fork(k)
 
     def side(self, flag):
         self.prog.side(flag)
 
-    def join(self):
-        self.prog.join()
+    def join(self, k=1):
+        self.prog.join(k)
 
-    def sync(self, which):
-        self.prog.sync(which)
+    def sync(self, which, k=1, src=0):
+        self.prog.sync(which, k, src)
 
     def pack_weights(self, jobs):
         """jobs: list of (dst bf16 tensor, w fp32 [d0,d1,kh,kw] parameter, order, flips, dst_strides|None): dst (viewed in

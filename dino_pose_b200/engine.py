@@ -403,10 +403,20 @@ class PoseEngine:
                 row_map="patch_tokens", map_a=N, map_b=T, name="patch_embed")
         scale = 1.0 / math.sqrt(D // heads)
         sv = plan["saved"] = {}      # per un-frozen layer: everything its backward reads
+        # DP_SPLIT_BATCH=1 switches the two-stream backbone on (A/B); DP_SPLIT_MIN_BATCH lowers the batch threshold (tests)
+        # Measured (gpurun_out/ab3): ViT-S step 3.974 -> 3.944 ms, ViT-B step and ViT-L inference 1-5 % SLOWER (half-size GEMMs
+        # lose more to wave quantisation than the overlap returns) -> off by default
+        split = bool(int(os.environ.get("DP_SPLIT_BATCH", "0"))) and B >= int(os.environ.get("DP_SPLIT_MIN_BATCH", "8"))
+        B0 = B // 2
+        halves = ((0, B0 * T, B0), (B0 * T, M, B - B0))
+        split_open = False
         x_cur = t["x"]               # residual stream entering the current layer
         for i in range(L):
             lp = f"backbone.encoder.layer.{i}."
             last = i == L - 1
+            if i in lw and split_open:
+                be.sync("main_wait")
+                split_open = False
             if i in lw:
                 # ---- un-frozen layer (reference model/dinov2_pose.py:25-39): same arithmetic, weights from the per-step
                 # packed copies; in training every intermediate the backward needs gets its own buffer
@@ -437,6 +447,33 @@ class PoseEngine:
                         name=f"fc2_{i}")
                 x_cur = s_["x_out"]
                 continue
+            if split and not (last and (use_lora or training)):
+                # ---- frozen layer, two half-batches on two streams: the HBM-bound LayerNorms and the MUFU-bound attention
+                # of one half overlap the tensor-bound GEMMs of the other (images are independent in the backbone)
+                if not split_open:
+                    be.sync("side_wait")          # second stream: wait for the embeddings
+                    split_open = True
+                for hb, (r0, r1, Bh) in enumerate(halves):
+                    be.side(hb == 1)
+                    xs_, xn_, qkv_, ctx_, h_ = (t[k][r0:r1] for k in ("x", "xn", "qkv", "ctx", "h"))
+                    Mh = r1 - r0
+                    be.layernorm_fwd(xs_, self.p(lp + "norm1.weight"), self.p(lp + "norm1.bias"), xn_, None, rows=Mh, D=D,
+                                     eps=LN_EPS)
+                    be.gemm(xn_, fz[f"wqkv{i}"], qkv_, M=Mh, N=3 * D, K=D, bias=fz[f"bqkv{i}"], name=f"qkv{i}")
+                    be.attention_fwd(qkv_, ctx_, B=Bh, T=T, heads=heads, scale=scale)
+                    be.gemm(ctx_, fz[f"wo{i}"], xs_, M=Mh, N=D, K=D, bias=fz[f"bo{i}"], out_dtype="f32",
+                            ls=self.p(lp + "layer_scale1.lambda1"), residual=xs_, name=f"proj{i}")
+                    be.layernorm_fwd(xs_, self.p(lp + "norm2.weight"), self.p(lp + "norm2.bias"), xn_, None, rows=Mh, D=D,
+                                     eps=LN_EPS)
+                    be.gemm(xn_, fz[f"w1{i}"], h_, M=Mh, N=4 * D, K=D, bias=self.p(lp + "mlp.fc1.bias"), act="gelu",
+                            name=f"fc1_{i}", block_n=192 if (4 * D) % 192 == 0 else 0)
+                    be.gemm(h_, fz[f"w2{i}"], xs_, M=Mh, N=D, K=4 * D, bias=self.p(lp + "mlp.fc2.bias"), out_dtype="f32",
+                            ls=self.p(lp + "layer_scale2.lambda1"), residual=xs_, name=f"fc2_{i}")
+                be.side(False)
+                continue
+            if split_open:
+                be.sync("main_wait")              # both halves done: the remaining layers run on the whole batch
+                split_open = False
             be.layernorm_fwd(t["x"], self.p(lp + "norm1.weight"), self.p(lp + "norm1.bias"), t["xn"], None, rows=M, D=D,
                              eps=LN_EPS)
             be.gemm(t["xn"], fz[f"wqkv{i}"], t["qkv"], M=M, N=3 * D, K=D, bias=fz[f"bqkv{i}"], name=f"qkv{i}")
@@ -470,6 +507,8 @@ class PoseEngine:
             x_out = t["x_last"] if (last and training) else t["x"]
             be.gemm(t["h"], fz[f"w2{i}"], x_out, M=M, N=D, K=4 * D, bias=self.p(lp + "mlp.fc2.bias"), out_dtype="f32",
                     ls=self.p(lp + "layer_scale2.lambda1"), residual=x_att, name=f"fc2_{i}")
+        if split_open:
+            be.sync("main_wait")
         x_fin = t["x_last"] if training else t["x"]
         plan["x_final"] = x_fin
         be.layernorm_fwd(x_fin, self.p("backbone.layernorm.weight"), self.p("backbone.layernorm.bias"), t["feat"], None,
@@ -655,22 +694,31 @@ class PoseEngine:
 
         a1 = unit("fr0", feat4)
         a1_4 = a1.view(B, g, g, 512)
+        # The hourglass has three independent branches (pose_heads.py:268-285).  The down/up branch is a chain of small
+        # launches on 8x8 / 4x4 maps (a handful of CTAs each, latency bound): it runs on side stream 2 underneath the
+        # skip and depthwise branches and is joined before the 3-way sum.  DP_HG_STREAMS=0 keeps it in line (A/B).
+        hg2 = bool(int(os.environ.get("DP_HG_STREAMS", "1")))
+        plan["hg2"] = hg2
         if training:
-            unit("skip", a1)
-            unit("dw", a1_4)
-            unit("pw", a["dw"])
+            if hg2:
+                be.fork(2)
             unit("down1", a1_4)
             unit("down2", a["down1"].view(B, g // 2, g // 2, 256))
             unit("bt1", a["down2"].view(B, g // 4, g // 4, 128))
             unit("bt2", a["bt1"].view(B, g // 4, g // 4, 128), add1=a["down2"], mode=1)
             unit("up1", a["bt2"])
+            be.side(False)
+            unit("skip", a1)
+            unit("dw", a1_4)
+            unit("pw", a["dw"])
+            if hg2:
+                be.join(2)
             # hourglass output = up2 + skip + depthwise branch (pose_heads.py:285), fused into up2's BN apply
             unit("up2", a["up1"], add1=a["skip"], add2=a["pw"])
             hgout = a["up2"]
         else:
-            unit("skip", a1)
-            unit("dw", a1_4)
-            unit("pw", a["dw"])
+            if hg2:
+                be.fork(2)
             unit("down1", a1_4)
             unit("down2", a["down1"].view(B, g // 2, g // 2, 256))
             unit("bt1", a["down2"].view(B, g // 4, g // 4, 128))
@@ -683,6 +731,12 @@ class PoseEngine:
             be.bn_apply(bt2, L.t["one"], L.t["zero"], a["down2"], None, a["bt2r"], P=bt2.shape[0], C=L.cout, relu=True, mode=1)
             unit("up1", a["bt2r"])
             up2 = unit("up2", a["up1"])
+            be.side(False)
+            unit("skip", a1)
+            unit("dw", a1_4)
+            unit("pw", a["dw"])
+            if hg2:
+                be.join(2)
             L2 = Ls["up2"]
             L2.t["one"] = self.new((L2.cout,), F32, 1.0)
             L2.t["zero"] = self.new((L2.cout,), F32)
@@ -733,8 +787,13 @@ class PoseEngine:
         # keeps them in line (A/B switch).
         overlap = bool(int(os.environ.get("DP_BWD_OVERLAP", "1")))
 
+        chain = {"ws": None}     # set while the hourglass' down/up branch is being recorded on side stream 2
+
         def wg(*a_, **k_):
-            if overlap:
+            if chain["ws"] is not None:
+                k_["workspace"] = chain["ws"]
+                be.wgrad(*a_, **k_)
+            elif overlap:
                 be.sync("side_wait")
                 be.side(True)
                 be.wgrad(*a_, **k_)
@@ -876,7 +935,13 @@ class PoseEngine:
         d = conv_bwd("ups0", bn_bwd("ups0", d), a["fr4"])
         d_hg = conv_bwd("fr4", bn_bwd("fr4", d), plan["hgout"])
         done("fr4")
-        # ---- hourglass (three consumers of d_hg: up2, skip, depthwise branch)
+        # ---- hourglass (three consumers of d_hg: up2, skip, depthwise branch).  As in the forward, the down/up branch (a
+        # latency-bound chain of ~25 small launches) runs on side stream 2, its weight gradients in line with their own
+        # split-K workspace; the depthwise and skip branches proceed on the main stream and need its result (d_a1) last.
+        hg2 = plan.get("hg2", False)
+        if hg2:
+            be.fork(2)
+            chain["ws"] = t["wgrad_ws2"] = self.new((8 << 20,), F32)
         d = conv_bwd("up2", bn_bwd("up2", d_hg, shuffle=True), a["up1"])
         d = conv_bwd("up1", bn_bwd("up1", d, shuffle=True), a["bt2"])
         P4 = B * (g // 4) ** 2
@@ -885,16 +950,21 @@ class PoseEngine:
         d = conv_bwd("bt1", bn_bwd("bt1", d), a["down2"], dx_residual=dres)
         d = conv_bwd("down2", bn_bwd("down2", d), a["down1"])
         d_a1 = conv_bwd("down1", bn_bwd("down1", d), a["fr0"])
-        done("down1")
+        chain["ws"] = None
+        be.side(False)
         # depthwise branch
         d = conv_bwd("pw", bn_bwd("pw", d_hg), a["dw"])
         ddw = bn_bwd("dw", d)
         Ldw = Ls["dw"]
         be.dwconv3x3_wgrad(a["fr0"], ddw, G[Ldw.name + ".weight"], NB=B, H=g, W=g, C=512)
+        dskip = bn_bwd("skip", d_hg)
+        if hg2:
+            be.join(2)
+        done("down1")
         d_a1b = self.new((B * g * g, 512), self.adt)
         be.dwconv3x3(ddw, self.p(Ldw.name + ".weight"), None, d_a1, d_a1b, NB=B, H=g, W=g, C=512, flip=True)
         # skip branch, accumulating into the running gradient of a1
-        d_a1c = conv_bwd("skip", bn_bwd("skip", d_hg), a["fr0"], dx_residual=d_a1b)
+        d_a1c = conv_bwd("skip", dskip, a["fr0"], dx_residual=d_a1b)
         dfeat = conv_bwd("fr0", bn_bwd("fr0", d_a1c), t["feat"].view(B, g, g, D))
         done("fr0")
         be.join()                # z-head chain (second stream): its input gradient dcur is needed now

@@ -43,16 +43,16 @@ class TorchEmulator:
     def host(self, name, fn):
         self.prog.calls.append(fn)
 
-    def fork(self):          # stream fork / join of the CUDA backend: the emulator runs everything in program order
+    def fork(self, k=1):     # stream fork / join of the CUDA backend: the emulator runs everything in program order
         pass
 
     def side(self, flag):
         pass
 
-    def join(self):
+    def join(self, k=1):
         pass
 
-    def sync(self, which):
+    def sync(self, which, k=1, src=0):
         pass
 
     def mark(self, tag):

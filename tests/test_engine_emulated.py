@@ -146,6 +146,21 @@ def test_unfrozen_layers_eval_uses_current_weights():
     assert relmax(hm1, rhm) < 2e-2
 
 
+def test_two_stream_half_batch_backbone_is_the_same_program(monkeypatch):
+    """DP_SPLIT_BATCH=1: the frozen layers run as two half-batches on two streams (engine.build_plan): same arithmetic, so
+    the emulated result must be bit-identical to the single-stream program (odd batch: halves of 1 and 2 images)."""
+    arch = "test/dinov2-tiny"
+    inp = make_inputs(3, 224, 224, 4)
+    outs = []
+    monkeypatch.setenv("DP_SPLIT_BATCH", "1")
+    for min_batch in ("2", "100"):
+        monkeypatch.setenv("DP_SPLIT_MIN_BATCH", min_batch)
+        m = build(arch, 8).eval()
+        with torch.no_grad():
+            outs.append(m(inp["pixel_values"]))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+
+
 def test_448_eval_matches_oracle():
     arch = "test/dinov2-tiny"
     m = build(arch, 0).eval()

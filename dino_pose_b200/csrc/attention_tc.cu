@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) attention_tc_kernel(const __grid_
 //   * the 257th QUERY is computed entirely on the CUDA cores by the otherwise idle warp 1 of the second tile's CTA.
 // Shared memory is re-used inside the tile: P (4 tiles of 64 keys) overwrites K (dead after the S-MMA, tiles 0-1) and
 // Q (tile 2); O overwrites TMEM columns [0, 64) of S.
-constexpr int kSmem257 = 6 * kTileBytes + 1024;   // K0 K1 V0 V1 Q P3 + extra rows / barriers
+constexpr int kSmem257 = 6 * kTileBytes + 1024 + 2048 + 2048;   // K0 K1 V0 V1 Q P3 + extra rows / barriers + max / sum exchange + extra-query scores
 
 struct Attn257Params {
   CUtensorMap tm;
@@ -271,6 +271,23 @@ struct Attn257Params {
   int D, heads;
   float scale_log2;
 };
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
 
 __device__ __forceinline__ void unpack8_bf16(const uint4& t, float (&f)[8]) {
   const uint32_t w[4] = {t.x, t.y, t.z, t.w};
@@ -282,7 +299,12 @@ __device__ __forceinline__ void unpack8_bf16(const uint4& t, float (&f)[8]) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 2) attention_tc257_kernel(const __grid_constant__ Attn257Params p) {
+// HALVES = 2: EIGHT softmax warps, two threads per query row (keys [0,128) and [128,256)); the row maximum is exchanged
+// through shared memory between the two passes, the row sum before the epilogue (each half normalises and stores 32 of
+// the 64 output dims).  The per-thread serial chain -- the exposed phase in the timeline of the HALVES = 1 version --
+// halves, and the SM holds 16 instead of 8 warps that issue MUFU / FMA work.
+template <int HALVES>
+__global__ void __launch_bounds__(64 + 128 * HALVES, 2) attention_tc257_kernel(const __grid_constant__ Attn257Params p) {
   constexpr int T = 257;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;                          // 2 tiles; later P tiles 0, 1
@@ -299,6 +321,10 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc257_kernel(const __gr
   uint64_t* p_ready = bars + 3;
   uint64_t* o_full = bars + 4;
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 5);
+  float* ex_max = reinterpret_cast<float*>(sP3 + kTileBytes + 1024);   // [2 halves][128 rows]
+  float* ex_sum = ex_max + 256;                                          // [2 halves][128 rows]
+  float* xs = ex_sum + 256;                                              // scores of the extra query row [256 + pad]
+  __nv_bfloat16* xp = reinterpret_cast<__nv_bfloat16*>(xs + 272);        // its unnormalised probabilities [256]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x & 1;
@@ -312,7 +338,7 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc257_kernel(const __gr
     mbar_init(ld_full, 1);
     mbar_init(s_full, 1);
     mbar_init(k_free, 1);
-    mbar_init(p_ready, 4);
+    mbar_init(p_ready, 4 * HALVES);
     mbar_init(o_full, 1);
     fence_barrier_init();
     pdl_grid_sync();   // programmatic dependent launch: every thread passes this before its first global-memory access
@@ -374,40 +400,63 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc257_kernel(const __gr
     if (qt == 0) {
       if (lane == 0) mbar_arrive(k_free);
     } else {
-      // ---- query row 256 on the CUDA cores.  Lane owns keys j = lane + 32*i (i < 8) and, on lane 0, key 256.
-      float qr[64];
-#pragma unroll
-      for (int e = 0; e < 64; ++e) qr[e] = xq[e];
+      // ---- query row 256 with warp-level MMAs (mma.sync m16n8k16: a 16-row A tile whose row 0 is q_256, the other 15
+      // rows zero).  The first version did this row with FMAs on the CUDA cores (2 x 257 x 64 MACs by one warp): under
+      // the issue pressure of the softmax warps it finished at 19 k cycles against 13.8 k for the rest of the tile
+      // (DP_ATTN_TRACE), i.e. it set the lifetime of every second CTA.
       mbar_wait(ld_full, 0);
+      const bool g0 = (lane >> 2) == 0;             // lanes 0..3 own row 0 of the A / accumulator fragments
+      const int c2 = 2 * (lane & 3);
+      const uint32_t k_addr = smem_u32(sK), v_addr = smem_u32(sV);
       const float sl = p.scale_log2;
-      float sc[9];
+      uint32_t qa0[4], qa2[4];
 #pragma unroll
-      for (int i = 0; i < 9; ++i) sc[i] = 0.f;
-      // chunk-outer / key-inner: 8 independent FMA chains (one per key) instead of one 64-long chain per key
+      for (int ks = 0; ks < 4; ++ks) {
+        qa0[ks] = g0 ? pack_bf16x2(xq[ks * 16 + c2], xq[ks * 16 + c2 + 1]) : 0u;
+        qa2[ks] = g0 ? pack_bf16x2(xq[ks * 16 + 8 + c2], xq[ks * 16 + 8 + c2 + 1]) : 0u;
+      }
+      // pass 1: scores of the 256 tile keys, 64 at a time, row 0 parked in shared memory
+#pragma unroll 1
+      for (int kc = 0; kc < 4; ++kc) {
+        float sacc[8][4];
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        uint4 kv[8];
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = lane + 32 * i;
-          kv[i] = *reinterpret_cast<const uint4*>(sK + (j >> 7) * kTileBytes + (j & 127) * 128 + ((c ^ (j & 7)) << 4));
+          for (int j = 0; j < 4; ++j) sacc[i][j] = 0.f;
+        const uint32_t tile = k_addr + (kc >> 1) * kTileBytes;
+        const int rbase = (kc & 1) * 64;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t af[4] = {qa0[ks], 0u, qa2[ks], 0u};
+#pragma unroll
+          for (int nb = 0; nb < 8; nb += 2) {
+            const int m = lane >> 3;
+            const int row = rbase + (nb + (m >> 1)) * 8 + (lane & 7);
+            const int chunk = ks * 2 + (m & 1);
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(tile + row * 128 + ((chunk ^ (lane & 7)) << 4), b0, b1, b2, b3);
+            mma_bf16(sacc[nb], af, b0, b1);
+            mma_bf16(sacc[nb + 1], af, b2, b3);
+          }
         }
+        if (g0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float f[8];
-          unpack8_bf16(kv[i], f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) sc[i] = fmaf(f[e], qr[c * 8 + e], sc[i]);
+          for (int nb = 0; nb < 8; ++nb)
+            *reinterpret_cast<float2*>(xs + kc * 64 + nb * 8 + c2) = make_float2(sacc[nb][0], sacc[nb][1]);
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(k_free);   // K has been read: the softmax warps may overwrite it with P
       if (tr && lane == 0) tr[12] = clock64();
+      // softmax over the 257 scores: lane owns keys lane + 32*i (i < 8), lane 0 also key 256
+      float sc[9];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sc[i] = xs[lane + 32 * i];
       {
         float acc = 0.f;
 #pragma unroll
-        for (int e = 0; e < 64; ++e) acc = fmaf(xk[e], qr[e], acc);
-        sc[8] = (lane == 0) ? acc : -INFINITY;   // key 256
+        for (int e = 0; e < 64; ++e) acc = fmaf(xk[e], xq[e], acc);
+        sc[8] = (lane == 0) ? acc : -INFINITY;
       }
       float m = sc[0];
 #pragma unroll
@@ -422,66 +471,135 @@ __global__ void __launch_bounds__(kThreads, 2) attention_tc257_kernel(const __gr
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-      // partial O over this lane's keys, all 64 dims in registers (re-using qr), then a recursive-halving reduction
-      // over the lanes: after the step with offset `o` a lane keeps `o * 2` of its dims, at the end 2 dims per lane
+      const float px = __shfl_sync(0xffffffffu, sc[8], 0);
 #pragma unroll
-      for (int e = 0; e < 64; ++e) qr[e] = (lane == 0) ? sc[8] * xv[e] : 0.f;
+      for (int i = 0; i < 8; ++i) xp[lane + 32 * i] = __float2bfloat16_rn(sc[i]);
+      __syncwarp();
+      // pass 2: O = P V, 16 keys per step
+      float oacc[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
+#pragma unroll 4
+      for (int kk = 0; kk < 16; ++kk) {
+        uint32_t af[4] = {0u, 0u, 0u, 0u};
+        if (g0) {
+          af[0] = *reinterpret_cast<const uint32_t*>(xp + kk * 16 + c2);
+          af[2] = *reinterpret_cast<const uint32_t*>(xp + kk * 16 + 8 + c2);
+        }
+        const uint32_t tile = v_addr + (kk >> 3) * kTileBytes;
+        const int rbase = (kk & 7) * 16;
+#pragma unroll
+        for (int nb = 0; nb < 8; nb += 2) {
+          const int mm = lane >> 3;
+          const int row = rbase + (mm & 1) * 8 + (lane & 7);
+          const int chunk = nb + (mm >> 1);
+          uint32_t b0, b1, b2, b3;
+          ldsm_x4_t(tile + row * 128 + ((chunk ^ (lane & 7)) << 4), b0, b1, b2, b3);
+          mma_bf16(oacc[nb], af, b0, b1);
+          mma_bf16(oacc[nb + 1], af, b2, b3);
+        }
+      }
+      if (g0) {
+        const float inv = 1.0f / sum;
+        __nv_bfloat16* dst = p.ctx + (long long)(row0 + 256) * p.D + h * kDh;
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          const int d = nb * 8 + c2;
+          *reinterpret_cast<uint32_t*>(dst + d) =
+              pack_bf16x2(fmaf(px, xv[d], oacc[nb][0]) * inv, fmaf(px, xv[d + 1], oacc[nb][1]) * inv);
+        }
+      }
+    }
+  } else if constexpr (HALVES == 2) {
+    const int q = warp & 3;                 // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;       // 0: keys [0,128) -> P tiles 0, 1 (over K);  1: keys [128,256) -> P tiles 2, 3
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
+    const float sl = p.scale_log2;
+    mbar_wait(s_full, 0);
+    tc_fence_after();
+    if (tr && threadIdx.x == 64) tr[2] = clock64();
+    float sx = 0.f;
+    {
+      const uint8_t* qrow = sQ + r * 128;
 #pragma unroll
       for (int c = 0; c < 8; ++c) {
-        uint4 vv[8];
+        float f[8];
+        unpack8_bf16(*reinterpret_cast<const uint4*>(qrow + ((c ^ (r & 7)) << 4)), f);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int j = lane + 32 * i;
-          vv[i] = *reinterpret_cast<const uint4*>(sV + (j >> 7) * kTileBytes + (j & 127) * 128 + ((c ^ (j & 7)) << 4));
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float f[8];
-          unpack8_bf16(vv[i], f);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) qr[c * 8 + e] = fmaf(sc[i], f[e], qr[c * 8 + e]);
-        }
+        for (int e = 0; e < 8; ++e) sx = fmaf(f[e], xk[c * 8 + e], sx);
       }
-      // halving: with offset 16 the lower half-warp keeps dims [0,32), the upper [32,64); and so on
+    }
+    float m = sx;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = 2 * half + cc;
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(trow + uint32_t(c * 64), v0);
+      tmem_ld_32x32(trow + uint32_t(c * 64 + 32), v1);
+      tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 32; ++e) {
-        const bool up = (lane & 16) != 0;
-        const float send = up ? qr[e] : qr[32 + e];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 16);
-        qr[e] = (up ? qr[32 + e] : qr[e]) + recv;
-      }
+      for (int j = 0; j < 32; ++j) m = fmaxf(m, fmaxf(__uint_as_float(v0[j]), __uint_as_float(v1[j])));
+    }
+    ex_max[half * 128 + r] = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // the 8 softmax warps: maxima exchanged, every read of the Q tile done
+    m = fmaxf(m, ex_max[(half ^ 1) * 128 + r]);
+    const float ms = m * sl;
+    const float px = ex2_approx(fmaf(sx, sl, -ms));
+    float sum = half == 0 ? px : 0.f;
+    if (tr && threadIdx.x == 64) tr[3] = clock64();
+    if (half == 0) {
+      if (tr && threadIdx.x == 64) tr[4] = clock64();
+      mbar_wait(k_free, 0);     // P tiles 0, 1 overwrite K, which the extra-query warp may still be reading
+      if (tr && threadIdx.x == 64) tr[5] = clock64();
+    }
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c = 2 * half + cc;
+      uint32_t v0[32], v1[32];
+      tmem_ld_32x32(trow + uint32_t(c * 64), v0);
+      tmem_ld_32x32(trow + uint32_t(c * 64 + 32), v1);
+      tmem_ld_wait();
+      uint8_t* tile = (c < 2 ? sK + c * kTileBytes : (c == 2 ? sQ : sP3)) + r * 128;
+      float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-      for (int e = 0; e < 16; ++e) {
-        const bool up = (lane & 8) != 0;
-        const float send = up ? qr[e] : qr[16 + e];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 8);
-        qr[e] = (up ? qr[16 + e] : qr[e]) + recv;
-      }
+      for (int g = 0; g < 8; ++g) {
+        const uint32_t* v = g < 4 ? v0 + g * 8 : v1 + (g - 4) * 8;
+        float e[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const bool up = (lane & 4) != 0;
-        const float send = up ? qr[e] : qr[8 + e];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 4);
-        qr[e] = (up ? qr[8 + e] : qr[e]) + recv;
+        for (int j = 0; j < 8; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(v[j]), sl, -ms));
+        s0 += (e[0] + e[1]) + (e[2] + e[3]);
+        s1 += (e[4] + e[5]) + (e[6] + e[7]);
+        *reinterpret_cast<uint4*>(tile + ((g ^ (r & 7)) << 4)) =
+            make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]), pack_bf16x2(e[6], e[7]));
       }
+      sum += s0 + s1;
+    }
+    ex_sum[half * 128 + r] = sum;     // read by the other half after o_full (ordered through p_ready -> MMA -> o_full)
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(p_ready);
+    if (tr && threadIdx.x == 64) tr[7] = clock64();
+    mbar_wait(o_full, 0);
+    tc_fence_after();
+    if (tr && threadIdx.x == 64) tr[8] = clock64();
+    sum += ex_sum[(half ^ 1) * 128 + r];
+    const float inv = 1.0f / sum;
+    __nv_bfloat16* dst = p.ctx + (long long)(row0 + qt * kTile + r) * p.D + h * kDh + half * 32;
+    uint32_t v0[32];
+    tmem_ld_32x32(trow + uint32_t(half * 32), v0);
+    tmem_ld_wait();
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const bool up = (lane & 2) != 0;
-        const float send = up ? qr[e] : qr[4 + e];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 2);
-        qr[e] = (up ? qr[4 + e] : qr[e]) + recv;
-      }
+    for (int g = 0; g < 4; ++g) {
+      const uint32_t* v = v0 + g * 8;
+      float o[8];
 #pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const bool up = (lane & 1) != 0;
-        const float send = up ? qr[e] : qr[2 + e];
-        const float recv = __shfl_xor_sync(0xffffffffu, send, 1);
-        qr[e] = (up ? qr[2 + e] : qr[e]) + recv;
-      }
-      // lane now holds dims d0, d0 + 1 with d0 = 32*b4 + 16*b3 + 8*b2 + 4*b1 + 2*b0 (b_k = bit k of the lane id)
-      const int d0 = ((lane >> 4) & 1) * 32 + ((lane >> 3) & 1) * 16 + ((lane >> 2) & 1) * 8 + ((lane >> 1) & 1) * 4 + (lane & 1) * 2;
-      const float inv = 1.0f / sum;
-      *reinterpret_cast<uint32_t*>(p.ctx + (long long)(row0 + 256) * p.D + h * kDh + d0) = pack_bf16x2(qr[0] * inv, qr[1] * inv);
+      for (int j = 0; j < 8; ++j) o[j] = fmaf(px, xv[half * 32 + g * 8 + j], __uint_as_float(v[j])) * inv;
+      reinterpret_cast<uint4*>(dst)[g] =
+          make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
     }
   } else {
     const int q = warp & 3;
@@ -625,11 +743,18 @@ cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, in
     }
     static bool attr2 = false;
     if (!attr2) {
-      cudaError_t e = cudaFuncSetAttribute(attention_tc257_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem257);
+      cudaError_t e = cudaFuncSetAttribute(attention_tc257_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem257);
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(attention_tc257_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem257);
       if (e != cudaSuccess) return e;
       attr2 = true;
     }
-    launch_k<attention_tc257_kernel>(B * heads * 2, kThreads, kSmem257, s, q);
+    static int halves = -1;     // DP_ATTN_HALVES=1: four softmax warps, thread = whole row (A/B switch)
+    if (halves < 0) { const char* v = getenv("DP_ATTN_HALVES"); halves = v ? atoi(v) : 2; }
+    if (halves == 2)
+      launch_k<attention_tc257_kernel<2>>(B * heads * 2, 64 + 128 * 2, kSmem257, s, q);
+    else
+      launch_k<attention_tc257_kernel<1>>(B * heads * 2, kThreads, kSmem257, s, q);
     if (trace_on) {   // debug only: synchronises
       long long h[16];
       cudaStreamSynchronize(s);

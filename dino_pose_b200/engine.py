@@ -117,15 +117,17 @@ class PoseEngine:
         trainable = set(self.trainable_names())
         Ls = self.build_head_layers(16)
         order = []
-        for key in self.BWD_LAYER_ORDER:
-            L = Ls[key]
-            group = ([L.bn + ".weight", L.bn + ".bias"] if L.bn else []) + [L.name + ".weight", L.name + ".bias"]
-            order.append((key, [n for n in group if n in trainable]))
+        # the z-head backward (a chain of small launches on the second stream) is the FIRST thing the backward finishes:
+        # its 4 MB of gradients ride in the first all-reduce bucket instead of an exposed one after the last kernel
         nz = len(self.cfg["z_hidden"]) + 1
         zg = []
         for j in reversed(range(nz)):
             zg += [f"pose_heads.z_head.mlp.{3 * j}.weight", f"pose_heads.z_head.mlp.{3 * j}.bias"]
         order.append(("z_head", [n for n in zg if n in trainable]))
+        for key in self.BWD_LAYER_ORDER:
+            L = Ls[key]
+            group = ([L.bn + ".weight", L.bn + ".bias"] if L.bn else []) + [L.name + ".weight", L.name + ".bias"]
+            order.append((key, [n for n in group if n in trainable]))
         lg = [self.lora_prefix + "lora_A", self.lora_prefix + "lora_B"] if self.lora else []
         order.append(("lora", [n for n in lg if n in trainable]))
         for i in reversed(self.train_layers):
@@ -802,9 +804,9 @@ class PoseEngine:
                 be.wgrad(*a_, **k_)
 
         def done(key):
-            # every gradient in flat[:group_end[key]] is final from here on
-            if overlap:
-                be.sync("main_wait")
+            # every gradient in flat[:group_end[key]] is final from here on: the second stream (z-head chain, weight
+            # gradients) has caught up
+            be.sync("main_wait")
             be.mark(("grads_final", lay["group_end"][key]))
         t["dhm"] = self.new(tuple(t["hm"].shape), F32)
         t["dz"] = self.new((B, K), F32)
@@ -969,7 +971,6 @@ class PoseEngine:
         done("fr0")
         be.join()                # z-head chain (second stream): its input gradient dcur is needed now
         be.mean_tokens_bwd(dfeat, dcur, B=B, N=N, D=D)
-        done("z_head")
         if self.train_layers:
             self.record_backward_layers(plan, dfeat, G, flat, ws, done)
             return

@@ -749,8 +749,11 @@ cudaError_t launch_attention_tc(const __nv_bfloat16* qkv, __nv_bfloat16* ctx, in
       if (e != cudaSuccess) return e;
       attr2 = true;
     }
-    static int halves = -1;     // DP_ATTN_HALVES=1: four softmax warps, thread = whole row (A/B switch)
-    if (halves < 0) { const char* v = getenv("DP_ATTN_HALVES"); halves = v ? atoi(v) : 2; }
+    // DP_ATTN_HALVES=2: eight softmax warps, two threads per row.  Measured equal to the four-warp version at the kernel
+    // level (26.3 vs 26.6 us, gpurun_out/ab5): the exponential pass is bound by the MUFU rate of the SM, not by the
+    // number of warps issuing it -> the simpler four-warp kernel stays the default
+    static int halves = -1;
+    if (halves < 0) { const char* v = getenv("DP_ATTN_HALVES"); halves = v ? atoi(v) : 1; }
     if (halves == 2)
       launch_k<attention_tc257_kernel<2>>(B * heads * 2, 64 + 128 * 2, kSmem257, s, q);
     else

@@ -219,24 +219,36 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_wgrad_kernel(const __grid_co
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
-// out[off(m) + off(n) + tap * so_t] = sum over splits of the workspace partials (overwrites: no pre-zeroing needed)
+// out[off(m) + off(n) + tap * so_t] = sum over splits of the workspace partials (overwrites: no pre-zeroing needed).
+// One thread per (tap, m, n) -- reads coalesced along n -- with the split loop unrolled over four independent
+// accumulators.  (First version: one thread per (m, n) walking taps x splits serially; with 16 k threads for a
+// 128 x 128 x 16-tap gradient it ran at 0.5 TB/s, ~15 us per launch, 14 launches per step -- profiles/r1h_step_metrics.md.)
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, float* __restrict__ out, int splits,
                                                            int taps, int Mpad, int ld, int Mc, int Nc, long long so_m,
                                                            long long so_mo, long long so_n, long long so_no, long long so_t,
                                                            int m_inner, int n_inner) {
   pdl_grid_sync();
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)Mc * Nc) return;
-  const int m = int(idx / Nc), n = int(idx - (long long)m * Nc);
+  const long long per_tap = (long long)Mc * Nc;
+  if (idx >= per_tap * taps) return;
+  const int t = int(idx / per_tap);
+  const long long rem = idx - (long long)t * per_tap;
+  const int m = int(rem / Nc), n = int(rem - (long long)m * Nc);
   const long long base = (long long)(m % m_inner) * so_m + (long long)(m / m_inner) * so_mo +
                          (long long)(n % n_inner) * so_n + (long long)(n / n_inner) * so_no;
   const long long slice = (long long)Mpad * ld;
-  for (int t = 0; t < taps; ++t) {
-    float acc = 0.f;
-    const float* p = ws + (long long)t * slice + (long long)m * ld + n;
-    for (int s = 0; s < splits; ++s) acc += __ldg(p + (long long)s * taps * slice);
-    out[base + (long long)t * so_t] = acc;
+  const long long step = (long long)taps * slice;
+  const float* p = ws + (long long)t * slice + (long long)m * ld + n;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int s = 0;
+  for (; s + 4 <= splits; s += 4) {
+    a0 += __ldg(p + (long long)s * step);
+    a1 += __ldg(p + (long long)(s + 1) * step);
+    a2 += __ldg(p + (long long)(s + 2) * step);
+    a3 += __ldg(p + (long long)(s + 3) * step);
   }
+  for (; s < splits; ++s) a0 += __ldg(p + (long long)s * step);
+  out[base + (long long)t * so_t] = (a0 + a1) + (a2 + a3);
 }
 
 template <int BN> cudaError_t launch_wgrad_t(const WgradParams& p, int grid, cudaStream_t s) {
@@ -299,7 +311,7 @@ cudaError_t launch_wgrad(const WgradParams& p, int block_n, int grid, cudaStream
     default: return cudaErrorInvalidValue;
   }
   if (e != cudaSuccess || p.ws == nullptr) return e;
-  const long long total = (long long)p.Mc * p.Nc;
+  const long long total = (long long)p.Mc * p.Nc * p.taps;
   launch_k<wgrad_reduce_kernel>(unsigned((total + 255) / 256), 256, 0, s, p.ws, p.out, p.splits, p.taps, p.m_tiles * kBlockM, p.ws_ld,
                                                                     p.Mc, p.Nc, p.so_m, p.so_mo, p.so_n, p.so_no, p.so_t,
                                                                     p.m_inner, p.n_inner);

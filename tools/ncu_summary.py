@@ -101,7 +101,7 @@ def _family(name):
     return re.sub(r"_kernel$", "", base)
 
 
-def steptraffic(path, last=261):
+def steptraffic(path, last=261, end=None):
     """Long-format CSV (`ncu --metrics ... --csv`, one row per launch and metric) of the whole program: keeps the LAST
     `last` launches (one steady-state fine-tuning step), prints a per-family markdown table on stderr-free stdout and
     writes the JSON bench.py reads (profiles/traffic.json) when a second argument names it."""
@@ -114,7 +114,10 @@ def steptraffic(path, last=261):
     for r in rows[1:]:
         d = launches.setdefault(r[idx["ID"]], {"name": r[idx["Kernel Name"]]})
         d[r[idx["Metric Name"]]] = float(r[idx["Metric Value"]].replace(",", "")) * mult.get(r[idx["Metric Unit"]], 1.0)
-    step = list(launches.values())[-int(last):]
+    import os
+    last = int(os.environ.get("STEP_LAST", last))
+    end = int(os.environ["STEP_END"]) if "STEP_END" in os.environ else end   # capture cut short: pick a complete step
+    step = list(launches.values())[:end][-int(last):]
     fam = collections.OrderedDict()
     for d in step:
         f = fam.setdefault(_family(d["name"]), {"launches": 0, "dram_bytes": 0.0, "us": 0.0, "tens": 0.0})

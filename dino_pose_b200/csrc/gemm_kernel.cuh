@@ -106,9 +106,23 @@ template <int BN, int OUT, int ACT, int MAP, int OPT>
 __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem_acc, int q, int half, int lane,
                                               int m_blk, int n_blk, float* __restrict__ stg,
                                               float* __restrict__ colstats, uint64_t* tfull, uint32_t tfull_phase,
-                                              long long* __restrict__ tr = nullptr) {
+                                              long long* __restrict__ tr = nullptr, int next_m_blk = -1, int next_n_blk = -1) {
   const Epilogue& e = p.epi;
   const int map = (MAP == EM_RUNTIME) ? e.row_map : MAP;
+  if constexpr ((OPT & OP_AUX_IN) != 0 && (OPT & OP_CONV) == 0) {
+    // The gelu' operand (fc1 pre-activation saved by the forward, 50 MB at batch 64) is cold in HBM, and this kernel is
+    // epilogue bound: the accumulator is already waiting when a warp gets here, so the ~2 us DRAM latency of the aux
+    // loads below was fully exposed once per tile (55 us for the fc2 input gradient against 26 us for fc1 forward with
+    // the same traffic).  Pull the NEXT tile's rows into L2 now, one 64-byte segment per lane and chunk.
+    if (next_m_blk >= 0 && e.aux_in != nullptr) {
+      const long long nrow = (long long)next_m_blk * kBlockM + q * 32 + lane;
+      if (nrow < p.M) {
+        const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(e.aux_in) + nrow * e.ld_aux + next_n_blk * BN;
+        for (int c = half; c < BN / 32; c += kEpiGroups)
+          if (next_n_blk * BN + c * 32 < e.n_valid) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + c * 32));
+      }
+    }
+  }
   const bool conv = (OPT & OP_CONV) && p.a_mode == 1;
   const int r = q * 32 + lane;
   int logical;
@@ -585,8 +599,17 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
         epilogue_tile_tma<BN, ACT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk,
                                    reinterpret_cast<uint8_t*>(stg), nstore, pre);
       } else {
+        int nm = -1, nn = -1;
+        if constexpr ((OPT & OP_AUX_IN) != 0) {
+          const int next = tile + gridDim.x;
+          if (next < num_tiles) {
+            DP_TILE_COORDS(next, nm2, nn2)
+            nm = nm2;
+            nn = nn2;
+          }
+        }
         epilogue_tile<BN, OUT, ACT, MAP, OPT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk, stg, colstats,
-                                              &tfull_bar[acc], acc_phase, tr);
+                                              &tfull_bar[acc], acc_phase, tr, nm, nn);
       }
       tc_fence_before();
       __syncwarp();

@@ -345,6 +345,23 @@ class PoseEngine:
         self.be.pack_weights(jobs)
         self.be.host("cat_qkv_bias", cat_biases)
 
+    def tile(self, which, M):
+        """Tile shape of the backbone GEMMs (tools/gemm_tune.py, B200).  K = D = 384 (ViT-S): single-CTA 128-row tiles,
+        192 columns for fc1 (fewer waves at N = 1536); the CTA-pair kernel is 5-20 % slower there (6 k-blocks per tile do
+        not amortise the cross-CTA handshakes).  K >= 768 (ViT-B / L): 256 x 256 CTA-pair tiles (`cta_group::2`, each
+        CTA stages half of the weight tile) -- fc2 69.0 vs 79.8 us, fc1 68.2 vs 72.5 us at ViT-B, M = 16448; the pair
+        kernel halves the weight traffic from L2, which is what bounds the long-K shapes.  DP_PAIR_WIDE=0: off;
+        DP_PAIR_QKV=0 keeps qkv / proj on the single-CTA kernel."""
+        D = self.D
+        wide = D >= 768 and M >= 4096 and bool(int(os.environ.get("DP_PAIR_WIDE", "1")))
+        if which in ("fc1", "fc2"):
+            if wide:
+                return dict(block_n=256, cta_pair=1)
+            return dict(block_n=192 if (which == "fc1" and (4 * D) % 192 == 0) else 0)
+        if wide and bool(int(os.environ.get("DP_PAIR_QKV", "1"))):
+            return dict(block_n=256, cta_pair=1)
+        return {}
+
     # ------------------------------------------------------------------ plans
     def get_plan(self, B, H, W, training):
         key = (B, H, W, bool(training))
@@ -443,10 +460,10 @@ class PoseEngine:
                 be.layernorm_fwd(s_["x_mid"], self.p(lp + "norm2.weight"), self.p(lp + "norm2.bias"), s_["xn2"], None, rows=M,
                                  D=D, eps=LN_EPS)
                 be.gemm(s_["xn2"], w["w1"], s_["h"], M=M, N=4 * D, K=D, bias=self.p(lp + "mlp.fc1.bias"), act="gelu",
-                        aux_out=s_["pre"], ld_aux=4 * D, name=f"fc1_{i}", block_n=192 if (4 * D) % 192 == 0 else 0)
+                        aux_out=s_["pre"], ld_aux=4 * D, name=f"fc1_{i}", **self.tile("fc1", M))
                 be.gemm(s_["h"], w["w2"], s_["x_out"], M=M, N=D, K=4 * D, bias=self.p(lp + "mlp.fc2.bias"), out_dtype="f32",
                         ls=self.p(lp + "layer_scale2.lambda1"), residual=s_["x_mid"], aux_out=s_["m"], ld_aux=D,
-                        name=f"fc2_{i}")
+                        name=f"fc2_{i}", **(self.tile("fc2", M) if s_["m"] is None else {}))   # no pair variant with aux_out
                 x_cur = s_["x_out"]
                 continue
             if split and not (last and (use_lora or training)):
@@ -468,9 +485,9 @@ class PoseEngine:
                     be.layernorm_fwd(xs_, self.p(lp + "norm2.weight"), self.p(lp + "norm2.bias"), xn_, None, rows=Mh, D=D,
                                      eps=LN_EPS)
                     be.gemm(xn_, fz[f"w1{i}"], h_, M=Mh, N=4 * D, K=D, bias=self.p(lp + "mlp.fc1.bias"), act="gelu",
-                            name=f"fc1_{i}", block_n=192 if (4 * D) % 192 == 0 else 0)
+                            name=f"fc1_{i}", **self.tile("fc1", Mh))
                     be.gemm(h_, fz[f"w2{i}"], xs_, M=Mh, N=D, K=4 * D, bias=self.p(lp + "mlp.fc2.bias"), out_dtype="f32",
-                            ls=self.p(lp + "layer_scale2.lambda1"), residual=xs_, name=f"fc2_{i}")
+                            ls=self.p(lp + "layer_scale2.lambda1"), residual=xs_, name=f"fc2_{i}", **self.tile("fc2", Mh))
                 be.side(False)
                 continue
             if split_open:
@@ -478,7 +495,8 @@ class PoseEngine:
                 split_open = False
             be.layernorm_fwd(t["x"], self.p(lp + "norm1.weight"), self.p(lp + "norm1.bias"), t["xn"], None, rows=M, D=D,
                              eps=LN_EPS)
-            be.gemm(t["xn"], fz[f"wqkv{i}"], t["qkv"], M=M, N=3 * D, K=D, bias=fz[f"bqkv{i}"], name=f"qkv{i}")
+            be.gemm(t["xn"], fz[f"wqkv{i}"], t["qkv"], M=M, N=3 * D, K=D, bias=fz[f"bqkv{i}"], name=f"qkv{i}",
+                    **self.tile("qkv", M))
             be.attention_fwd(t["qkv"], t["ctx"], B=B, T=T, heads=heads, scale=scale)
             x_in = t["x"]
             x_att = t["x_mid"] if (last and training) else t["x"]
@@ -500,15 +518,15 @@ class PoseEngine:
                             ls=self.p(lp + "layer_scale1.lambda1"), residual=x_in, name="proj_last_merged")
             else:
                 be.gemm(t["ctx"], fz[f"wo{i}"], x_att, M=M, N=D, K=D, bias=fz[f"bo{i}"], out_dtype="f32",
-                        ls=self.p(lp + "layer_scale1.lambda1"), residual=x_in, name=f"proj{i}")
+                        ls=self.p(lp + "layer_scale1.lambda1"), residual=x_in, name=f"proj{i}", **self.tile("proj", M))
             be.layernorm_fwd(x_att, self.p(lp + "norm2.weight"), self.p(lp + "norm2.bias"), t["xn"], None, rows=M, D=D,
                              eps=LN_EPS)
             be.gemm(t["xn"], fz[f"w1{i}"], t["h"], M=M, N=4 * D, K=D, bias=self.p(lp + "mlp.fc1.bias"), act="gelu",
                     aux_out=t["pre"] if (last and training) else None, ld_aux=4 * D, name=f"fc1_{i}",
-                    block_n=192 if (4 * D) % 192 == 0 else 0)   # 192-wide tiles: fewer waves for N = 1536 / 3072 (tools/gemm_tune.py)
+                    **self.tile("fc1", M))
             x_out = t["x_last"] if (last and training) else t["x"]
             be.gemm(t["h"], fz[f"w2{i}"], x_out, M=M, N=D, K=4 * D, bias=self.p(lp + "mlp.fc2.bias"), out_dtype="f32",
-                    ls=self.p(lp + "layer_scale2.lambda1"), residual=x_att, name=f"fc2_{i}")
+                    ls=self.p(lp + "layer_scale2.lambda1"), residual=x_att, name=f"fc2_{i}", **self.tile("fc2", M))
         if split_open:
             be.sync("main_wait")
         x_fin = t["x_last"] if training else t["x"]

@@ -31,8 +31,8 @@ enum : int {
   OP_SCALE = 1,      // per-column scale (folded eval BatchNorm)
   OP_LSRES = 2,      // LayerScale and / or fp32 residual
   OP_RES_BF16 = 4,   // bf16 residual
-  OP_AUX_OUT = 8,    // bf16 copy of the pre-activation
-  OP_AUX_IN = 16,    // multiply by gelu'(aux_in)
+  OP_AUX_OUT = 8,    // bf16 side output: gelu'(v) when the activation is GELU, else v
+  OP_AUX_IN = 16,    // multiply by aux_in (the saved gelu' of the forward)
   OP_STATS = 32,     // fused BatchNorm statistics
   OP_CONV = 64,      // implicit-conv row decoding (a_mode = 1)
   OP_ALL = 127,
@@ -310,28 +310,29 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
           s2[k] = fmaf(f[k] * m, f[k], s2[k]);
         }
       }
+      // aux_out: what the backward of this layer multiplies with.  With a GELU it is gelu'(v) (same tanh as the forward
+      // value, six more FMAs), so the backward epilogue is a plain multiply; without an activation it is v itself.
+      const bool gelu_here = (ACT == EA_GELU) || (ACT == EA_RUNTIME && act == ACT_GELU);
+      float dg[4] = {f[0], f[1], f[2], f[3]};
+      if (gelu_here) {
+        if constexpr ((OPT & OP_AUX_OUT) != 0) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) f[k] = gelu_fast_both(f[k], dg[k]);
+        } else {
+#pragma unroll
+          for (int k = 0; k < 4; ++k) f[k] = gelu_fast(f[k]);
+        }
+      } else if ((ACT == EA_RELU) || (ACT == EA_RUNTIME && act == ACT_RELU)) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], 0.f);
+      }
       if constexpr ((OPT & OP_AUX_OUT) != 0) {
         const uint32_t a_off = __shfl_sync(kFull, off_aux, row);   // all lanes take part
         if (has_aux_out && ok) {
           uint2 t;
-          t.x = pack_bf16x2(f[0], f[1]);
-          t.y = pack_bf16x2(f[2], f[3]);
+          t.x = pack_bf16x2(dg[0], dg[1]);
+          t.y = pack_bf16x2(dg[2], dg[3]);
           *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.aux_out) + a_off + ccol) = t;
-        }
-      }
-      if constexpr (ACT == EA_RELU) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], 0.f);
-      } else if constexpr (ACT == EA_GELU) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) f[k] = gelu_fast(f[k]);
-      } else if constexpr (ACT == EA_RUNTIME) {
-        if (act == ACT_RELU) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) f[k] = fmaxf(f[k], 0.f);
-        } else if (act == ACT_GELU) {
-#pragma unroll
-          for (int k = 0; k < 4; ++k) f[k] = gelu_fast(f[k]);
         }
       }
       if constexpr ((OPT & OP_AUX_IN) != 0) {
@@ -339,7 +340,7 @@ __device__ __forceinline__ void epilogue_tile(const GemmParams& p, uint32_t tmem
         unpack_bf16x4(auxin[it], t);
         if (has_aux_in) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) f[k] *= gelu_fast_grad(t[k]);
+          for (int k = 0; k < 4; ++k) f[k] *= t[k];
         }
       }
       if constexpr ((OPT & OP_LSRES) != 0) {

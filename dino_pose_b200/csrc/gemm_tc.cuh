@@ -11,9 +11,9 @@ enum : int { OUT_BF16 = 0, OUT_F32 = 1 };
 
 // Epilogue of the K-major GEMM / implicit conv:   (per output element, column c, logical row r)
 //   v = acc * scale[c] + bias[c]
-//   aux_out[r,c] = bf16(v)                    (optional: pre-activation copy kept for backward)
+//   aux_out[r,c] = bf16(act == GELU ? gelu'(v) : v)   (optional: what the backward multiplies with / the branch output)
 //   v = act(v)
-//   v = v * gelu'(aux_in[r,c])                (optional: fused GELU backward for the fc2->fc1 dgrad)
+//   v = v * aux_in[r,c]                       (optional: fused GELU backward for the fc2->fc1 dgrad)
 //   v = residual[rr,c] + v * ls[c]            (optional: LayerScale + residual / pos-emb add)
 //   out[map(r),c] = v
 struct Epilogue {

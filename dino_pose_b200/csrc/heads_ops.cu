@@ -1362,7 +1362,10 @@ cudaError_t launch_relu_mask(const float* d, const float* ref, float* out, long 
   return cudaGetLastError();
 }
 cudaError_t launch_colsum(const void* x, int is_bf16, float* out, long long P, int C, long long ld, cudaStream_t s) {
-  int rpb = int((P + 295) / 296);
+  // narrow matrices (the 24-channel heat-map gradient: one warp per block) need many more blocks than two per SM to
+  // cover the load latency: 296 one-warp blocks walked 498 rows each and took 35 us for 9.4 MB (profiles/r1h_step_metrics)
+  const int target = C >= 128 ? 296 : 296 * 16;
+  int rpb = int((P + target - 1) / target);
   if (rpb < 32) rpb = 32;
   const int block = C >= 128 ? 128 : 32;
   dim3 grid(unsigned((P + rpb - 1) / rpb), unsigned((C + block - 1) / block));

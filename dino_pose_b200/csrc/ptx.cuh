@@ -230,6 +230,19 @@ __device__ __forceinline__ float gelu_fast_grad(float x) {
   const float r = (0.5f * x) * fmaf(-th, th, 1.f);
   return fmaf(r, q, fmaf(0.5f, th, 0.5f));
 }
+// gelu_fast and gelu_fast_grad of the same argument with ONE tanh (forward epilogue that also saves the derivative)
+__device__ __forceinline__ float gelu_fast_both(float x, float& dgelu) {
+  const float x2 = fminf(x * x, 64.f);
+  float p = fmaf(-0.00035190239f, x2, 0.03700802f);
+  p = fmaf(p, x2, 0.79750528f);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(p * x));
+  float q = fmaf(5.f * -0.00035190239f, x2, 3.f * 0.03700802f);
+  q = fmaf(q, x2, 0.79750528f);
+  const float hx = 0.5f * x;
+  dgelu = fmaf(hx * fmaf(-th, th, 1.f), q, fmaf(0.5f, th, 0.5f));
+  return fmaf(hx, th, hx);
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

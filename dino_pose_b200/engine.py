@@ -400,7 +400,7 @@ class PoseEngine:
         if training:
             t["x_mid"] = self.new((M, D), F32)     # residual stream after the last block's attention branch
             t["x_last"] = self.new((M, D), F32)    # residual stream entering the final LayerNorm
-            t["pre"] = self.new((M, 4 * D), self.adt)  # fc1 pre-activation of the last block
+            t["pre"] = self.new((M, 4 * D), self.adt)  # gelu'(fc1 pre-activation) of the last block: the fc2 input gradient's multiplier
         if lora_train:
             t["y"] = self.new((M, D), F32)
             t["u"] = self.new((M, self.lora["rank"]), F32)

@@ -42,8 +42,9 @@ enum { DP_OUT_BF16 = 0, DP_OUT_F32 = 1 };
  * Replaces: nn.Linear q/k/v/dense/fc1/fc2 (HF modeling_dinov2.py:211-213,250,325-327), the patch
  * conv (HF:139,148), and -- with a_mode = 1 (implicit convolution over an NHWC activation) -- the
  * stride-1 nn.Conv2d / ConvTranspose2d(k4,s1) of model/pose_heads.py:306-340.
- * Epilogue (per element): v = acc*scale[c] + bias[c]; aux_out = bf16(v); v = act(v);
- *   v *= gelu'(aux_in); v *= ls[c]; v += residual[row,c]; out[row_map(row), c] = v            */
+ * Epilogue (per element): v = acc*scale[c] + bias[c]; aux_out = bf16(act == GELU ? gelu'(v) : v); v = act(v);
+ *   v *= aux_in; v *= ls[c]; v += residual[row,c]; out[row_map(row), c] = v
+ * (aux_out of the fc1 forward is therefore exactly the multiplier aux_in of the fc2 input-gradient GEMM)            */
 typedef struct {
   const void* A;          /* bf16 */
   const void* W;          /* bf16 [N, K] row-major, row pitch ldw */

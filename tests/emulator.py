@@ -144,16 +144,19 @@ class TorchEmulator:
                 stats[:sc] += s1
                 stats[sc:2 * sc] += s2
             if aux_out is not None:
-                aux_out.view(-1, ld_aux)[:M, :nv] = v.to(aux_out.dtype)
+                side = v
+                if act == "gelu":       # what the backward multiplies with: gelu'(v)
+                    pre = v.detach().clone().requires_grad_(True)
+                    with torch.enable_grad():
+                        F.gelu(pre).sum().backward()
+                    side = pre.grad
+                aux_out.view(-1, ld_aux)[:M, :nv] = side.to(aux_out.dtype)
             if act == "relu":
                 v = F.relu(v)
             elif act == "gelu":
                 v = F.gelu(v)
             if aux_in is not None:
-                pre = aux_in.view(-1, ld_aux)[:M, :nv].float().requires_grad_(True)
-                with torch.enable_grad():
-                    F.gelu(pre).sum().backward()
-                v = v * pre.grad
+                v = v * aux_in.view(-1, ld_aux)[:M, :nv].float()
             if ls is not None:
                 v = v * ls[:nv]
             if row_map == "identity":

@@ -68,7 +68,7 @@ def test_gemm_cta_pair(M, N, K, bn):
     run(lambda b: b.gemm(A, W, out, M=M, N=N, K=K, bias=bias, block_n=bn, cta_pair=1))
     ref = A.float() @ W.float().t() + bias
     assert rel(out.float(), ref) < 1e-2
-    # fp32 out + LayerScale + in-place residual, and GELU (+ saved pre-activation) through the pair kernel
+    # fp32 out + LayerScale + in-place residual, and GELU (+ saved derivative) through the pair kernel
     ls = rnd(N, seed=4)
     x = rnd(M, N, seed=5)
     x0 = x.clone()
@@ -78,7 +78,9 @@ def test_gemm_cta_pair(M, N, K, bn):
         out2 = torch.zeros(M, N, device=dev(), dtype=BF)
         aux = torch.zeros(M, N, device=dev(), dtype=BF)
         run(lambda b: b.gemm(A, W, out2, M=M, N=N, K=K, bias=bias, act="gelu", aux_out=aux, ld_aux=N, block_n=bn, cta_pair=1))
-        assert rel(aux.float(), ref) < 1e-2
+        xr = ref.clone().requires_grad_(True)
+        F.gelu(xr).sum().backward()
+        assert rel(aux.float(), xr.grad) < 1e-2       # side output of a GELU epilogue = gelu'(v), the backward's multiplier
         assert rel(out2.float(), F.gelu(ref)) < 1e-2
 
 
@@ -97,8 +99,14 @@ def test_gemm_epilogues():
     out2 = torch.zeros(M, N, device=dev(), dtype=BF)
     aux = torch.zeros(M, N, device=dev(), dtype=BF)
     run(lambda b: b.gemm(A, W, out2, M=M, N=N, K=K, bias=bias, scale=scale, act="gelu", aux_out=aux, ld_aux=N))
-    assert rel(aux.float(), base) < 1e-2
+    xb = base.clone().requires_grad_(True)
+    F.gelu(xb).sum().backward()
+    assert rel(aux.float(), xb.grad) < 1e-2          # with a GELU the side output is gelu'(v), the backward's multiplier
     assert rel(out2.float(), F.gelu(base)) < 1e-2
+    aux0 = torch.zeros(M, N, device=dev(), dtype=BF)
+    out20 = torch.zeros(M, N, device=dev(), dtype=BF)
+    run(lambda b: b.gemm(A, W, out20, M=M, N=N, K=K, bias=bias, scale=scale, aux_out=aux0, ld_aux=N))
+    assert rel(aux0.float(), base) < 1e-2            # without an activation it is v itself
     # relu, bf16 residual
     resb = res.to(BF)
     out3 = torch.zeros(M, N, device=dev(), dtype=BF)
@@ -106,11 +114,9 @@ def test_gemm_epilogues():
     assert rel(out3.float(), F.relu(A.float() @ W.float().t() + bias) + resb.float()) < 1e-2
     # fused GELU backward multiplier
     out4 = torch.zeros(M, N, device=dev(), dtype=BF)
-    pre = rnd(M, N, seed=9, dtype=BF)
-    run(lambda b: b.gemm(A, W, out4, M=M, N=N, K=K, aux_in=pre, ld_aux=N))
-    x = pre.float().requires_grad_(True)
-    F.gelu(x).sum().backward()
-    assert rel(out4.float(), (A.float() @ W.float().t()) * x.grad) < 1e-2
+    mult = rnd(M, N, seed=9, dtype=BF)
+    run(lambda b: b.gemm(A, W, out4, M=M, N=N, K=K, aux_in=mult, ld_aux=N))
+    assert rel(out4.float(), (A.float() @ W.float().t()) * mult.float()) < 1e-2
 
 
 @pytest.mark.parametrize("M,N,bn", [(5000, 128, 128), (40000, 512, 256), (3000, 384, 192), (129, 64, 64)])

@@ -85,6 +85,8 @@ SIGNATURES = {
     "dp_attention_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, i, i, i, f, c_vp],
     "dp_layernorm_bwd_params": [c_vp, i, c_vp, c_vp, c_vp, c_ll, i, f, c_vp],
     "dp_colsum_prod": [c_vp, c_vp, c_vp, c_ll, i, c_vp],
+    "dp_pred1x1_fwd": [c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, c_vp],
+    "dp_pred1x1_bwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, c_vp],
     "dp_decode": [c_vp, i, i, i, d, d, c_vp, c_vp, c_vp, c_vp],
     "dp_im2col": [c_vp, c_vp, i, i, i, i, i, i, i, i, i, i, c_vp],
     "dp_col2im": [c_vp, c_vp, c_vp, i, i, i, i, i, i, i, i, i, i, i, c_vp],

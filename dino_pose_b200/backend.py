@@ -329,6 +329,21 @@ class CudaBackend:
         _chk(a, torch.bfloat16, "colsum_prod.a")
         self.prog.add("colsum_prod", self.lib.dp_colsum_prod, _p(g), _p(a), _p(out), P, C, keep=(g, a, out))
 
+    # ---- prediction.3 (1x1 conv, 64 -> K <= 32) on CUDA cores, forward and fused backward
+    def pred1x1_fwd(self, a, w, bias, out, *, P, HW, C, K):
+        _chk(a, torch.bfloat16, "pred1x1.a")
+        _chk(w, torch.float32, "pred1x1.w")
+        _chk(out, torch.float32, "pred1x1.out")
+        self.prog.add("pred1x1_fwd", self.lib.dp_pred1x1_fwd, _p(a), _p(w), _p(bias), _p(out), P, HW, C, K,
+                      keep=(a, w, bias, out), flops=2.0 * P * C * K, bytes=P * (C * 2.0 + K * 4.0))
+
+    def pred1x1_bwd(self, g, a, w, d, dW, db, *, P, HW, C, K):
+        _chk(g, torch.float32, "pred1x1_bwd.g")
+        _chk(a, torch.bfloat16, "pred1x1_bwd.a")
+        _chk(d, torch.bfloat16, "pred1x1_bwd.d")
+        self.prog.add("pred1x1_bwd", self.lib.dp_pred1x1_bwd, _p(g), _p(a), _p(w), _p(d), _p(dW), _p(db), P, HW, C, K,
+                      keep=(g, a, w, d, dW, db), flops=4.0 * P * C * K, bytes=P * (C * 4.0 + K * 4.0))
+
     def decode(self, hm, idx, xy, conf, *, maps, H, W, target_w, target_h):
         _chk(hm, torch.float32, "decode.heatmaps")
         self.prog.add("decode", self.lib.dp_decode, _p(hm), maps, H, W, float(target_w), float(target_h), _p(idx),

@@ -24,6 +24,9 @@ cudaError_t launch_attention_bwd(const __nv_bfloat16*, const __nv_bfloat16*, con
                                  int, int, float, cudaStream_t);
 cudaError_t launch_layernorm_bwd_params(const void*, int, const float*, float*, float*, long long, int, float, int, cudaStream_t);
 cudaError_t launch_colsum_prod(const float*, const __nv_bfloat16*, float*, long long, int, cudaStream_t);
+cudaError_t launch_pred1x1_fwd(const __nv_bfloat16*, const float*, const float*, float*, long long, int, int, cudaStream_t);
+cudaError_t launch_pred1x1_bwd(const float*, const __nv_bfloat16*, const float*, __nv_bfloat16*, float*, float*, long long, int,
+                               int, int, cudaStream_t);
 cudaError_t launch_decode(const float*, int, int, int, double, double, int*, double*, float*, cudaStream_t);
 cudaError_t launch_im2col(const void*, void*, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
 cudaError_t launch_col2im(const void*, const float*, void*, int, int, int, int, int, int, int, int, int, int, int, cudaStream_t);
@@ -205,6 +208,19 @@ extern "C" int dp_bn_bwd_apply(const void* dout, const void* raw, int raw_f32, c
 extern "C" int dp_avgpool2(const float* in, float* out, long long planes, int OH, int OW, void* stream) {
   if (!in || !out) return set_error(-1, "dp_avgpool2: bad args");
   return cuda_error(launch_avgpool2(in, out, planes, OH, OW, ST), "dp_avgpool2");
+}
+extern "C" int dp_pred1x1_fwd(const void* a, const float* w, const float* bias, float* out, long long P, int HW, int C, int K,
+                              void* stream) {
+  if (!a || !w || !bias || !out) return set_error(-1, "dp_pred1x1_fwd: null pointer");
+  if (C != 64 || K < 1 || K > 32 || HW <= 0 || P <= 0 || P % HW) return set_error(-2, "dp_pred1x1_fwd: needs C = 64, K <= 32, P %% HW == 0 (C=%d K=%d)", C, K);
+  return cuda_error(launch_pred1x1_fwd(static_cast<const __nv_bfloat16*>(a), w, bias, out, P, HW, K, ST), "dp_pred1x1_fwd");
+}
+extern "C" int dp_pred1x1_bwd(const float* g, const void* a, const float* w, void* d, float* dW, float* db, long long P, int HW,
+                              int C, int K, void* stream) {
+  if (!g || !a || !w || !d || !dW || !db) return set_error(-1, "dp_pred1x1_bwd: null pointer");
+  if (C != 64 || K < 1 || K > 32 || HW <= 0 || P <= 0 || P % HW) return set_error(-2, "dp_pred1x1_bwd: needs C = 64, K <= 32, P %% HW == 0 (C=%d K=%d)", C, K);
+  return cuda_error(launch_pred1x1_bwd(g, static_cast<const __nv_bfloat16*>(a), w, static_cast<__nv_bfloat16*>(d), dW, db, P, HW,
+                                       K, sm_count(), ST), "dp_pred1x1_bwd");
 }
 extern "C" int dp_hm_grad_to_nhwc(const float* g, void* out, int NB, int K, int Kp, int OH, int OW, int up, void* stream) {
   if (!g || !out || (up != 1 && up != 2)) return set_error(-1, "dp_hm_grad_to_nhwc: bad args");

@@ -772,8 +772,15 @@ class PoseEngine:
         L = Ls["pred3"]
         K = self.K
         t["hm_full"] = self.new((B, K, s48, s48), F32)
-        be.gemm(a["pred0"], L.t["wf"], t["hm_full"], M=B * s48 * s48, N=K, K=64, bias=self.p(L.name + ".bias"),
-                out_dtype="f32", row_map="nchw", n_valid=K, map_a=K, OH=s48, OW=s48, NB=B, block_n=32, name="pred3")
+        # 0.45 GFLOP on 33 MB: a CUDA-core kernel with the fp32 parameter (csrc/pred_ops.cu) instead of 1152 one-k-block
+        # tensor-core tiles.  DP_PRED_SIMT=0 keeps the GEMM (A/B); K > 32 has no SIMT variant.
+        plan["pred_simt"] = K <= 32 and L.cin == 64 and bool(int(os.environ.get("DP_PRED_SIMT", "1")))
+        if plan["pred_simt"]:
+            be.pred1x1_fwd(a["pred0"], self.p(L.name + ".weight"), self.p(L.name + ".bias"), t["hm_full"], P=B * s48 * s48,
+                           HW=s48 * s48, C=64, K=K)
+        else:
+            be.gemm(a["pred0"], L.t["wf"], t["hm_full"], M=B * s48 * s48, N=K, K=64, bias=self.p(L.name + ".bias"),
+                    out_dtype="f32", row_map="nchw", n_valid=K, map_a=K, OH=s48, OW=s48, NB=B, block_n=32, name="pred3")
         if s48 == self.hm_size:
             t["hm"] = t["hm_full"]       # bilinear resize to the same size is the identity (pose_heads.py:353-359)
         elif s48 == 2 * self.hm_size:
@@ -942,14 +949,19 @@ class PoseEngine:
 
         # ---- heat-map head
         up = s48 // self.hm_size
-        t["ghm"] = self.new((P48, HM_PAD), self.adt)
-        be.hm_grad_to_nhwc(t["dhm"], t["ghm"], NB=B, K=K, Kp=HM_PAD, OH=s48, OW=s48, up=up)
         L = Ls["pred3"]
-        be.colsum(t["ghm"], G[L.name + ".bias"], P=P48, C=K, ld=HM_PAD)
-        wg(t["ghm"], a["pred0"], G[L.name + ".weight"], Mc=K, Nc=64, so_m=64, so_n=1, P=P48, block_n=64,
-                 name="pred3.wgrad", workspace=ws)
         d = self.new((P48, 64), self.adt)
-        be.gemm(t["ghm"], L.t["wd"], d, M=P48, N=64, K=HM_PAD, name="pred3.dgrad")
+        if plan.get("pred_simt") and up == 1:
+            # one launch: input gradient, weight gradient and bias gradient straight from the fp32 NCHW heat-map gradient
+            be.pred1x1_bwd(t["dhm"], a["pred0"], self.p(L.name + ".weight"), d, G[L.name + ".weight"], G[L.name + ".bias"],
+                           P=P48, HW=s48 * s48, C=64, K=K)
+        else:
+            t["ghm"] = self.new((P48, HM_PAD), self.adt)
+            be.hm_grad_to_nhwc(t["dhm"], t["ghm"], NB=B, K=K, Kp=HM_PAD, OH=s48, OW=s48, up=up)
+            be.colsum(t["ghm"], G[L.name + ".bias"], P=P48, C=K, ld=HM_PAD)
+            wg(t["ghm"], a["pred0"], G[L.name + ".weight"], Mc=K, Nc=64, so_m=64, so_n=1, P=P48, block_n=64,
+               name="pred3.wgrad", workspace=ws)
+            be.gemm(t["ghm"], L.t["wd"], d, M=P48, N=64, K=HM_PAD, name="pred3.dgrad")
         d = conv_bwd("pred0", bn_bwd("pred0", d), a["ups1"])
         d = conv_bwd("ups1", bn_bwd("ups1", d), a["ups0"])
         d = conv_bwd("ups0", bn_bwd("ups0", d), a["fr4"])

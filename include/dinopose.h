@@ -192,6 +192,14 @@ int dp_bn_bwd_apply(const void* dout, const void* raw, int raw_is_f32, const voi
                     void* dres, float* dgamma, float* dbeta, long long P, int C, int relu, int mode, int eval_mode,
                     int shuffle_oh, int shuffle_ow, void* stream);
 int dp_avgpool2(const float* in, float* out, long long planes, int OH, int OW, void* stream);
+/* prediction.3 = Conv2d(64, K, 1) + bias (reference model/pose_heads.py:335-340) on CUDA cores, K <= 32, fp32 weights read
+ * from the parameter: a bf16 [P, 64] (NHWC rows, P = NB*HW) -> out fp32 NCHW [NB, K, HW]. */
+int dp_pred1x1_fwd(const void* a_bf16, const float* w /* [K,64] */, const float* bias, float* out_nchw, long long P, int HW,
+                   int C, int K, void* stream);
+/* its backward in one launch: g fp32 NCHW [NB, K, HW] -> d bf16 [P, 64] (input gradient); dW [K,64] and db [K] are
+ * accumulated with atomics (caller zeroes them). */
+int dp_pred1x1_bwd(const float* g_nchw, const void* a_bf16, const float* w, void* d_bf16, float* dW, float* db, long long P,
+                   int HW, int C, int K, void* stream);
 int dp_hm_grad_to_nhwc(const float* g, void* out_bf16, int NB, int K, int Kp, int OH, int OW, int up, void* stream);
 int dp_mean_tokens(const void* feat_bf16, float* out, int B, int N, int D, void* stream);
 int dp_mean_tokens_bwd(void* dfeat_bf16, const float* dmean, int B, int N, int D, void* stream);

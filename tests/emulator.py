@@ -303,6 +303,20 @@ class TorchEmulator:
             out.view(-1)[:C].add_((g.float().view(P, C) * a.float().view(P, C)).sum(0))
         self.prog.calls.append(fn)
 
+    def pred1x1_fwd(self, a, w, bias, out, *, P, HW, C, K):
+        def fn():
+            y = a.float().view(P, C) @ w.detach().view(K, C).t() + bias.detach()
+            out.copy_(y.view(P // HW, HW, K).permute(0, 2, 1).reshape(out.shape))
+        self.prog.calls.append(fn)
+
+    def pred1x1_bwd(self, g, a, w, d, dW, db, *, P, HW, C, K):
+        def fn():
+            gp = g.reshape(P // HW, K, HW).permute(0, 2, 1).reshape(P, K)
+            d.copy_((gp @ w.detach().view(K, C)).to(d.dtype))
+            dW.view(K, C).add_(gp.t() @ a.float().view(P, C))
+            db.add_(gp.sum(0))
+        self.prog.calls.append(fn)
+
     # ------------------------------------------------------------------ heads
     def im2col(self, x, col, *, NB, IH, IW, C, OH, OW, KH, KW, stride, pad):
         def fn():

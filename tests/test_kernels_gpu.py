@@ -440,6 +440,32 @@ def test_layernorm_param_grads_and_colsum_prod(D, rows, dt):
     assert rel(out, (x.double() * a.double()).sum(0)) < 2e-4
 
 
+@pytest.mark.parametrize("NB,HW,K", [(2, 2304, 24), (3, 700, 17), (1, 256, 32), (5, 2304, 24)])
+def test_pred1x1_fwd_bwd(NB, HW, K):
+    """prediction.3 (Conv2d(64, K, 1) + bias, pose_heads.py:335-340) and its backward on CUDA cores vs torch fp32."""
+    P, C = NB * HW, 64
+    a = rnd(P, C, dtype=BF)
+    w = rnd(K, C, 1, 1, scale=0.2, seed=1)
+    bias = rnd(K, seed=2)
+    out = torch.full((NB, K, HW), 7.0, device=dev())
+    run(lambda b: b.pred1x1_fwd(a, w, bias, out, P=P, HW=HW, C=C, K=K))
+    # fp64 reference (torch's fp32 conv on the GPU may run in TF32)
+    x = a.double().view(NB, HW, C).permute(0, 2, 1).reshape(NB, C, HW, 1).requires_grad_(True)
+    wr = w.double().requires_grad_(True)
+    br = bias.double().requires_grad_(True)
+    ref = F.conv2d(x, wr, br)
+    assert rel(out, ref.view(NB, K, HW)) < 1e-5
+    g = rnd(NB, K, HW, seed=3)
+    ref.backward(g.double().view(NB, K, HW, 1))
+    d = torch.zeros(P, C, device=dev(), dtype=BF)
+    dW = torch.zeros(K, C, 1, 1, device=dev())
+    db = torch.zeros(K, device=dev())
+    run(lambda b: b.pred1x1_bwd(g, a, w, d, dW, db, P=P, HW=HW, C=C, K=K))
+    assert rel(d.float(), x.grad.view(NB, C, HW).permute(0, 2, 1).reshape(P, C)) < 1e-2     # bf16 output
+    assert rel(dW, wr.grad) < 1e-4
+    assert rel(db, br.grad) < 1e-4
+
+
 def test_patch_im2col_and_cls():
     B, H, W, Kp, D = 2, 28, 42, 640, 128
     px = rnd(B, 3, H, W)

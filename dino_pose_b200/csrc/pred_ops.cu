@@ -101,10 +101,10 @@ __global__ void __launch_bounds__(128) pred1x1_fwd_kernel(const __nv_bfloat16* _
 
 // ------------------------------------------------------------------------------------------------ backward
 // Persistent blocks of 256 threads.  Per 256-pixel tile: phase 1, thread = pixel: the K gradients of the pixel (coalesced
-// NCHW reads) -> input gradient of its 64 channels; phase 2, thread = (channel c, group of KP/4 key-points): weight
+// NCHW reads) -> input gradient of its 64 channels; phase 2, thread = (channel pair, key-point half, pixel quarter): weight
 // gradient partial sums over the tile's pixels from shared memory, kept in registers across tiles.
 constexpr int kGRow = kTilePix + 4;   // fp32 elements per row of the gradient tile (k-major), 16-byte aligned rows
-template <int KP> constexpr int pred_bwd_smem() { return KP * kC * 4 + KP * kGRow * 4 + kTilePix * kARow * 2; }
+template <int KP> constexpr int pred_bwd_smem() { return KP * kC * 4 + KP * kGRow * 4 + 2 * kTilePix * kARow * 2; }
 
 template <int KP>
 __global__ void __launch_bounds__(256) pred1x1_bwd_kernel(const float* __restrict__ g, const __nv_bfloat16* __restrict__ a,
@@ -116,13 +116,17 @@ __global__ void __launch_bounds__(256) pred1x1_bwd_kernel(const float* __restric
   float* sW = reinterpret_cast<float*>(psm);                          // [KP][64]
   float* sG = sW + KP * kC;                                           // [KP][kGRow]
   __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(sG + KP * kGRow);   // [256][kARow]
+  __nv_bfloat16* sD = sA + kTilePix * kARow;                               // [256][kARow] input-gradient tile (coalesced write-out)
   for (int i = threadIdx.x; i < KP * kC; i += 256) sW[i] = (i / kC) < K ? __ldg(w + i) : 0.f;
   const int t = threadIdx.x;
-  constexpr int KPT = KP / 4;               // key-points per thread in phase 2
-  const int c2 = t & 63, kq = t >> 6;       // phase 2: channel, key-point group [kq*KPT, kq*KPT + KPT)
-  float wacc[KPT], bacc = 0.f;
+  // phase 2: thread = (channel pair cp, key-point half kh, pixel quarter pg): 2 x KP/2 partial sums in registers.  Per four
+  // pixels a thread issues 4 + KP/2 shared-memory loads for 4 * KP FMAs (a (channel, KP/4 key-points) mapping needed
+  // 4 + KP/4 loads for KP FMAs and was bound by the shared-memory pipe)
+  constexpr int KH = KP / 2;
+  const int cp = t & 31, kh = (t >> 5) & 1, pg = t >> 6;
+  float wacc[KH][2], bacc = 0.f;
 #pragma unroll
-  for (int j = 0; j < KPT; ++j) wacc[j] = 0.f;
+  for (int j = 0; j < KH; ++j) wacc[j][0] = wacc[j][1] = 0.f;
   for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     const long long p0 = (long long)tile * kTilePix;
     __syncthreads();                        // previous tile's phase 2 has finished with sG / sA (and sW is staged)
@@ -159,24 +163,36 @@ __global__ void __launch_bounds__(256) pred1x1_bwd_kernel(const float* __restric
             dacc[4 * c4 + 3] = fmaf(gk[k], wv.w, dacc[4 * c4 + 3]);
           }
         }
-        uint4* dst = reinterpret_cast<uint4*>(d + p * kC + half * 32);
+        uint4* dst = reinterpret_cast<uint4*>(sD + t * kARow + half * 32);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
           dst[q] = make_uint4(pack_bf16x2(dacc[8 * q], dacc[8 * q + 1]), pack_bf16x2(dacc[8 * q + 2], dacc[8 * q + 3]),
                               pack_bf16x2(dacc[8 * q + 4], dacc[8 * q + 5]), pack_bf16x2(dacc[8 * q + 6], dacc[8 * q + 7]));
       }
     }
-    __syncthreads();                        // sG / sA of this tile complete
-    // phase 2: dW[k, c] += sum_p g[p, k] * a[p, c]  (four pixels per step: KPT broadcast float4 + four bf16 loads)
+    __syncthreads();                        // sG / sA / sD of this tile complete
+#pragma unroll
+    for (int i = 0; i < kTilePix * 8 / 256; ++i) {       // 16-byte pieces, consecutive threads -> consecutive addresses
+      const int idx = t + 256 * i;
+      const int row = idx >> 3, ch = idx & 7;
+      if (p0 + row < P)
+        *(reinterpret_cast<uint4*>(d + (p0 + row) * kC) + ch) = *reinterpret_cast<const uint4*>(sD + row * kARow + ch * 8);
+    }
+    // phase 2: dW[k, c] += sum_p g[p, k] * a[p, c] over this thread's quarter of the tile, four pixels per step
 #pragma unroll 2
-    for (int pp = 0; pp < kTilePix; pp += 4) {
-      float av[4];
+    for (int pp = pg * (kTilePix / 4); pp < (pg + 1) * (kTilePix / 4); pp += 4) {
+      float a0[4], a1[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) av[i] = __bfloat162float(sA[(pp + i) * kARow + c2]);
+      for (int i = 0; i < 4; ++i) {
+        const uint32_t v = *reinterpret_cast<const uint32_t*>(sA + (pp + i) * kARow + 2 * cp);
+        a0[i] = __uint_as_float(v << 16);
+        a1[i] = __uint_as_float(v & 0xffff0000u);
+      }
 #pragma unroll
-      for (int j = 0; j < KPT; ++j) {
-        const float4 gv = *reinterpret_cast<const float4*>(sG + (kq * KPT + j) * kGRow + pp);
-        wacc[j] = fmaf(gv.x, av[0], fmaf(gv.y, av[1], fmaf(gv.z, av[2], fmaf(gv.w, av[3], wacc[j]))));
+      for (int j = 0; j < KH; ++j) {
+        const float4 gv = *reinterpret_cast<const float4*>(sG + (kh * KH + j) * kGRow + pp);
+        wacc[j][0] = fmaf(gv.x, a0[0], fmaf(gv.y, a0[1], fmaf(gv.z, a0[2], fmaf(gv.w, a0[3], wacc[j][0]))));
+        wacc[j][1] = fmaf(gv.x, a1[0], fmaf(gv.y, a1[1], fmaf(gv.z, a1[2], fmaf(gv.w, a1[3], wacc[j][1]))));
       }
     }
     if (t < KP) {                           // bias gradient: thread k sums its row of the gradient tile
@@ -190,11 +206,18 @@ __global__ void __launch_bounds__(256) pred1x1_bwd_kernel(const float* __restric
       bacc += sacc;
     }
   }
+  // combine the four pixel quarters in shared memory (the gradient tile is dead), then ONE atomic per output and block
+  __syncthreads();
+  float* red = sG;                          // [4][KP * 64] <= KP * kGRow floats
 #pragma unroll
-  for (int j = 0; j < KPT; ++j) {
-    const int k = kq * KPT + j;
-    if (k < K) atomicAdd(dW + k * kC + c2, wacc[j]);
+  for (int j = 0; j < KH; ++j) {
+    const int k = kh * KH + j;
+    red[pg * (KP * kC) + k * kC + 2 * cp] = wacc[j][0];
+    red[pg * (KP * kC) + k * kC + 2 * cp + 1] = wacc[j][1];
   }
+  __syncthreads();
+  for (int i = t; i < K * kC; i += 256)
+    atomicAdd(dW + i, (red[i] + red[KP * kC + i]) + (red[2 * KP * kC + i] + red[3 * KP * kC + i]));
   if (t < K) atomicAdd(db + t, bacc);
 }
 

@@ -671,19 +671,33 @@ __global__ void __launch_bounds__(64 + 128 * HALVES, 2) attention_tc257_kernel(c
     tc_fence_after();
     if (tr && threadIdx.x == 64) tr[8] = clock64();
     const float inv = 1.0f / sum;
-    __nv_bfloat16* dst = p.ctx + (long long)(row0 + qt * kTile + r) * p.D + h * kDh;
     uint32_t v0[32], v1[32];
     tmem_ld_32x32(trow, v0);
     tmem_ld_32x32(trow + 32, v1);
     tmem_ld_wait();
+    // thread = row gives 16-byte stores 768 bytes apart (32 half-used sectors per instruction).  Stage the warp's
+    // 32 x 64 bf16 block in the dead P-tile-3 buffer (PV has completed), swizzled like the operand tiles, and write it
+    // out as four full 128-byte row segments per instruction.
+    uint8_t* stage = sP3 + q * (32 * 128);
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
       const uint32_t* v = g < 4 ? v0 + g * 8 : v1 + (g - 4) * 8;
       float o[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = fmaf(px, xv[g * 8 + j], __uint_as_float(v[j])) * inv;
-      reinterpret_cast<uint4*>(dst)[g] =
+      *reinterpret_cast<uint4*>(stage + lane * 128 + ((g ^ (lane & 7)) << 4)) =
           make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]), pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+    }
+    __syncwarp();
+    {
+      const int rr = lane >> 3, ch = lane & 7;
+      __nv_bfloat16* dst = p.ctx + (long long)(row0 + qt * kTile + q * 32) * p.D + h * kDh + ch * 8;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + rr;
+        *reinterpret_cast<uint4*>(dst + (long long)row * p.D) =
+            *reinterpret_cast<const uint4*>(stage + row * 128 + ((ch ^ (row & 7)) << 4));
+      }
     }
   }
   if (tr && threadIdx.x == 64) tr[9] = clock64();

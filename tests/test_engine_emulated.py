@@ -177,3 +177,22 @@ def test_cpu_without_backend_raises():
     m = Dinov2PoseModel(backbone="test/dinov2-tiny").eval()
     with pytest.raises(RuntimeError, match="no CPU execution path"):
         m(torch.zeros(1, 3, 224, 224))
+
+
+def test_backbone_tile_selection(monkeypatch):
+    """PoseEngine.tile: 128-row single-CTA tiles at K = 384 (192 columns for fc1), 256 x 256 CTA-pair tiles for D >= 768
+    at batch sizes that fill the chip; every N the pair kernel is asked for is a multiple of 256."""
+    from dino_pose_b200.engine import PoseEngine
+
+    def eng(D, L, heads):
+        return PoseEngine({}, {}, dict(D=D, L=L, heads=heads, num_keypoints=24, heatmap_size=48, z_hidden=(8,)), TorchEmulator(),
+                          torch.device("cpu"))
+    s = eng(384, 12, 6)
+    assert s.tile("fc1", 16448) == {"block_n": 192} and s.tile("fc2", 16448) == {"block_n": 0} and s.tile("qkv", 16448) == {}
+    for D, L, h in ((768, 12, 12), (1024, 24, 16)):
+        e = eng(D, L, h)
+        for which, n in (("qkv", 3 * D), ("proj", D), ("fc1", 4 * D), ("fc2", D)):
+            assert e.tile(which, 32896) == {"block_n": 256, "cta_pair": 1} and n % 256 == 0
+            assert "cta_pair" not in e.tile(which, 257)          # batch 1: too few tiles for pairs
+    monkeypatch.setenv("DP_PAIR_WIDE", "0")
+    assert "cta_pair" not in eng(768, 12, 12).tile("fc2", 32896)

@@ -138,3 +138,54 @@ def test_data_parallel_world2_gloo():
         assert err < 1e-5, (rank, err)
         assert nb >= 3 and ok_cover, (rank, nb)
         assert same and moved
+
+
+def test_trainer_unfrozen_layer_matches_reference_loop():
+    """PoseTrainer over Dinov2PoseModel(unfreeze_last_n_layers=1) (reference model/dinov2_pose.py:25-39): two AdamW steps
+    move the un-frozen encoder layer like the reference loop does (oracle forward, train.py losses, torch AdamW), the
+    frozen layer stays put, and the flat layout puts the q / k / v gradient triples in contiguous slices."""
+    from dino_pose_b200.model import Dinov2PoseModel
+    lr, wd, steps, eps = 1e-3, 1e-2, 2, 1e-3
+    batches = [make_inputs(3, 224, 224, s) for s in range(steps)]
+    m = Dinov2PoseModel(backbone=ARCH, unfreeze_last_n_layers=1)
+    m.load_state_dict(make_state_dict(ARCH, 0, 0))
+    for mod in m.modules():
+        if isinstance(mod, torch.nn.Dropout):
+            mod.p = 0.0
+    m._backend_factory = TorchEmulator
+    m._act_dtype = torch.float32
+    tr = PoseTrainer(m.train(), lr=lr, weight_decay=wd, eps=eps, use_graph=False)
+    lay = tr.layout
+    ap = "backbone.encoder.layer.1.attention.attention."
+    oq, ok_, ov = (lay["offsets"][ap + n + ".weight"][0] for n in ("query", "key", "value"))
+    assert ok_ - oq == ov - ok_ == 128 * 128
+    for b in batches:
+        tr.step(b["pixel_values"], b["heatmaps"], b["keypoints"], b["z"])
+    # reference loop
+    sd = make_state_dict(ARCH, 0, 0)
+    init = {k: v.clone() for k, v in sd.items()}
+    names = pose_oracle.trainable_names(sd, None, unfreeze=1, arch=ARCH)
+    opt = torch.optim.AdamW([sd[n].requires_grad_(True) for n in names], lr=lr, weight_decay=wd, eps=eps)
+    w = pose_oracle.DynamicLossWeighting()
+    for b in batches:
+        opt.zero_grad(set_to_none=True)
+        hm, z = pose_oracle.model_forward(sd, b["pixel_values"], ARCH, None, training=True)
+        conf = b["keypoints"][..., 2]
+        kp, zl = pose_oracle.keypoint_loss(hm, b["heatmaps"], conf), pose_oracle.z_loss(z, b["z"], conf)
+        w.update(kp.item(), zl.item())
+        w.balanced(kp, zl).backward()
+        opt.step()
+    params = dict(m.named_parameters())
+    assert set(n for n, p in params.items() if p.requires_grad) == set(names)
+    worst = 0.0
+    for n in names:
+        if not n.startswith("backbone."):
+            continue
+        a, b = params[n].detach(), sd[n].detach()
+        moved = (b - init[n]).norm().item()
+        if moved < 1e-7:
+            continue
+        worst = max(worst, ((a - b).norm() / moved).item())
+    assert worst < 8e-2, worst      # error relative to the 2-step UPDATE (fp32 noise through Adam, as in the LoRA test)
+    frozen = "backbone.encoder.layer.0.mlp.fc1.weight"
+    assert torch.equal(params[frozen].detach(), init[frozen])

@@ -15,6 +15,9 @@ from __future__ import annotations
 import argparse
 import json
 import os
+
+# random-init weights of the named architecture (BASELINE.json north_star: no network, no checkpoints): explicit opt-in
+os.environ.setdefault("DINO_POSE_RANDOM_INIT", "1")
 import subprocess
 import sys
 import threading

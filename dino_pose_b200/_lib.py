@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdinopose_sm100a.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 c_ll = C.c_longlong
 c_vp = C.c_void_p
@@ -112,6 +112,7 @@ SIGNATURES = {
     "dp_relu_mask": [c_vp, c_vp, c_vp, c_ll, f, c_vp],
     "dp_pose_loss": [c_vp, c_vp, c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, i, i, f, f, c_vp],
     "dp_adamw": [c_vp, c_vp, c_vp, c_vp, c_ll, f, f, f, f, f, f, c_vp, c_vp],
+    "dp_adamw_dev": [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, f, f, f, f, c_vp, c_vp],
     "dp_pack_weights_bf16": [c_vp, i, c_ll, c_vp],
     "dp_add_i64": [c_vp, i, c_ll, c_vp],
 }

@@ -161,9 +161,19 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
                           !e.scale && !e.ls && !e.residual && !e.aux_out && !e.aux_in && !e.stats && a->act != DP_ACT_RELU &&
                           (e.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && dbg == 0;
   const GemmVariant* var = nullptr;
-  const bool may_pair = (allow_pair || a->cta_pair == 1) && a->cta_pair != 2 && a->M > 128;
-  const bool may_single = a->cta_pair != 1;
-  if (a->block_n != 0) {
+  const bool may_pair = (allow_pair || a->cta_pair == 1) && a->cta_pair != 2 && a->cta_pair != 3 && a->M > 128;
+  const bool may_single = a->cta_pair != 1 && a->cta_pair != 3;
+  // A-stationary TS-mode kernel (gemm_astat.cuh): plain K-major A with K <= 512, 128-wide tiles, several tiles per row block.
+  // cta_pair = 3 requests it, DP_GEMM_ASTAT=0 keeps it out of the automatic choice.
+  static int allow_astat = -1;
+  if (allow_astat < 0) { const char* v = getenv("DP_GEMM_ASTAT"); allow_astat = v ? atoi(v) : 1; }
+  const bool astat_shape = a->a_mode == 0 && a->K <= 512 && (a->K % 64) == 0 && a->N >= 256 && e.row_map == DP_ROWMAP_IDENTITY &&
+                           (a->block_n == 0 || a->block_n == 128) && !e.stats && !e.scale;
+  if (astat_shape && (a->cta_pair == 3 || (a->cta_pair == 0 && allow_astat && a->M >= 2048)))
+    var = select_gemm_variant(e, a->a_mode, 128, 2, tma_out_ok);
+  if (a->cta_pair == 3 && !var) return set_error(-3, "dp_gemm_bf16: no A-stationary variant for this shape / epilogue");
+  if (var) {
+  } else if (a->block_n != 0) {
     if (may_pair) var = select_gemm_variant(e, a->a_mode, a->block_n, 1, false);
     if (!var && may_single) var = select_gemm_variant(e, a->a_mode, a->block_n, 0, tma_out_ok);
   } else {
@@ -215,7 +225,7 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   {
     const uint64_t dims[2] = {uint64_t(a->K), uint64_t(a->N)};
     const uint64_t st[1] = {uint64_t(a->ldw) * 2};
-    const uint32_t box[2] = {64, uint32_t(var->pair ? bn / 2 : bn)};   // a pair CTA stages half of the weight rows
+    const uint32_t box[2] = {64, uint32_t(var->pair == 1 ? bn / 2 : bn)};   // a pair CTA stages half of the weight rows
     if ((rc = make_tmap(&p.tmB, a->W, 2, dims, st, box))) return rc;
   }
   if (var->opt & 128) {   // OP_TMA_OUT: 32 x 32 bf16 boxes, 64-byte rows, 64B swizzle; columns >= n_valid and rows >= M are clipped
@@ -225,7 +235,10 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
     if ((rc = make_tmap(&p.tmC, e.out, 2, dims, st, box, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
   }
   int grid;
-  if (var->pair) {
+  if (var->pair == 2) {
+    const int tiles = p.m_tiles * p.n_tiles;
+    grid = tiles < sm_count() ? tiles : sm_count();
+  } else if (var->pair) {
     const int tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
     grid = 2 * clusters;

@@ -420,7 +420,7 @@ __device__ __forceinline__ void epilogue_tma_prefetch(const GemmParams& p, int h
 template <int BN, int ACT>
 __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, uint32_t tmem_acc, int q, int half, int lane,
                                                   int m_blk, int n_blk, uint8_t* __restrict__ stg, uint32_t& nstore,
-                                                  const TmaEpiBias<BN>& pre) {
+                                                  const TmaEpiBias<BN>& pre, long long* __restrict__ tr = nullptr) {
   const Epilogue& e = p.epi;
   constexpr uint32_t kFull = 0xffffffffu;
   int i = 0;
@@ -429,8 +429,10 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, uint32_t 
     const int col0 = n_blk * BN + c * 32;
     if (col0 >= e.n_valid) continue;  // warp-uniform
     uint32_t v[32];
+    if (tr && i == 0) tr[0] = clock64();
     tmem_ld_32x32(tmem_acc + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
     tmem_ld_wait();
+    if (tr && i == 0) tr[1] = clock64();
     const float bl = pre.v[i];
     uint32_t pk[16];
 #pragma unroll
@@ -445,10 +447,12 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, uint32_t 
       pk[j] = pack_bf16x2(f0, f1);
     }
     uint8_t* buf = stg + (nstore & 1u) * 2048u;
+    if (tr && i == 0) tr[2] = clock64();
     if (nstore >= 2) {   // the store issued two chunks ago has to be done reading this buffer
       if (lane == 0) bulk_wait_read<1>();
       __syncwarp();
     }
+    if (tr && i == 0) tr[3] = clock64();
     // row = lane, 64 bytes per row; 16-byte piece j lands at j ^ ((row >> 1) & 3) (CU_TENSOR_MAP_SWIZZLE_64B)
     uint8_t* rowp = buf + lane * 64;
     const int sw = (lane >> 1) & 3;
@@ -461,6 +465,7 @@ __device__ __forceinline__ void epilogue_tile_tma(const GemmParams& p, uint32_t 
       tma_store_2d(&p.tmC, buf, col0, m_blk * kBlockM + q * 32);
       bulk_commit();
     }
+    if (tr && i == 0) tr[4] = clock64();
     ++nstore;
   }
 }
@@ -537,15 +542,20 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
           mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
           uint8_t* sa = smem + ps.stage * C::kStageBytes;
           uint8_t* sb = sa + kABytes;
-          mbar_arrive_expect_tx(&full_bar[ps.stage], C::kStageBytes);
-          if (conv) {
+          // tuning knobs: 16 = A tile loaded only for the first k-blocks of the launch (A-stationary emulation),
+          // 32 = same for the weight tile; results are garbage by design
+          const bool skip_a = (p.epi.debug & 16) && (tile != (int)blockIdx.x);
+          const bool skip_b = (p.epi.debug & 32) && (tile != (int)blockIdx.x);
+          mbar_arrive_expect_tx(&full_bar[ps.stage], (skip_a ? 0 : kABytes) + (skip_b ? 0 : C::kBBytes));
+          if (skip_a) {
+          } else if (conv) {
             const int ky = tap / p.kw, kx = tap - ky * p.kw;
             tma_load_4d(sa, &p.tmA, &full_bar[ps.stage], cb * kBlockK, x0 + kx - p.pad_x, y0 + ky - p.pad_y, b0);
             if (++cb == p.cin_blocks) { cb = 0; ++tap; }
           } else {
             tma_load_2d(sa, &p.tmA, &full_bar[ps.stage], kb * kBlockK, m_blk * kBlockM);
           }
-          tma_load_2d(sb, &p.tmB, &full_bar[ps.stage], kb * kBlockK, n_blk * BN);
+          if (!skip_b) tma_load_2d(sb, &p.tmB, &full_bar[ps.stage], kb * kBlockK, n_blk * BN);
           ps.template advance<C::kStages>();
         }
       }
@@ -598,7 +608,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
         mbar_wait(&tfull_bar[acc], acc_phase);
         tc_fence_after();
         epilogue_tile_tma<BN, ACT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk,
-                                   reinterpret_cast<uint8_t*>(stg), nstore, pre);
+                                   reinterpret_cast<uint8_t*>(stg), nstore, pre, tr);
       } else {
         int nm = -1, nn = -1;
         if constexpr ((OPT & OP_AUX_IN) != 0) {

@@ -266,9 +266,9 @@ template <int BN> cudaError_t launch_wgrad_t(const WgradParams& p, int grid, cud
 }  // namespace
 
 extern const GemmVariant kGemmVariantsA[], kGemmVariantsB[], kGemmVariantsC[], kGemmVariantsD[], kGemmVariantsGeneric[],
-    kGemmVariantsPair[];
+    kGemmVariantsPair[], kGemmVariantsAstat[];
 extern const int kNumGemmVariantsA, kNumGemmVariantsB, kNumGemmVariantsC, kNumGemmVariantsD, kNumGemmVariantsGeneric,
-    kNumGemmVariantsPair;
+    kNumGemmVariantsPair, kNumGemmVariantsAstat;
 
 // Pick the cheapest compiled variant (single-CTA or CTA-pair, as requested) whose compile-time feature set covers
 // what this launch needs; nullptr if none is compiled for this tile width.
@@ -281,13 +281,13 @@ const GemmVariant* select_gemm_variant(const Epilogue& e, int a_mode, int block_
   if (e.aux_in) need |= OP_AUX_IN;
   if (e.stats) need |= OP_STATS;
   if (a_mode == 1) need |= OP_CONV;
-  const GemmVariant* tables[6] = {kGemmVariantsA, kGemmVariantsB, kGemmVariantsC, kGemmVariantsD, kGemmVariantsGeneric,
-                                  kGemmVariantsPair};
-  const int counts[6] = {kNumGemmVariantsA, kNumGemmVariantsB, kNumGemmVariantsC, kNumGemmVariantsD, kNumGemmVariantsGeneric,
-                         kNumGemmVariantsPair};
+  const GemmVariant* tables[7] = {kGemmVariantsA, kGemmVariantsB, kGemmVariantsC, kGemmVariantsD, kGemmVariantsGeneric,
+                                  kGemmVariantsPair, kGemmVariantsAstat};
+  const int counts[7] = {kNumGemmVariantsA, kNumGemmVariantsB, kNumGemmVariantsC, kNumGemmVariantsD, kNumGemmVariantsGeneric,
+                         kNumGemmVariantsPair, kNumGemmVariantsAstat};
   const GemmVariant* best = nullptr;
   int best_cost = 1 << 30;
-  for (int t = 0; t < 6; ++t)
+  for (int t = 0; t < 7; ++t)
     for (int i = 0; i < counts[t]; ++i) {
       const GemmVariant& v = tables[t][i];
       if (v.bn != block_n || v.pair != pair) continue;

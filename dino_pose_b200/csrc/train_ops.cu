@@ -120,8 +120,12 @@ __global__ void __launch_bounds__(256) pose_loss_grad_kernel(const float4* __res
 // p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps).   step_dev holds t-1 on entry; thread 0 bumps it.
 __global__ void __launch_bounds__(256) adamw_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                                                     float4* __restrict__ v, long long n4, float lr, float b1, float b2,
-                                                    float eps, float wd, float grad_scale, const long long* __restrict__ step_dev) {
+                                                    float eps, float wd, float grad_scale, const long long* __restrict__ step_dev,
+                                                    const float* __restrict__ hyper) {
   pdl_grid_sync();
+  // hyper = device {lr, weight_decay}: a scheduler (train.py:286-293, ReduceLROnPlateau) changes the rate between
+  // replays of the captured step without re-recording it
+  if (hyper != nullptr) { lr = hyper[0]; wd = hyper[1]; }
   const float t = float(*step_dev + 1);
   const float bc1 = 1.f - powf(b1, t), bc2 = 1.f - powf(b2, t);
   const float step_size = lr / bc1, inv_sqrt_bc2 = rsqrtf(bc2), decay = 1.f - lr * wd;
@@ -164,13 +168,13 @@ cudaError_t launch_pose_loss(const float* hm, const float* thm, const float* kps
 }
 
 cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                         float wd, float grad_scale, long long* step_dev, int sms, cudaStream_t s) {
+                         float wd, float grad_scale, long long* step_dev, const float* hyper, int sms, cudaStream_t s) {
   const long long n4 = n / 4;
   int grid = int((n4 + 255) / 256);
   if (grid > sms * 8) grid = sms * 8;
   if (grid < 1) grid = 1;
   launch_k<adamw_kernel>(grid, 256, 0, s, reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
-                                    reinterpret_cast<float4*>(v), n4, lr, b1, b2, eps, wd, grad_scale, step_dev);
+                                    reinterpret_cast<float4*>(v), n4, lr, b1, b2, eps, wd, grad_scale, step_dev, hyper);
   launch_k<bump_step_kernel>(1, 1, 0, s, step_dev);
   return cudaGetLastError();
 }

@@ -1132,6 +1132,7 @@ class PoseEngine:
         plan["t"]["px"].copy_(pixel_values, non_blocking=True)
         if training:
             self.seed.add_(1)
+            plan["generation"] = plan.get("generation", 0) + 1   # stamps the contents of the saved-activation buffers
             plan["fwd"].run()
             return plan
         # inference: the ~130 launches of the forward program are replayed as ONE CUDA graph (batch-1 latency is

@@ -8,6 +8,8 @@ modeling_dinov2.py:97-116,141-149,203-234,249-252,272-278,324-328,367-386,473-47
 """
 from __future__ import annotations
 
+import os
+import warnings
 from types import SimpleNamespace
 
 import torch
@@ -155,17 +157,34 @@ class Dinov2Model(nn.Module):
         nn.init.trunc_normal_(self.embeddings.cls_token, mean=0.0, std=std)
 
     @classmethod
-    def from_pretrained(cls, name, *_, **__):
-        """Build the named architecture.  Weights: a locally cached HF checkpoint if one exists (same
-        ``state_dict`` keys), otherwise HF-style random init (no network in this environment)."""
+    def from_pretrained(cls, name, *args, **kwargs):
+        """``transformers.Dinov2Model.from_pretrained`` for the named architecture (reference model/dinov2_pose.py:13,180).
+
+        The checkpoint is loaded through HuggingFace (cache or hub; ``local_files_only`` and the other keyword
+        arguments are passed on, ``HF_HUB_OFFLINE`` is honoured by HF itself) with ``strict=True`` and every failure
+        PROPAGATES: a fine-tuning run on a silently random backbone is meaningless.  Random initialisation
+        (HF ``_init_weights``) is an explicit opt-in -- ``DINO_POSE_RANDOM_INIT=1`` in the environment, or a
+        ``test/...`` architecture -- and is announced with a warning; the benchmark and the tests use it because this
+        environment has no network and no checkpoints."""
         model = cls(make_config(name))
-        if name.startswith("facebook/"):
-            try:
-                from transformers import Dinov2Model as HFModel
-                hf = HFModel.from_pretrained(name, local_files_only=True)
-                model.load_state_dict(hf.state_dict(), strict=True)
-            except Exception:
-                pass
+        if name.startswith("test/"):
+            return model
+        if os.environ.get("DINO_POSE_RANDOM_INIT", "0") not in ("", "0"):
+            warnings.warn(f"Dinov2Model.from_pretrained({name!r}): DINO_POSE_RANDOM_INIT is set -- the backbone is RANDOMLY "
+                          "initialised (no pretrained weights were loaded); results are only meaningful for benchmarking "
+                          "and parity tests", RuntimeWarning, stacklevel=2)
+            return model
+        try:
+            from transformers import Dinov2Model as HFModel
+        except Exception as ex:   # no transformers: say what to do instead of training on noise
+            raise RuntimeError(f"loading the pretrained backbone {name!r} needs `transformers` ({ex}); set "
+                               "DINO_POSE_RANDOM_INIT=1 to opt in to a randomly initialised backbone") from ex
+        try:
+            hf = HFModel.from_pretrained(name, *args, **kwargs)
+        except Exception as ex:
+            raise RuntimeError(f"could not load the pretrained backbone {name!r} ({type(ex).__name__}: {ex}); set "
+                               "DINO_POSE_RANDOM_INIT=1 to opt in to a randomly initialised backbone") from ex
+        model.load_state_dict(hf.state_dict(), strict=True)
         return model
 
     def forward(self, pixel_values):

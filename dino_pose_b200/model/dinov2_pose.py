@@ -3,6 +3,7 @@
 """
 from __future__ import annotations
 
+import warnings
 from types import SimpleNamespace
 from typing import Any, Dict
 
@@ -33,11 +34,22 @@ class _PoseFunction(torch.autograd.Function):
         eng = model._get_engine(pixel_values.device)
         plan = eng.forward(pixel_values, training=True)
         ctx.eng, ctx.plan, ctx.names = eng, plan, model._trainable_names
+        # The saved activations of this graph are the plan's STATIC buffers.  A later train-mode forward with the same
+        # (batch, H, W) overwrites them; the stamp lets backward() detect that instead of returning wrong gradients.
+        ctx.generation = plan["generation"]
         ctx.mark_non_differentiable()
         return plan["t"]["hm"].clone(), plan["t"]["z"].clone()
 
     @staticmethod
     def backward(ctx, dhm, dz):
+        if ctx.plan["generation"] != ctx.generation or ctx.plan.get("consumed") == ctx.generation:
+            raise RuntimeError(
+                "dino_pose_b200: backward() of a forward pass whose saved activations are gone -- the model keeps ONE set "
+                "of activation buffers per (batch, height, width), so each train-mode forward must be followed by its "
+                "backward before the next forward of the same shape, and a graph can be back-propagated once "
+                "(no retain_graph double backward).  Run forward/backward pairs in order, or use a different batch size "
+                "for the second view.")
+        ctx.plan["consumed"] = ctx.generation
         grads = ctx.eng.backward(ctx.plan, dhm, dz)
         return (None, None) + tuple(grads[n].clone() for n in ctx.names)
 
@@ -118,7 +130,14 @@ class _Dinov2PoseBase(BasePoseModel):
         self._trainable_names = [n for n, p in self.named_parameters() if p.requires_grad]
         needs_grad = torch.is_grad_enabled() and self.training and bool(self._trainable_names)
         if not self.training and torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            needs_grad = False   # eval-mode forward: inference program, no graph (see DESIGN.md "eval + grad")
+            # eval-mode forward: the inference program (folded BatchNorm, merged LoRA) records no graph.  The reference is
+            # differentiable here; say so loudly instead of silently returning detached outputs.
+            needs_grad = False
+            if not getattr(self, "_warned_eval_grad", False):
+                warnings.warn("dino_pose_b200: forward() in eval mode with autograd enabled returns outputs WITHOUT a graph "
+                              "(the inference program is not differentiable); wrap inference in torch.no_grad() or call "
+                              "model.train() for a differentiable forward", RuntimeWarning, stacklevel=2)
+                self._warned_eval_grad = True
         if needs_grad:
             params = [p for p in self.parameters() if p.requires_grad]
             return _PoseFunction.apply(self, pixel_values, *params)

@@ -35,6 +35,23 @@ def z_loss(pred_z, target_z, conf):
     return (pred_z * mask - target_z * mask).abs().mean()
 
 
+class _ParamGroup(dict):
+    """``optimizer.param_groups[0]`` look-alike: assigning ``group['lr']`` (what torch's schedulers do) updates the device
+    scalar the AdamW kernel reads."""
+
+    def __init__(self, trainer, **kw):
+        super().__init__(**kw)
+        self._trainer = trainer
+
+    def __setitem__(self, key, value):
+        if key == "lr":
+            self._trainer.set_lr(lr=value)
+        elif key == "weight_decay":
+            self._trainer.set_lr(weight_decay=value)
+        else:
+            super().__setitem__(key, value)
+
+
 class PoseTrainer:
     """AdamW fine-tuning of a ``Dinov2PoseModelLoRA`` / ``Dinov2PoseModel`` on this rank's shard of the batch.
 
@@ -58,6 +75,10 @@ class PoseTrainer:
         self.exp_avg = torch.zeros(n, device=dev)
         self.exp_avg_sq = torch.zeros(n, device=dev)
         self.step_dev = torch.zeros((), dtype=torch.int64, device=dev)
+        # learning rate / weight decay live on the device: the recorded (and graph-captured) AdamW launch reads them there,
+        # so a scheduler (reference train.py:286-293, ReduceLROnPlateau(factor=0.7)) can change them between steps
+        self.hyper = torch.tensor([lr, weight_decay], dtype=torch.float32, device=dev)
+        self.param_groups = [_ParamGroup(self, lr=lr, weight_decay=weight_decay, betas=betas, eps=eps)]
         self.loss_sums = torch.zeros(2, dtype=torch.float64, device=dev)
         self.loss_state = torch.tensor([0.0, 0.0, 0.0, 0.1], device=dev)   # kp_avg, z_avg, started, weight (train.py:18)
         self.loss_out = torch.zeros(3, device=dev)
@@ -82,6 +103,61 @@ class PoseTrainer:
         model._engine = None        # plans recorded on the old parameter storage are stale
         self.engine = model._get_engine(self.device)
 
+    # ------------------------------------------------------------------ optimizer surface (torch.optim.AdamW look-alike)
+    def set_lr(self, lr=None, weight_decay=None):
+        """Change the learning rate / weight decay of every following step (also of an already captured graph)."""
+        if lr is not None:
+            self.lr = float(lr)
+            self.hyper[0:1].fill_(self.lr)
+            dict.__setitem__(self.param_groups[0], "lr", self.lr)
+        if weight_decay is not None:
+            self.wd = float(weight_decay)
+            self.hyper[1:2].fill_(self.wd)
+            dict.__setitem__(self.param_groups[0], "weight_decay", self.wd)
+
+    def state_dict(self):
+        """Everything `train.py:304-318` checkpoints about the optimizer side: AdamW moments and step counter (per
+        parameter NAME, so a checkpoint survives a change of the flat layout), hyper-parameters, the loss-weighting
+        state (`checkpoint['loss_weight']`, DynamicLossWeighting :17-69) and the dropout seed counter."""
+        lay = self.layout
+        per = {}
+        for name in lay["names"]:
+            off, k = lay["offsets"][name]
+            shape = tuple(dict(self.model.named_parameters())[name].shape)
+            per[name] = {"exp_avg": self.exp_avg[off:off + k].detach().clone().view(shape),
+                         "exp_avg_sq": self.exp_avg_sq[off:off + k].detach().clone().view(shape)}
+        ls = self.loss_state.tolist()
+        return {"state": per, "step": int(self.step_dev.item()),
+                "param_groups": [{"lr": self.lr, "weight_decay": self.wd, "betas": tuple(self.betas), "eps": self.eps}],
+                "loss_weighting": {"kp_loss_avg": ls[0], "z_loss_avg": ls[1], "started": ls[2], "weight": ls[3]},
+                "dropout_seed": int(self.engine.seed.item()) if self.engine.seed is not None else 0}
+
+    def load_state_dict(self, sd, loss_weight=None):
+        """Inverse of ``state_dict``; ``loss_weight`` alone restores the reference checkpoint's `loss_weight` entry."""
+        lay = self.layout
+        with torch.no_grad():
+            for name, st in sd.get("state", {}).items():
+                if name not in lay["offsets"]:
+                    raise KeyError(f"optimizer state for unknown / non-trainable parameter {name!r}")
+                off, k = lay["offsets"][name]
+                self.exp_avg[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                self.exp_avg_sq[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+            if "step" in sd:
+                self.step_dev.fill_(int(sd["step"]))
+            for g in sd.get("param_groups", [])[:1]:
+                if tuple(g.get("betas", self.betas)) != tuple(self.betas) or g.get("eps", self.eps) != self.eps:
+                    # betas / eps are immediates of the recorded launch: re-record the optimizer programs
+                    self.betas, self.eps = tuple(g.get("betas", self.betas)), g.get("eps", self.eps)
+                    self._steps = {}
+                self.set_lr(g.get("lr"), g.get("weight_decay"))
+            lw = sd.get("loss_weighting")
+            if lw is not None:
+                self.loss_state.copy_(torch.tensor([lw["kp_loss_avg"], lw["z_loss_avg"], lw["started"], lw["weight"]]))
+            if loss_weight is not None:
+                self.loss_state[3:4].fill_(float(loss_weight))
+            if "dropout_seed" in sd and self.engine.seed is not None:
+                self.engine.seed.fill_(int(sd["dropout_seed"]))
+
     @property
     def weighting_state(self):
         """(kp_loss_avg, z_loss_avg, weight) of the reference's DynamicLossWeighting, read back from the device."""
@@ -103,7 +179,7 @@ class PoseTrainer:
         st["opt"] = be.begin()
         be.adamw(self.flat_params, plan["gflat"], self.exp_avg, self.exp_avg_sq, self.step_dev, n=self.layout["total"],
                  lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.wd,
-                 grad_scale=1.0 / self.world)
+                 grad_scale=1.0 / self.world, hyper=self.hyper)
         st["graph"] = None
         return st
 

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 4
+#define DP_ABI_VERSION 5
 
 const char* dp_last_error(void);
 int dp_abi_version(void);
@@ -226,6 +226,11 @@ int dp_pose_loss(const float* heatmaps, const float* target_heatmaps, const floa
  * device int64 holding the number of steps taken so far and is incremented. */
 int dp_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
              float beta2, float eps, float weight_decay, float grad_scale, long long* step_dev, void* stream);
+/* Same step with the learning rate and the weight decay read from DEVICE memory, hyper_dev = fp32 {lr, weight_decay}:
+ * the reference's ReduceLROnPlateau (train.py:286-293,341) changes the rate between steps, and a step captured in a
+ * CUDA graph would otherwise keep the value it was recorded with. */
+int dp_adamw_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, const float* hyper_dev,
+                 float beta1, float beta2, float eps, float grad_scale, long long* step_dev, void* stream);
 
 /* Re-pack trainable conv weights (fp32 [d0,d1,kh,kw] nn.Parameters, reference model/pose_heads.py) into the bf16 GEMM
  * layouts, all layers in one launch.  jobs_dev: device table, 16 int64 per job =

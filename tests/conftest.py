@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# no network / no checkpoints here: every model in the suite is built with random-init weights of the named architecture
+os.environ.setdefault("DINO_POSE_RANDOM_INIT", "1")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)

@@ -102,8 +102,11 @@ class TorchEmulator:
             dz.view(B, K).copy_(s1 * mask.view(B, K) * torch.sign(zd))
         self.prog.calls.append(fn)
 
-    def adamw(self, p, g, m, v, step_dev, *, n, lr, beta1, beta2, eps, weight_decay, grad_scale):
+    def adamw(self, p, g, m, v, step_dev, *, n, lr, beta1, beta2, eps, weight_decay, grad_scale, hyper=None):
+        lr0, wd0 = lr, weight_decay
+
         def fn():
+            lr, weight_decay = (float(hyper[0]), float(hyper[1])) if hyper is not None else (lr0, wd0)
             t = int(step_dev.item()) + 1
             gg = g[:n] * grad_scale
             p[:n].mul_(1 - lr * weight_decay)

@@ -196,3 +196,27 @@ def test_backbone_tile_selection(monkeypatch):
             assert "cta_pair" not in e.tile(which, 257)          # batch 1: too few tiles for pairs
     monkeypatch.setenv("DP_PAIR_WIDE", "0")
     assert "cta_pair" not in eng(768, 12, 12).tile("fc2", 32896)
+
+
+def test_stale_activation_buffers_are_detected():
+    """the autograd node saves no activations of its own (they are the plan's static buffers); a second
+    train-mode forward of the same shape, or a second backward of the same graph, must raise instead of silently
+    returning gradients computed from another pass's activations.  Eval + autograd warns (no graph is recorded)."""
+    arch = "test/dinov2-tiny"
+    m = build(arch, 8, act_dtype=torch.float32).train()
+    a, b = make_inputs(2, 224, 224, 0), make_inputs(2, 224, 224, 1)
+    hm_a, _ = m(a["pixel_values"])
+    hm_b, _ = m(b["pixel_values"])          # overwrites the buffers hm_a's backward would read
+    with pytest.raises(RuntimeError, match="saved activations are gone"):
+        hm_a.sum().backward()
+    hm_b.sum().backward(retain_graph=True)  # the latest pass is fine ...
+    with pytest.raises(RuntimeError, match="saved activations are gone"):
+        hm_b.sum().backward()               # ... once
+    m.zero_grad()
+    hm_c, z_c = m(a["pixel_values"])
+    (hm_c.sum() + z_c.sum()).backward()     # ordinary forward / backward pairs keep working
+    assert any(p.grad is not None and p.grad.abs().sum() > 0 for p in m.parameters())
+    m.eval()
+    with pytest.warns(RuntimeWarning, match="WITHOUT a graph"):
+        hm_e, _ = m(a["pixel_values"])
+    assert not hm_e.requires_grad

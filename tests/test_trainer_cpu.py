@@ -87,6 +87,45 @@ def test_trainer_matches_reference_loop():
     assert set(lay["names"]) == set(names)
 
 
+def test_trainer_lr_schedule_and_state_dict():
+    """the learning rate is a device scalar the recorded AdamW launch reads (a scheduler's `group['lr'] = x`
+    takes effect on the next step), and state_dict / load_state_dict round-trip the moments, the step counter, the
+    loss-weighting state and the rate (reference train.py:286-318 checkpoints and restores all of these)."""
+    batches = [make_inputs(2, 224, 224, s) for s in range(4)]
+
+    def run(tr, rng):
+        for s in rng:
+            b = batches[s]
+            tr.step(b["pixel_values"], b["heatmaps"], b["keypoints"], b["z"])
+
+    # lr = 0 freezes the parameters; raising it through the param group moves them without rebuilding anything
+    ta = PoseTrainer(build_model(), lr=0.0, weight_decay=0.0, eps=1e-3, use_graph=False)
+    p0 = ta.flat_params.clone()
+    run(ta, [0])
+    assert torch.equal(ta.flat_params, p0)
+    ta.param_groups[0]["lr"] = 1e-3
+    assert ta.lr == 1e-3 and abs(float(ta.hyper[0]) - 1e-3) < 1e-9
+    run(ta, [1])
+    assert (ta.flat_params - p0).abs().max().item() > 0
+    # checkpoint after 2 steps, resume in a fresh trainer, compare with an uninterrupted run
+    tb = PoseTrainer(build_model(), lr=1e-3, weight_decay=1e-2, eps=1e-3, use_graph=False)
+    run(tb, [0, 1])
+    ck_model = {k: v.clone() for k, v in tb.model.state_dict().items()}
+    ck_opt = tb.state_dict()
+    run(tb, [2, 3])
+    m2 = build_model()
+    m2.load_state_dict(ck_model)
+    tc = PoseTrainer(m2.train(), lr=5.0, weight_decay=0.5, eps=1e-3, use_graph=False)   # wrong on purpose: must be restored
+    tc.load_state_dict(ck_opt)
+    assert tc.lr == 1e-3 and tc.wd == 1e-2 and int(tc.step_dev.item()) == 2
+    run(tc, [2, 3])
+    assert torch.allclose(tc.flat_params, tb.flat_params, rtol=0, atol=1e-6)
+    assert torch.allclose(tc.exp_avg, tb.exp_avg, rtol=1e-5, atol=1e-9)
+    assert abs(tc.weighting_state["weight"] - tb.weighting_state["weight"]) < 1e-7
+    tc.load_state_dict({}, loss_weight=0.25)      # reference checkpoint['loss_weight']
+    assert abs(tc.weighting_state["weight"] - 0.25) < 1e-7
+
+
 def _dp_worker(rank, world, port, q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)

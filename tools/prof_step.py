@@ -3,6 +3,9 @@
 with nothing else in the process -- the command ncu wraps (profiles/README.md).  Not a benchmark."""
 import argparse
 import os
+
+# random-init weights of the named architecture (BASELINE.json north_star: no network, no checkpoints): explicit opt-in
+os.environ.setdefault("DINO_POSE_RANDOM_INIT", "1")
 import sys
 
 import torch

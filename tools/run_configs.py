@@ -3,6 +3,9 @@
 configs[1] is the benchmark (bench.py); the others are reported in profiles/ as supporting numbers."""
 import json
 import os
+
+# random-init weights of the named architecture (BASELINE.json north_star: no network, no checkpoints): explicit opt-in
+os.environ.setdefault("DINO_POSE_RANDOM_INIT", "1")
 import sys
 import time
 

@@ -112,6 +112,13 @@ extern "C" int dp_abi_version(void) { return DP_ABI_VERSION; }
 extern "C" int dp_sizeof_gemm_args(void) { return int(sizeof(dp_gemm_args)); }
 extern "C" int dp_sizeof_wgrad_args(void) { return int(sizeof(dp_wgrad_args)); }
 
+static long long* g_trace_buf = nullptr;
+// tuning aid (DP_GEMM_TRACE=2): copy the trace buffer of the most recent traced launch to the host (synchronises)
+extern "C" int dp_debug_read_trace(long long* host, int n) {
+  if (!g_trace_buf || !host || n <= 0 || n > 4096) return set_error(-1, "dp_debug_read_trace: no trace buffer");
+  cudaDeviceSynchronize();
+  return cuda_error(cudaMemcpy(host, g_trace_buf, size_t(n) * sizeof(long long), cudaMemcpyDeviceToHost), "dp_debug_read_trace");
+}
 extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   if (!a || !a->A || !a->W || !a->out) return set_error(-1, "dp_gemm_bf16: null pointer");
   if (a->M <= 0 || a->N <= 0 || a->K <= 0) return set_error(-2, "dp_gemm_bf16: bad shape M=%d N=%d K=%d", a->M, a->N, a->K);
@@ -161,17 +168,21 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
                           !e.scale && !e.ls && !e.residual && !e.aux_out && !e.aux_in && !e.stats && a->act != DP_ACT_RELU &&
                           (e.ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && dbg == 0;
   const GemmVariant* var = nullptr;
-  const bool may_pair = (allow_pair || a->cta_pair == 1) && a->cta_pair != 2 && a->cta_pair != 3 && a->M > 128;
-  const bool may_single = a->cta_pair != 1 && a->cta_pair != 3;
+  const bool may_pair = (allow_pair || a->cta_pair == 1) && a->cta_pair != 2 && a->cta_pair < 3 && a->M > 128;
+  const bool may_single = a->cta_pair != 1 && a->cta_pair < 3;
   // A-stationary TS-mode kernel (gemm_astat.cuh): plain K-major A with K <= 512, 128-wide tiles, several tiles per row block.
   // cta_pair = 3 requests it, DP_GEMM_ASTAT=0 keeps it out of the automatic choice.
   static int allow_astat = -1;
-  if (allow_astat < 0) { const char* v = getenv("DP_GEMM_ASTAT"); allow_astat = v ? atoi(v) : 1; }
+  if (allow_astat < 0) { const char* v = getenv("DP_GEMM_ASTAT"); allow_astat = v ? atoi(v) : 0; }
   const bool astat_shape = a->a_mode == 0 && a->K <= 512 && (a->K % 64) == 0 && a->N >= 256 && e.row_map == DP_ROWMAP_IDENTITY &&
                            (a->block_n == 0 || a->block_n == 128) && !e.stats && !e.scale;
-  if (astat_shape && (a->cta_pair == 3 || (a->cta_pair == 0 && allow_astat && a->M >= 2048)))
+  // cta_pair: 3 = A-stationary, 4 = A-stationary in clusters of two (multicast weight loads); DP_GEMM_ASTAT = 0 off, 1 single
+  // CTAs, 2 clusters for the automatic choice
+  if (astat_shape && (a->cta_pair == 3 || (a->cta_pair == 0 && allow_astat == 1 && a->M >= 2048)))
     var = select_gemm_variant(e, a->a_mode, 128, 2, tma_out_ok);
-  if (a->cta_pair == 3 && !var) return set_error(-3, "dp_gemm_bf16: no A-stationary variant for this shape / epilogue");
+  if (astat_shape && (a->N % 128) == 0 && (a->cta_pair == 4 || (a->cta_pair == 0 && allow_astat == 2 && a->M >= 2048)))
+    var = select_gemm_variant(e, a->a_mode, 128, 3, tma_out_ok);
+  if (a->cta_pair >= 3 && !var) return set_error(-3, "dp_gemm_bf16: no A-stationary variant for this shape / epilogue");
   if (var) {
   } else if (a->block_n != 0) {
     if (may_pair) var = select_gemm_variant(e, a->a_mode, a->block_n, 1, false);
@@ -225,7 +236,7 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   {
     const uint64_t dims[2] = {uint64_t(a->K), uint64_t(a->N)};
     const uint64_t st[1] = {uint64_t(a->ldw) * 2};
-    const uint32_t box[2] = {64, uint32_t(var->pair == 1 ? bn / 2 : bn)};   // a pair CTA stages half of the weight rows
+    const uint32_t box[2] = {64, uint32_t((var->pair == 1 || var->pair == 3) ? bn / 2 : bn)};   // a pair CTA stages half of the weight rows
     if ((rc = make_tmap(&p.tmB, a->W, 2, dims, st, box))) return rc;
   }
   if (var->opt & 128) {   // OP_TMA_OUT: 32 x 32 bf16 boxes, 64-byte rows, 64B swizzle; columns >= n_valid and rows >= M are clipped
@@ -238,6 +249,10 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   if (var->pair == 2) {
     const int tiles = p.m_tiles * p.n_tiles;
     grid = tiles < sm_count() ? tiles : sm_count();
+  } else if (var->pair == 3) {
+    const int tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
+    const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+    grid = 2 * clusters;
   } else if (var->pair) {
     const int tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
     const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
@@ -248,7 +263,13 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   }
   static int trace_on = -1;
   if (trace_on < 0) { const char* v = getenv("DP_GEMM_TRACE"); trace_on = v ? atoi(v) : 0; }
-  if (trace_on && !var->pair) {
+  if (trace_on == 2 && var->pair != 1) {
+    // asynchronous probe: CTA 0 of every launch overwrites the buffer; dp_debug_read_trace() fetches the last one
+    if (!g_trace_buf) cudaMalloc(&g_trace_buf, 4096 * sizeof(long long));
+    p.epi.trace = g_trace_buf;
+    return cuda_error(var->launch(p, grid, static_cast<cudaStream_t>(stream)), "dp_gemm_bf16 launch");
+  }
+  if (trace_on && var->pair != 1) {
     // debug only (synchronises): per-tile timeline of CTA 0, cycles relative to the first MMA start
     static long long* dbuf = nullptr;
     if (!dbuf) cudaMalloc(&dbuf, 4096 * sizeof(long long));

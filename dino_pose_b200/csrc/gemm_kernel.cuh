@@ -516,6 +516,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
   // everything above touches only shared memory / TMEM / the parameter bank: it overlaps the tail of the previous
   // launch (programmatic dependent launch); global memory is read or written only below this line
   pdl_grid_sync();
+  if (p.epi.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64) {   // SM clock probe: cycles and ns of this CTA's lifetime
+    p.epi.trace[4000] = clock64();
+    p.epi.trace[4001] = global_timer_ns();
+  }
 
   const int num_tiles = p.m_tiles * p.n_tiles;
   // tile order: n fastest (A tile shared by neighbouring CTAs through L2) unless column statistics are
@@ -657,6 +661,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) gemm_fwd_kernel(const __grid_
 #undef DP_TILE_COORDS
   tc_fence_before();
   __syncthreads();
+  if (p.epi.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 64) {
+    p.epi.trace[4002] = clock64();
+    p.epi.trace[4003] = global_timer_ns();
+  }
   if (warp == 2) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 

@@ -243,6 +243,11 @@ __device__ __forceinline__ float gelu_fast_both(float x, float& dgelu) {
   dgelu = fmaf(hx * fmaf(-th, th, 1.f), q, fmaf(0.5f, th, 0.5f));
   return fmaf(hx, th, hx);
 }
+__device__ __forceinline__ long long global_timer_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);

@@ -103,6 +103,9 @@ typedef struct {
   long long workspace_bytes;
 } dp_wgrad_args;
 int dp_wgrad_bf16(const dp_wgrad_args* a, void* stream);
+/* Tuning aid, not part of the reference surface: with DP_GEMM_TRACE=2 in the environment CTA 0 of every dp_gemm_bf16 launch
+ * records a cycle / nanosecond timeline in a device buffer; this copies its first n (<= 4096) int64 entries to the host. */
+int dp_debug_read_trace(long long* host, int n);
 
 /* ---------------------------------------------------------------- backbone row-wise kernels */
 

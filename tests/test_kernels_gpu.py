@@ -84,36 +84,38 @@ def test_gemm_cta_pair(M, N, K, bn):
         assert rel(out2.float(), F.gelu(ref)) < 1e-2
 
 
+@pytest.mark.parametrize("kind", [3, 4])
 @pytest.mark.parametrize("M,N,K", [(16448, 1152, 384), (16448, 1536, 384), (300, 256, 64), (2049, 384, 128),
                                    (1000, 1152, 512), (4100, 640, 384)])
-def test_gemm_a_stationary(M, N, K):
+def test_gemm_a_stationary(M, N, K, kind):
     """A-stationary kernel (gemm_astat.cuh): the 128 x K row block of A is copied into tensor memory (tcgen05.cp) once
-    per row block and the MMAs run in the TS form; contiguous tile ranges per CTA, ragged last row block / column tile."""
+    per row block and the MMAs run in the TS form; contiguous tile ranges per CTA, ragged last row block / column tile.
+    kind 4: clusters of two CTAs, weight k-blocks fetched half / half and multicast (odd row-block counts: phantom half)."""
     A = rnd(M, K, dtype=BF)
     W = rnd(N, K, scale=0.05, seed=1, dtype=BF)
     bias = rnd(N, seed=2)
     ref = A.float() @ W.float().t() + bias
     out = torch.zeros(M, N, device=dev(), dtype=BF)
-    run(lambda b: b.gemm(A, W, out, M=M, N=N, K=K, bias=bias, cta_pair=3))              # TMA-store epilogue
+    run(lambda b: b.gemm(A, W, out, M=M, N=N, K=K, bias=bias, cta_pair=kind))              # TMA-store epilogue
     assert rel(out.float(), ref) < 1e-2
     out2 = torch.zeros(M, N, device=dev(), dtype=BF)
     aux = torch.zeros(M, N, device=dev(), dtype=BF)
-    run(lambda b: b.gemm(A, W, out2, M=M, N=N, K=K, bias=bias, act="gelu", aux_out=aux, ld_aux=N, cta_pair=3))
+    run(lambda b: b.gemm(A, W, out2, M=M, N=N, K=K, bias=bias, act="gelu", aux_out=aux, ld_aux=N, cta_pair=kind))
     xr = ref.clone().requires_grad_(True)
     F.gelu(xr).sum().backward()
     assert rel(aux.float(), xr.grad) < 1e-2
     assert rel(out2.float(), F.gelu(ref)) < 1e-2
     out3 = torch.zeros(M, N, device=dev(), dtype=BF)
-    run(lambda b: b.gemm(A, W, out3, M=M, N=N, K=K, bias=bias, act="gelu", cta_pair=3))  # GELU + TMA store
+    run(lambda b: b.gemm(A, W, out3, M=M, N=N, K=K, bias=bias, act="gelu", cta_pair=kind))  # GELU + TMA store
     assert rel(out3.float(), F.gelu(ref)) < 1e-2
     mult = rnd(M, N, seed=9, dtype=BF)
     out4 = torch.zeros(M, N, device=dev(), dtype=BF)
-    run(lambda b: b.gemm(A, W, out4, M=M, N=N, K=K, aux_in=mult, ld_aux=N, cta_pair=3))
+    run(lambda b: b.gemm(A, W, out4, M=M, N=N, K=K, aux_in=mult, ld_aux=N, cta_pair=kind))
     assert rel(out4.float(), (A.float() @ W.float().t()) * mult.float()) < 1e-2
     ls = rnd(N, seed=4)
     x = rnd(M, N, seed=5)
     x0 = x.clone()
-    run(lambda b: b.gemm(A, W, x, M=M, N=N, K=K, bias=bias, ls=ls, residual=x, out_dtype="f32", cta_pair=3))
+    run(lambda b: b.gemm(A, W, x, M=M, N=N, K=K, bias=bias, ls=ls, residual=x, out_dtype="f32", cta_pair=kind))
     assert rel(x, x0 + ref * ls) < 2e-3
 
 

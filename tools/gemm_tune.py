@@ -70,6 +70,13 @@ def bench(name, bn, reps=20, nbuf=6, pair=2):
     torch.cuda.synchronize()
     us = e0.elapsed_time(e1) / reps * 1e3
     tf = 2.0 * m * n * k / us / 1e6
+    if os.environ.get("DP_GEMM_TRACE") == "2":
+        # SM clock during the replay: cycles / ns of CTA 0 of the last launch; cycles from its first MMA to its end
+        import ctypes
+        buf = (ctypes.c_longlong * 4096)()
+        be.lib.dp_debug_read_trace(buf, 4096)
+        cyc, ns = buf[4002] - buf[4000], buf[4003] - buf[4001]
+        print(f"      probe: CTA0 {cyc} cycles in {ns} ns = {cyc / max(ns, 1):.3f} GHz", flush=True)
     return us, tf
 
 

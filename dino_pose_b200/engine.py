@@ -363,13 +363,59 @@ class PoseEngine:
         return {}
 
     # ------------------------------------------------------------------ plans
-    def get_plan(self, B, H, W, training):
-        key = (B, H, W, bool(training))
+    def get_plan(self, B, H, W, training, scope="model"):
+        key = (B, H, W, bool(training)) if scope == "model" else (B, H, W, bool(training), scope)
         if key not in self.plans:
-            self.plans[key] = self.build_plan(B, H, W, bool(training))
+            if scope in ("model", "backbone"):
+                self.plans[key] = self.build_plan(B, H, W, bool(training), scope)
+            else:
+                self.plans[key] = self.build_scope_plan(scope, B, H // PATCH, bool(training))
         return self.plans[key]
 
-    def build_plan(self, B, H, W, training):
+    # layers of the head table that belong to each stand-alone module scope (reference model/pose_heads.py)
+    HOURGLASS_KEYS = ("skip", "dw", "pw", "down1", "down2", "bt1", "bt2", "up1", "up2")
+
+    def scope_layers(self, scope, g):
+        Ls = self.build_head_layers(g)
+        if scope == "hourglass":
+            return {k: Ls[k] for k in Ls if k in self.HOURGLASS_KEYS}
+        if scope == "z_head":
+            return {}
+        return Ls
+
+    def build_scope_plan(self, scope, B, g, training):
+        """Plan for a stand-alone sub-module of the heads (reference model/pose_heads.py:268-285 HourglassModule,
+        :345-361 SpatialAwareHeatmapHead, :161-162 ZCoordinateHead, :395-400 SpatialAwarePoseHeads): the same recorded
+        launches as inside the full model, starting from the module's own input buffer."""
+        be = self.be
+        if self.seed is None:
+            self.seed = torch.zeros(1, dtype=torch.int64, device=self.device)
+        N = g * g
+        plan = {"B": B, "H": g * PATCH, "W": g * PATCH, "training": training, "g": g, "N": N, "T": N + 1, "M": B * (N + 1),
+                "scope": scope, "lw": {}, "saved": {}}
+        t = plan["t"] = {}
+        if scope in ("pose_heads", "heatmap_head"):
+            t["feat"] = self.new((B * N, self.D), self.adt)        # NHWC rows, what the final LayerNorm writes in the model
+        elif scope == "hourglass":
+            t["hg_in"] = self.new((B * N, 512), self.adt)
+        elif scope == "z_head":
+            t["zin"] = self.new((B, self.D), F32)
+        else:
+            raise ValueError(scope)
+        prog_f = be.begin()
+        plan["layers"] = self.scope_layers(scope, g)
+        be.fork()
+        if plan["layers"]:
+            self.record_pack_heads(plan)
+        be.side(False)
+        self.record_heads_forward(plan)
+        plan["fwd"] = prog_f
+        if training:
+            plan["bwd"] = be.begin()
+            self.record_backward(plan)
+        return plan
+
+    def build_plan(self, B, H, W, training, scope="model"):
         if H % PATCH or W % PATCH or H != W:
             raise ValueError(f"pixel_values must be square with sides a multiple of {PATCH} "
                              f"(reference model/dinov2_pose.py:151 assumes H = W = sqrt(N)); got {H}x{W}")
@@ -383,7 +429,7 @@ class PoseEngine:
         N = g * g
         T = N + 1
         M = B * T
-        plan = {"B": B, "H": H, "W": W, "training": training, "g": g, "N": N, "T": T, "M": M}
+        plan = {"B": B, "H": H, "W": W, "training": training, "g": g, "N": N, "T": T, "M": M, "scope": scope}
         fz = self.frozen
         t = plan["t"] = {}
         t["px"] = self.new((B, 3, H, W), F32)
@@ -412,9 +458,10 @@ class PoseEngine:
         lw = plan["lw"]
         # the bf16 re-packing of the trainable head weights only has to be done before the first head convolution: it
         # runs on the second stream underneath the backbone (gather-bound, ~50 us, a fraction of the SMs)
-        plan["layers"] = self.build_head_layers(g)
+        plan["layers"] = self.build_head_layers(g) if scope == "model" else {}
         be.fork()
-        self.record_pack_heads(plan)
+        if scope == "model":
+            self.record_pack_heads(plan)
         be.side(False)
         be.patch_im2col(t["px"], t["acol"], B=B, H=H, W=W, Kp=PATCH_KP)
         be.fill_cls(t["x"], pos[0], B=B, T=T, D=D)
@@ -531,6 +578,14 @@ class PoseEngine:
             be.sync("main_wait")
         x_fin = t["x_last"] if training else t["x"]
         plan["x_final"] = x_fin
+        if scope == "backbone":
+            # stand-alone Dinov2Model.forward (HF:473-478): last_hidden_state = LayerNorm(all tokens), fp32
+            be.join()
+            t["lhs"] = self.new((M, D), F32)
+            be.layernorm_fwd(x_fin, self.p("backbone.layernorm.weight"), self.p("backbone.layernorm.bias"), None, t["lhs"],
+                             rows=M, D=D, eps=LN_EPS)
+            plan["fwd"] = prog_f
+            return plan
         be.layernorm_fwd(x_fin, self.p("backbone.layernorm.weight"), self.p("backbone.layernorm.bias"), t["feat"], None,
                          rows=M, D=D, T=T, drop_cls=True, eps=LN_EPS)
         self.record_heads_forward(plan)
@@ -666,6 +721,9 @@ class PoseEngine:
         B, g, training = plan["B"], plan["g"], plan["training"]
         t = plan["t"]
         Ls = plan["layers"]
+        scope = plan.get("scope", "model")
+        has_z = scope in ("model", "pose_heads", "z_head")
+        has_hm = scope in ("model", "pose_heads", "heatmap_head")
         be.join()                # packed head weights (second stream, forked at the start of the program)
         for L in Ls.values():
             if L.bn is not None:
@@ -679,29 +737,34 @@ class PoseEngine:
         # The z head (5 small launches on a [B, D] matrix) only needs the final LayerNorm output: it runs on the second
         # stream underneath the heat-map head and is joined at the end of the program.
         be.fork()
-        # z head: mean over patch tokens -> MLP (pose_heads.py:397-398, :148-159)
-        zh = self.cfg["z_hidden"]
-        dims = [self.D] + list(zh) + [K]
-        t["zin"] = self.new((B, self.D), F32)
-        be.mean_tokens(t["feat"], t["zin"], B=B, N=plan["N"], D=self.D)
-        zp = "pose_heads.z_head.mlp."
-        cur = t["zin"]
-        p_drop = float(self.cfg.get("z_dropout", 0.0)) if training else 0.0
-        t["zact"] = [cur]
-        for j in range(len(dims) - 1):
-            lastl = j == len(dims) - 2
-            out = self.new((B, dims[j + 1]), F32)
-            be.sgemm_small(cur, dims[j], 1, self.p(zp + f"{3 * j}.weight"), 1, dims[j], out, dims[j + 1], M=B,
-                           N=dims[j + 1], K=dims[j], bias=self.p(zp + f"{3 * j}.bias"), relu=not lastl,
-                           p_drop=0.0 if lastl else p_drop, seed=self.seed if (p_drop > 0 and not lastl) else None)
-            cur = out
-            t["zact"].append(cur)
-        t["z"] = cur
-        plan["zdims"] = dims
+        if has_z:
+            # z head: mean over patch tokens -> MLP (pose_heads.py:397-398, :148-159)
+            zh = self.cfg["z_hidden"]
+            dims = [self.D] + list(zh) + [K]
+            if scope != "z_head":    # stand-alone ZCoordinateHead: the [B, D] feature vector IS the input
+                t["zin"] = self.new((B, self.D), F32)
+                be.mean_tokens(t["feat"], t["zin"], B=B, N=plan["N"], D=self.D)
+            zp = "pose_heads.z_head.mlp."
+            cur = t["zin"]
+            p_drop = float(self.cfg.get("z_dropout", 0.0)) if training else 0.0
+            t["zact"] = [cur]
+            for j in range(len(dims) - 1):
+                lastl = j == len(dims) - 2
+                out = self.new((B, dims[j + 1]), F32)
+                be.sgemm_small(cur, dims[j], 1, self.p(zp + f"{3 * j}.weight"), 1, dims[j], out, dims[j + 1], M=B,
+                               N=dims[j + 1], K=dims[j], bias=self.p(zp + f"{3 * j}.bias"), relu=not lastl,
+                               p_drop=0.0 if lastl else p_drop, seed=self.seed if (p_drop > 0 and not lastl) else None)
+                cur = out
+                t["zact"].append(cur)
+            t["z"] = cur
+            plan["zdims"] = dims
         be.side(False)
-        feat4 = t["feat"].view(B, g, g, self.D)
         a = plan["a"] = {}    # activations (bf16 [P, C])
         r = plan["raw"] = {}  # pre-BN conv outputs (training only)
+        if scope == "z_head":
+            be.join()
+            return
+        feat4 = t["feat"].view(B, g, g, self.D) if has_hm else None
 
         def unit(key, x, **kw):
             L = Ls[key]
@@ -712,7 +775,10 @@ class PoseEngine:
                 a[key] = self._conv_forward(L, x, B, False)
             return a[key]
 
-        a1 = unit("fr0", feat4)
+        if has_hm:
+            a1 = unit("fr0", feat4)
+        else:                       # stand-alone HourglassModule: its input takes the place of feature_refine's first unit
+            a1 = a["fr0"] = t["hg_in"]
         a1_4 = a1.view(B, g, g, 512)
         # The hourglass has three independent branches (pose_heads.py:268-285).  The down/up branch is a chain of small
         # launches on 8x8 / 4x4 maps (a handful of CTAs each, latency bound): it runs on side stream 2 underneath the
@@ -763,6 +829,9 @@ class PoseEngine:
             hgout = a["hg"] = self.new(tuple(up2.shape), self.adt)
             be.bn_apply(up2, L2.t["one"], L2.t["zero"], a["skip"], a["pw"], hgout, P=up2.shape[0], C=L2.cout, relu=False, mode=0)
         plan["hgout"] = hgout
+        if not has_hm:
+            be.join()
+            return
         unit("fr4", hgout.view(B, g, g, 512))
         unit("ups0", a["fr4"])
         s47, s48 = Ls["ups0"].oh, Ls["ups1"].oh
@@ -801,6 +870,9 @@ class PoseEngine:
         B, g, N, T, M = plan["B"], plan["g"], plan["N"], plan["T"], plan["M"]
         D, K = self.D, self.K
         t, a, r, Ls = plan["t"], plan["a"], plan["raw"], plan["layers"]
+        scope = plan.get("scope", "model")
+        has_z = scope in ("model", "pose_heads", "z_head")
+        has_hm = scope in ("model", "pose_heads", "heatmap_head")
         lay = self.layout()
         flat = plan["gflat"] = self.new((lay["total"],), F32)
         G = plan["grads"] = {}
@@ -833,22 +905,22 @@ class PoseEngine:
             # gradients) has caught up
             be.sync("main_wait")
             be.mark(("grads_final", lay["group_end"][key]))
-        t["dhm"] = self.new(tuple(t["hm"].shape), F32)
-        t["dz"] = self.new((B, K), F32)
+        if has_hm:
+            t["dhm"] = self.new(tuple(t["hm"].shape), F32)
+        if has_z:
+            t["dz"] = self.new((B, K), F32)
         # split-K workspace shared by all weight-gradient launches (they run one after the other): partial tiles are
         # stored without atomics and reduced by a second kernel (deterministic, no contention on the gradient buffer)
         ws = t["wgrad_ws"] = self.new((16 << 20,), F32)
         be.host("zero_grads", flat.zero_)
-        s47, s48 = Ls["ups0"].oh, Ls["ups1"].oh
-        P48 = B * s48 * s48
         # the z-head backward (12 small launches, M = batch) depends only on dz: second stream, under the heat-map head
         be.fork()
-        dims = plan["zdims"]
+        dims = plan.get("zdims", [0])
         zp = "pose_heads.z_head.mlp."
         p_drop = float(self.cfg.get("z_dropout", 0.0))
-        dcur = t["dz"]
+        dcur = t.get("dz")
         nl = len(dims) - 1
-        for j in reversed(range(nl)):
+        for j in reversed(range(nl if has_z else 0)):
             xin, yout = t["zact"][j], t["zact"][j + 1]
             if j < nl - 1:
                 # through dropout + relu of layer j: mask by the saved (post-dropout) activation
@@ -863,6 +935,11 @@ class PoseEngine:
                            K=dims[j + 1])
             dcur = dx
         be.side(False)
+        if scope == "z_head":
+            be.join()
+            plan["d_in"] = dcur            # gradient w.r.t. the [B, D] feature vector
+            be.mark(("grads_final", lay["total"]))
+            return
 
         def bn_bwd(key, dact, add1=None, mode=0, dres=None, shuffle=False):
             L = Ls[key]
@@ -948,25 +1025,36 @@ class PoseEngine:
             return dx
 
         # ---- heat-map head
-        up = s48 // self.hm_size
-        L = Ls["pred3"]
-        d = self.new((P48, 64), self.adt)
-        if plan.get("pred_simt") and up == 1:
-            # one launch: input gradient, weight gradient and bias gradient straight from the fp32 NCHW heat-map gradient
-            be.pred1x1_bwd(t["dhm"], a["pred0"], self.p(L.name + ".weight"), d, G[L.name + ".weight"], G[L.name + ".bias"],
-                           P=P48, HW=s48 * s48, C=64, K=K)
+        def tail_backward():
+            """prediction.3 .. feature_refine.4: heat-map gradient -> gradient w.r.t. the hourglass output"""
+            s47, s48 = Ls["ups0"].oh, Ls["ups1"].oh
+            P48 = B * s48 * s48
+            up = s48 // self.hm_size
+            L = Ls["pred3"]
+            d = self.new((P48, 64), self.adt)
+            if plan.get("pred_simt") and up == 1:
+                # one launch: input gradient, weight gradient and bias gradient straight from the fp32 NCHW heat-map gradient
+                be.pred1x1_bwd(t["dhm"], a["pred0"], self.p(L.name + ".weight"), d, G[L.name + ".weight"],
+                               G[L.name + ".bias"], P=P48, HW=s48 * s48, C=64, K=K)
+            else:
+                t["ghm"] = self.new((P48, HM_PAD), self.adt)
+                be.hm_grad_to_nhwc(t["dhm"], t["ghm"], NB=B, K=K, Kp=HM_PAD, OH=s48, OW=s48, up=up)
+                be.colsum(t["ghm"], G[L.name + ".bias"], P=P48, C=K, ld=HM_PAD)
+                wg(t["ghm"], a["pred0"], G[L.name + ".weight"], Mc=K, Nc=64, so_m=64, so_n=1, P=P48, block_n=64,
+                   name="pred3.wgrad", workspace=ws)
+                be.gemm(t["ghm"], L.t["wd"], d, M=P48, N=64, K=HM_PAD, name="pred3.dgrad")
+            d = conv_bwd("pred0", bn_bwd("pred0", d), a["ups1"])
+            d = conv_bwd("ups1", bn_bwd("ups1", d), a["ups0"])
+            d = conv_bwd("ups0", bn_bwd("ups0", d), a["fr4"])
+            d = conv_bwd("fr4", bn_bwd("fr4", d), plan["hgout"])
+            done("fr4")
+            return d
+
+        if has_hm:
+            d_hg = tail_backward()
         else:
-            t["ghm"] = self.new((P48, HM_PAD), self.adt)
-            be.hm_grad_to_nhwc(t["dhm"], t["ghm"], NB=B, K=K, Kp=HM_PAD, OH=s48, OW=s48, up=up)
-            be.colsum(t["ghm"], G[L.name + ".bias"], P=P48, C=K, ld=HM_PAD)
-            wg(t["ghm"], a["pred0"], G[L.name + ".weight"], Mc=K, Nc=64, so_m=64, so_n=1, P=P48, block_n=64,
-               name="pred3.wgrad", workspace=ws)
-            be.gemm(t["ghm"], L.t["wd"], d, M=P48, N=64, K=HM_PAD, name="pred3.dgrad")
-        d = conv_bwd("pred0", bn_bwd("pred0", d), a["ups1"])
-        d = conv_bwd("ups1", bn_bwd("ups1", d), a["ups0"])
-        d = conv_bwd("ups0", bn_bwd("ups0", d), a["fr4"])
-        d_hg = conv_bwd("fr4", bn_bwd("fr4", d), plan["hgout"])
-        done("fr4")
+            # stand-alone HourglassModule: the seed is the gradient w.r.t. its output, [P, 512] NHWC
+            d_hg = t["d_hg"] = self.new((B * g * g, 512), self.adt)
         # ---- hourglass (three consumers of d_hg: up2, skip, depthwise branch).  As in the forward, the down/up branch (a
         # latency-bound chain of ~25 small launches) runs on side stream 2, its weight gradients in line with their own
         # split-K workspace; the depthwise and skip branches proceed on the main stream and need its result (d_a1) last.
@@ -997,10 +1085,20 @@ class PoseEngine:
         be.dwconv3x3(ddw, self.p(Ldw.name + ".weight"), None, d_a1, d_a1b, NB=B, H=g, W=g, C=512, flip=True)
         # skip branch, accumulating into the running gradient of a1
         d_a1c = conv_bwd("skip", dskip, a["fr0"], dx_residual=d_a1b)
+        if not has_hm:
+            be.join()
+            plan["d_in"] = d_a1c           # gradient w.r.t. the hourglass input, [P, 512] NHWC
+            be.mark(("grads_final", lay["total"]))
+            return
         dfeat = conv_bwd("fr0", bn_bwd("fr0", d_a1c), t["feat"].view(B, g, g, D))
         done("fr0")
         be.join()                # z-head chain (second stream): its input gradient dcur is needed now
-        be.mean_tokens_bwd(dfeat, dcur, B=B, N=N, D=D)
+        if has_z:
+            be.mean_tokens_bwd(dfeat, dcur, B=B, N=N, D=D)
+        plan["d_in"] = dfeat               # gradient w.r.t. the NHWC feature map (stand-alone head modules)
+        if scope != "model":
+            be.mark(("grads_final", lay["total"]))
+            return
         if self.train_layers:
             self.record_backward_layers(plan, dfeat, G, flat, ws, done)
             return

@@ -92,10 +92,18 @@ class SelfOutput(_Holder):
 
 
 class Attention(_Holder):
+    """HF ``Dinov2Attention`` (modeling_dinov2.py:237-252): the block ``LoRAAttention`` wraps (reference model/lora.py:53-65)."""
+
     def __init__(self, cfg):
         super().__init__()
         self.attention = SelfAttention(cfg)
         self.output = SelfOutput(cfg)
+
+    def forward(self, hidden_states, head_mask=None, output_attentions=False):
+        if head_mask is not None or output_attentions:
+            raise NotImplementedError("head_mask / output_attentions are not supported by the fused attention kernel")
+        from ..functional import run_attention
+        return run_attention(self, hidden_states)
 
 
 class LayerScale(_Holder):

@@ -2,7 +2,7 @@
 (so ``state_dict`` keys are identical) whose ``forward`` runs on the sm_100a kernels.
 
 Layer tables are written in a tiny spec language instead of literal ``nn.Sequential`` code:
-  ``c<k>[s<stride>][p<pad>][g]:<out>``  Conv2d (g = depthwise)     ``t<k>s<stride>[p<pad>]:<out>``  ConvTranspose2d
+  ``c<k>[s<stride>][p<pad>][g]:<out>``  Conv2d (g = depthwise)     ``t<k>s<stride>[p<pad>][o<outpad>]:<out>``  ConvTranspose2d
   ``bn``  BatchNorm2d of the running width                         ``relu``  ReLU (no parameters)
   ``fc:<out>``  Linear                                              ``drop:<p>``  Dropout
 """
@@ -14,7 +14,7 @@ from typing import Optional, Tuple
 import torch
 import torch.nn as nn
 
-_TOKEN = re.compile(r"^(?P<op>[ct])(?P<k>\d+)(s(?P<s>\d+))?(p(?P<p>\d+))?(?P<g>g)?:(?P<o>\d+)$")
+_TOKEN = re.compile(r"^(?P<op>[ct])(?P<k>\d+)(s(?P<s>\d+))?(p(?P<p>\d+))?(o(?P<op_>\d+))?(?P<g>g)?:(?P<o>\d+)$")
 
 
 def _build(spec: str, width: int):
@@ -39,7 +39,7 @@ def _build(spec: str, width: int):
             if m["op"] == "c":
                 mods.append(nn.Conv2d(width, out, k, s, p, groups=width if m["g"] else 1))
             else:
-                mods.append(nn.ConvTranspose2d(width, out, k, s, p))
+                mods.append(nn.ConvTranspose2d(width, out, k, s, p, output_padding=int(m["op_"] or 0)))
             width = out
     return nn.Sequential(*mods), width
 
@@ -127,20 +127,61 @@ class SpatialAwarePoseHeads(nn.Module):
 
 
 class HeatmapHead(nn.Module):
-    """reference model/pose_heads.py:6-125 -- never instantiated by the reference (dead code);
-    the class is kept so imports keep working."""
+    """reference model/pose_heads.py:6-125: MLP projection of a feature VECTOR to a ``spatial_size``^2 map, then stride-2
+    transposed-conv stages up to ``heatmap_size``.  Never instantiated by the reference (dead code) and not on
+    the hot path: kept as an ordinary torch module (same parameter tree and ``forward``) so imports and old checkpoints
+    keep working; it runs on whatever device torch puts it on and uses none of the sm_100a kernels."""
 
     def __init__(self, feat_dim: int, num_keypoints: int, heatmap_size: int = 48, intermediate_features: int = 512,
                  spatial_size: int = 6):
         super().__init__()
-        raise NotImplementedError("HeatmapHead (MLP heat-map head) is dead code in the reference; "
-                                  "both DINOv2 pose models use SpatialAwarePoseHeads")
+        self.feat_dim, self.num_keypoints, self.heatmap_size = feat_dim, num_keypoints, heatmap_size
+        self.spatial_size, self.intermediate_features = spatial_size, intermediate_features
+        self.feature_projection, _ = _build(
+            f"fc:2048 relu drop:0.1 fc:1024 relu drop:0.1 fc:{spatial_size * spatial_size * intermediate_features} relu", feat_dim)
+        for m in self.feature_projection:
+            if isinstance(m, nn.ReLU):
+                m.inplace = False
+        self.num_stages, size = 0, spatial_size
+        while size < heatmap_size:
+            size, self.num_stages = size * 2, self.num_stages + 1
+        stages, size, width, nxt = [], spatial_size * 2, 256, 128
+        stages.append(_build("t3s2p1o1:256 bn relu", intermediate_features)[0])
+        while size < heatmap_size:                      # reference :76-86
+            stages.append(_build(f"t3s2p1o1:{nxt} bn relu", width)[0])
+            size, width, nxt = size * 2, nxt, max(64, nxt // 2)
+        if size > heatmap_size:                         # overshoot: conv + adaptive pooling to the exact size (:89-96)
+            stages.append(nn.Sequential(*_build("c3p1:64 bn relu", width)[0], nn.AdaptiveAvgPool2d(heatmap_size)))
+        elif width != 64:                               # :97-103
+            stages.append(_build("c3p1:64 bn relu", width)[0])
+        for st in stages:
+            for m in st:
+                if isinstance(m, nn.ReLU):
+                    m.inplace = False
+        self.upsampling_layers = nn.ModuleList(stages)
+        self.prediction_layer = nn.Conv2d(64, num_keypoints, kernel_size=1)
+
+    def forward(self, features: torch.Tensor) -> torch.Tensor:
+        x = self.feature_projection(features)
+        x = x.view(features.size(0), self.intermediate_features, self.spatial_size, self.spatial_size)
+        for layer in self.upsampling_layers:
+            x = layer(x)
+        return self.prediction_layer(x)
 
 
 class PoseHeads(nn.Module):
-    """reference model/pose_heads.py:165-208 -- dead code in the reference, see ``HeatmapHead``."""
+    """reference model/pose_heads.py:165-208 (``HeatmapHead`` + ``ZCoordinateHead`` on a feature vector) -- dead code in
+    the reference, see ``HeatmapHead``; the z head is the kernel-backed ``ZCoordinateHead``."""
 
     def __init__(self, feat_dim: int, num_keypoints: int, heatmap_size: int = 48, heatmap_config: Optional[dict] = None,
                  z_coord_config: Optional[dict] = None):
         super().__init__()
-        raise NotImplementedError("PoseHeads is dead code in the reference; use SpatialAwarePoseHeads")
+        self.heatmap_head = HeatmapHead(feat_dim=feat_dim, num_keypoints=num_keypoints, heatmap_size=heatmap_size,
+                                        **(heatmap_config or {}))
+        self.z_head = ZCoordinateHead(feat_dim=feat_dim, num_keypoints=num_keypoints, **(z_coord_config or {}))
+
+    def forward(self, features: torch.Tensor):
+        return self.heatmap_head(features), self.z_head(features)
+
+    def count_parameters(self, trainable_only: bool = True) -> int:
+        return sum(p.numel() for p in self.parameters() if p.requires_grad or not trainable_only)

@@ -9,7 +9,7 @@
 // Output  dqkv bf16 [B*T, 3*D] (dq | dk | dv in the layout of qkv, i.e. the operand of the QKV weight / input gradients)
 // Scratch stats fp32 [2][B*heads*T]: log2-domain log-sum-exp of every score row, and delta
 //
-// Two kernels, both with the tiling of the forward flash kernel (attention.cu: 64 rows per CTA, 4 warps x 16 rows,
+// Two kernels, both with the tiling of the round-1 mma.sync forward kernel (64 rows per CTA, 4 warps x 16 rows,
 // 64-row tiles of the other side streamed through a cp.async double buffer, mma.sync m16n8k16 bf16, fp32 accumulation,
 // scores never leave the SM):
 //   1. dq kernel, one CTA per 64 queries: pass 1 recomputes the row statistics (the forward kernels do not store

@@ -418,8 +418,10 @@ def test_lora_fwd_bwd():
     assert rel(v[kept], full[kept] / 0.9) < 1e-2
 
 
-@pytest.mark.parametrize("B,T,heads", [(2, 257, 6), (1, 1025, 6), (3, 65, 2), (2, 257, 12)])
+@pytest.mark.parametrize("B,T,heads", [(2, 257, 6), (1, 1025, 6), (3, 65, 2), (2, 257, 12), (2, 1025, 2), (3, 300, 2),
+                                       (2, 401, 3), (1, 528, 1), (1, 2304, 1), (2, 273, 1)])
 def test_attention(B, T, heads):
+    """T <= 272: resident-K/V tcgen05 kernels; longer: the flash-style tcgen05 kernel (ragged last key / query tiles)."""
     D = heads * 64
     qkv = rnd(B * T, 3 * D, dtype=BF)
     ctx = torch.zeros(B * T, D, device=dev(), dtype=BF)

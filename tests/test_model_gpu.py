@@ -101,19 +101,25 @@ def test_train_step_vs_reference_golden(golden_dir, case):
         sub = subsample(p.grad)
         rel = np.linalg.norm(sub - ref) / (np.linalg.norm(ref) + 1e-30)
         cos = float(np.dot(sub, ref) / (np.linalg.norm(sub) * np.linalg.norm(ref) + 1e-30))
-        print(f"  {pname[-60:]:60s} relL2 {rel:.3e} cos {cos:.4f}")
+        ratio = float(np.linalg.norm(sub) / (np.linalg.norm(ref) + 1e-30))
+        print(f"  {pname[-60:]:60s} relL2 {rel:.3e} cos {cos:.4f} |g|/|ref| {ratio:.4f}")
         allg.append(sub); allr.append(ref)
         # per-tensor bf16-vs-fp32 criterion (tests/test_engine_emulated.py explains why train-mode BN at batch 2-4
         # makes single small tensors move by tens of percent); the tight kernel-level check of the backward is
         # test_train_step_cuda_vs_emulated_op_graph below
-        if rel > 0.5 or cos < 0.9:
-            bad[pname] = (float(rel), cos)
+        # Measured worst case over all golden cases: relL2 0.33, cos 0.946 (batch 2-4).  The norm ratio is the scale check:
+        # bf16 noise is nearly orthogonal to the gradient, a wrong factor is not (a 1.3x error fails; the tight version of
+        # this check, at batch 64 where the BatchNorm statistics are stable, is tests/test_parity_bench_shape_gpu.py).
+        if rel > 0.4 or cos < 0.93 or not (0.8 < ratio < 1.2):
+            bad[pname] = (float(rel), cos, ratio)
     assert n == int(g["num_grad_tensors"])
     assert not bad, bad
     fa, fr = np.concatenate(allg), np.concatenate(allr)
     gcos = float(np.dot(fa, fr) / (np.linalg.norm(fa) * np.linalg.norm(fr)))
-    print(f"  all trainable gradients: cosine {gcos:.4f}")
+    gratio = float(np.linalg.norm(fa) / np.linalg.norm(fr))
+    print(f"  all trainable gradients: cosine {gcos:.4f} norm ratio {gratio:.4f}")
     assert gcos > 0.97, gcos
+    assert 0.95 < gratio < 1.05, gratio
     bufs = dict(m.named_buffers())
     for k in g.files:
         if k.startswith("buf."):

@@ -28,4 +28,4 @@ g.replay(); torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
 us = e0.elapsed_time(e1) / reps * 1e3
-print(f"legacy={os.environ.get('DP_ATTN_LEGACY','0')} B={B} T={T} H={H}: {us:7.1f} us  {4.0*B*H*T*T*64/us/1e6:6.1f} TFLOP/s  max-rel err {err:.2e}")
+print(f"flash={os.environ.get('DP_ATTN_FLASH','0')} B={B} T={T} H={H}: {us:7.1f} us  {4.0*B*H*T*T*64/us/1e6:6.1f} TFLOP/s  max-rel err {err:.2e}")

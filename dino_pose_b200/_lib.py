@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdinopose_sm100a.so")
 
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 c_ll = C.c_longlong
 c_vp = C.c_void_p
@@ -44,6 +44,7 @@ class GemmArgs(C.Structure):
         ("ld_aux", c_ll),
         ("row_map", C.c_int), ("n_valid", C.c_int), ("map_a", C.c_int), ("map_b", C.c_int),
         ("stats", c_vp), ("stats_c", C.c_int), ("cta_pair", C.c_int),
+        ("ln_gamma", c_vp), ("ln_beta", c_vp), ("ln_out", c_vp), ("ld_ln", c_ll), ("ln_eps", C.c_float),
     ]
 
 

@@ -197,9 +197,10 @@ class CudaBackend:
     def gemm(self, A, W, out, *, M, N, K, lda=None, ldw=None, ldo=None, out_dtype="bf16", bias=None, scale=None,
              ls=None, residual=None, ldr=None, aux_out=None, aux_in=None, ld_aux=0, act="none", row_map="identity",
              n_valid=0, map_a=0, map_b=0, conv=None, OH=0, OW=0, NB=0, block_n=0, stats=None, stats_c=0, cta_pair=0,
-             name="gemm"):
+             ln=None, name="gemm"):
         """out = epilogue(A[M,K] @ W[N,K]^T).  ``conv`` = dict(KH, KW, pad, OH, OW) makes A an NHWC
-        [NB,IH,IW,C] activation (any strides with unit channel stride) read as an implicit conv."""
+        [NB,IH,IW,C] activation (any strides with unit channel stride) read as an implicit conv.
+        ``ln`` = dict(gamma, beta, out, eps): LayerNorm of the output rows fused into the epilogue (row-owning kernel)."""
         _chk(W, torch.bfloat16, name + ".W", contiguous=False)
         a = GemmArgs()
         a.A, a.W, a.out = _p(A), _p(W), _p(out)
@@ -240,8 +241,16 @@ class CudaBackend:
         _chk(stats, torch.float64, name + ".stats")
         a.stats, a.stats_c = _p(stats), stats_c
         a.cta_pair = cta_pair
+        lnk = ()
+        if ln is not None:
+            _chk(ln["gamma"], torch.float32, name + ".ln_gamma")
+            _chk(ln["beta"], torch.float32, name + ".ln_beta")
+            _chk(ln["out"], torch.bfloat16, name + ".ln_out", contiguous=False)
+            a.ln_gamma, a.ln_beta, a.ln_out = _p(ln["gamma"]), _p(ln["beta"]), _p(ln["out"])
+            a.ld_ln, a.ln_eps = ln["out"].stride(0), float(ln.get("eps", 1e-6))
+            lnk = (ln["gamma"], ln["beta"], ln["out"])
         self.prog.add(name, self.lib.dp_gemm_bf16, C.byref(a), kernel="gemm_kmajor_tcgen05", flops=2.0 * M * N * K,
-                      keep=(a, A, W, out, bias, scale, ls, residual, aux_out, aux_in, stats))
+                      keep=(a, A, W, out, bias, scale, ls, residual, aux_out, aux_in, stats) + lnk)
 
     def wgrad(self, A, B, out, *, Mc, Nc, so_m, so_n, so_t=0, so_mo=0, so_no=0, m_inner=0, n_inner=0, conv=None,
               P=0, lda=None, ldb=None, block_n=0, splits=0, workspace=None, name="wgrad"):

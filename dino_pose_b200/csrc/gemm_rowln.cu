@@ -1,0 +1,254 @@
+// Row-owning tcgen05 GEMM with the NEXT LayerNorm fused into its epilogue: the attention / MLP output projections of the
+// frozen encoder layers (HF modeling_dinov2.py:250 + 373-379, 327 + 382-384 followed by :371 / :379 of the next sub-block).
+//
+//   v[M, N]  = residual + ls * (A[M,K] * W[N,K]^T + bias)        fp32 residual stream, written to `out` (may alias residual)
+//   ln_out   = LayerNorm(v; gamma, beta, eps)                    bf16, the A operand of the following QKV / fc1 GEMM
+//
+// One CTA owns 128 COMPLETE rows (N = 128 * NACC <= 512 fp32 accumulator columns in tensor memory: N = 384 for ViT-S), so
+// the row statistics never leave the SM and the separate LayerNorm launch (25 per forward: 38 MB of traffic and a launch
+// gap each) disappears.  Main loop: TMA ring of {A 128 x 64, W N x 64} stages, per 16-wide k-step one N = 256 and one
+// N = 128 MMA (NACC = 3).  Epilogue (16 warps; warp (q, g) owns TMEM lanes [32q, 32q+32) and the 32-column chunks c with
+// c % 4 == g):
+//   pass 1  TMEM -> registers -> 32x32 shared-memory transpose -> coalesced row segments: v written to `out`, per-row
+//           partial sums of v and v^2 kept in registers, reduced over the 8 lanes that share a row, then over the four
+//           column-group warps through shared memory;
+//   pass 2  every lane re-reads the v it wrote itself (L1 / L2 hot), normalises and writes bf16.
+// The variance is E[v^2] - E[v]^2 in fp32 over N <= 512 values (relative error ~1e-6 * mean^2 / var; the residual stream
+// of a ViT is close to zero-mean across channels).  129 tiles at batch 64 = one wave on 148 SMs: the kernel trades 13 % of
+// the SMs for not writing, re-reading and re-launching.
+#include "gemm_kernel.cuh"
+
+namespace dp {
+
+constexpr int kRlStages = 3;
+
+template <int NACC> struct RlCfg {
+  static constexpr int kN = 128 * NACC;
+  static constexpr int kStageBytes = kABytes + kN * kBlockK * 2;            // 16 KB + NACC x 16 KB
+  static constexpr int kRingBytes = kRlStages * kStageBytes;
+  static constexpr int kStatBytes = 128 * 4 * 2 * 4;                         // [row][column group][sum, sumsq]
+  static constexpr int kSmemBytes = kRingBytes + kStatBytes + 256;
+  static_assert(kRingBytes >= kStagingBytes, "the epilogue staging aliases the operand ring");
+  static_assert(kSmemBytes <= kSmemLimit, "shared memory");
+  static_assert(kN <= 512, "accumulator columns");
+};
+
+template <int NACC>
+__global__ void __launch_bounds__(kGemmThreads, 1) gemm_rowln_kernel(const __grid_constant__ GemmParams p) {
+  using C = RlCfg<NACC>;
+  extern __shared__ __align__(1024) uint8_t smem_gemm[];
+  uint8_t* smem = smem_gemm;
+  float* staging = reinterpret_cast<float*>(smem);      // aliases the ring: used only after the last MMA has completed
+  float* rowstat = reinterpret_cast<float*>(smem + C::kRingBytes);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::kRingBytes + C::kStatBytes);
+  uint64_t* empty_bar = full_bar + kRlStages;
+  uint64_t* tfull_bar = empty_bar + kRlStages;
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tfull_bar + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const Epilogue& e = p.epi;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) __trap();
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kRlStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tfull_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_holder, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_holder;
+  pdl_grid_sync();
+  const int m_blk = blockIdx.x;
+  const int nkb = p.num_k_blocks;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      PipeState ps;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty_bar[ps.stage], ps.phase ^ 1);
+        uint8_t* sa = smem + ps.stage * C::kStageBytes;
+        mbar_arrive_expect_tx(&full_bar[ps.stage], C::kStageBytes);
+        tma_load_2d(sa, &p.tmA, &full_bar[ps.stage], kb * kBlockK, m_blk * kBlockM);
+#pragma unroll
+        for (int a = 0; a < NACC; ++a)
+          tma_load_2d(sa + kABytes + a * kABytes, &p.tmB, &full_bar[ps.stage], kb * kBlockK, a * 128);
+        ps.template advance<kRlStages>();
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      PipeState ps;
+      constexpr int kWide = NACC >= 2 ? 256 : 128;                 // first MMA of a k-step
+      constexpr int kRest = C::kN - kWide;                          // second (0, 128 or 256 columns)
+      constexpr uint32_t idesc_w = make_idesc_bf16(kBlockM, kWide, 0, 0);
+      constexpr uint32_t idesc_r = make_idesc_bf16(kBlockM, kRest > 0 ? kRest : 128, 0, 0);
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[ps.stage], ps.phase);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + ps.stage * C::kStageBytes);
+        const uint32_t b_addr = a_addr + kABytes;
+#pragma unroll
+        for (int k = 0; k < kBlockK / 16; ++k) {
+          const uint64_t adesc = make_sdesc_sw128(a_addr + k * 32, 0, 1024);
+          umma_bf16(tmem_base, adesc, make_sdesc_sw128(b_addr + k * 32, 0, 1024), idesc_w, (kb | k) != 0 ? 1u : 0u);
+          if constexpr (kRest > 0)
+            umma_bf16(tmem_base + kWide, adesc, make_sdesc_sw128(b_addr + kWide * 128 + k * 32, 0, 1024), idesc_r,
+                      (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[ps.stage]);
+        ps.template advance<kRlStages>();
+      }
+      umma_commit(tfull_bar);
+    }
+  } else {
+    const int q = warp & 3;             // TMEM lane quarter
+    const int g = (warp - 2) >> 2;      // column group: chunks g, g + 4, g + 8, ...
+    float* stg = staging + (warp - 2) * (32 * 32);
+    const int rr = lane >> 3, cg = lane & 7;
+    constexpr uint32_t kFull = 0xffffffffu;
+    const int r = q * 32 + lane;
+    const long long row = (long long)m_blk * kBlockM + r;
+    const bool valid = row < p.M;
+    const uint32_t off_out = valid ? uint32_t(row) * uint32_t(e.ldo) : kInvalidRow;
+    const uint32_t off_res = uint32_t(valid ? row : 0) * uint32_t(e.ldr);
+    const uint32_t off_ln = uint32_t(valid ? row : 0) * uint32_t(e.ld_ln);
+    float rs1[8], rs2[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) rs1[it] = rs2[it] = 0.f;
+    bool waited = false;
+    // ---- pass 1
+#pragma unroll 1
+    for (int c = g; c < C::kN / 32; c += kEpiGroups) {
+      const int ccol = c * 32 + cg * 4;
+      const float4 bi = e.bias != nullptr ? ldg4(e.bias + ccol) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 lsv = e.ls != nullptr ? ldg4(e.ls + ccol) : make_float4(1.f, 1.f, 1.f, 1.f);
+      float4 res[8];
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rw = it * 4 + rr;
+        const bool ok = __shfl_sync(kFull, off_out, rw) != kInvalidRow;
+        const uint32_t r_off = __shfl_sync(kFull, off_res, rw);
+        res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok && e.residual != nullptr) res[it] = ldg4(e.residual + r_off + ccol);
+      }
+      if (!waited) {
+        mbar_wait(tfull_bar, 0);
+        tc_fence_after();
+        waited = true;
+      }
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(c * 32), v);
+      tmem_ld_wait();
+      {
+        float4* srow = reinterpret_cast<float4*>(stg + lane * 32);
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+          srow[jj ^ (lane & 7)] = make_float4(__uint_as_float(v[4 * jj]), __uint_as_float(v[4 * jj + 1]),
+                                              __uint_as_float(v[4 * jj + 2]), __uint_as_float(v[4 * jj + 3]));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rw = it * 4 + rr;
+        const float4 x = *reinterpret_cast<const float4*>(stg + rw * 32 + ((cg ^ (rw & 7)) << 2));
+        const uint32_t o_off = __shfl_sync(kFull, off_out, rw);
+        float4 f;
+        f.x = fmaf(x.x + bi.x, lsv.x, res[it].x);
+        f.y = fmaf(x.y + bi.y, lsv.y, res[it].y);
+        f.z = fmaf(x.z + bi.z, lsv.z, res[it].z);
+        f.w = fmaf(x.w + bi.w, lsv.w, res[it].w);
+        if (o_off != kInvalidRow) {
+          *reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + o_off + ccol) = f;
+          rs1[it] += (f.x + f.y) + (f.z + f.w);
+          rs2[it] += fmaf(f.x, f.x, f.y * f.y) + fmaf(f.z, f.z, f.w * f.w);
+        }
+      }
+      __syncwarp();   // the staging buffer is rewritten by the next chunk
+    }
+    // ---- row statistics: over the 8 lanes that share a row, then over the 4 column-group warps
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        rs1[it] += __shfl_xor_sync(kFull, rs1[it], o);
+        rs2[it] += __shfl_xor_sync(kFull, rs2[it], o);
+      }
+      if (cg == 0) {
+        const int rw = q * 32 + it * 4 + rr;
+        rowstat[(rw * 4 + g) * 2] = rs1[it];
+        rowstat[(rw * 4 + g) * 2 + 1] = rs2[it];
+      }
+    }
+    named_bar_sync(1, 32 * kEpiWarps);
+    float mean[8], rstd[8];
+    const float inv_n = 1.0f / float(C::kN);
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int rw = q * 32 + it * 4 + rr;
+      const float4 a = *reinterpret_cast<const float4*>(rowstat + rw * 8);
+      const float4 b = *reinterpret_cast<const float4*>(rowstat + rw * 8 + 4);
+      const float s1 = (a.x + a.z) + (b.x + b.z), s2 = (a.y + a.w) + (b.y + b.w);
+      mean[it] = s1 * inv_n;
+      rstd[it] = rsqrtf(fmaxf(s2 * inv_n - mean[it] * mean[it], 0.f) + e.ln_eps);
+    }
+    // ---- pass 2: every lane re-reads the values it wrote in pass 1 (same thread, program order), normalises, writes bf16
+#pragma unroll 1
+    for (int c = g; c < C::kN / 32; c += kEpiGroups) {
+      const int ccol = c * 32 + cg * 4;
+      const float4 ga = ldg4(e.ln_gamma + ccol), be = ldg4(e.ln_beta + ccol);
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int rw = it * 4 + rr;
+        const uint32_t o_off = __shfl_sync(kFull, off_out, rw);
+        const uint32_t l_off = __shfl_sync(kFull, off_ln, rw);
+        if (o_off != kInvalidRow) {
+          const float4 f = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(e.out) + o_off + ccol);
+          const float m = mean[it], s = rstd[it];
+          uint2 t;
+          t.x = pack_bf16x2(fmaf((f.x - m) * s, ga.x, be.x), fmaf((f.y - m) * s, ga.y, be.y));
+          t.y = pack_bf16x2(fmaf((f.z - m) * s, ga.z, be.z), fmaf((f.w - m) * s, ga.w, be.w));
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(e.ln_out) + l_off + ccol) = t;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem_base, 512);
+}
+
+template <int NACC>
+cudaError_t launch_gemm_rowln_t(const GemmParams& p, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_rowln_kernel<NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         RlCfg<NACC>::kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  launch_k<gemm_rowln_kernel<NACC>>(p.m_tiles, kGemmThreads, RlCfg<NACC>::kSmemBytes, s, p);
+  return cudaGetLastError();
+}
+
+// N = 128 * nacc accumulator columns; nacc in {1, 2, 3} (shared memory bounds the operand ring: nacc = 4 needs 80 KB stages)
+cudaError_t launch_gemm_rowln(const GemmParams& p, int nacc, cudaStream_t s) {
+  switch (nacc) {
+    case 1: return launch_gemm_rowln_t<1>(p, s);
+    case 2: return launch_gemm_rowln_t<2>(p, s);
+    case 3: return launch_gemm_rowln_t<3>(p, s);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+}  // namespace dp

@@ -36,6 +36,12 @@ struct Epilogue {
   int debug;        // tuning knobs (DP_GEMM_DEBUG env): 1 skip stores, 2 skip residual/aux loads, 4 skip phase 2, 8 skip TMEM loads
   int map_a, map_b; // ROWMAP_PATCH_TOKENS: (patches per image, tokens per image); NCHW: (channels K, 0);
                     // SHUFFLE2X2: (Cout, 0)
+  // row-owning kernel with the next LayerNorm fused (gemm_rowln.cu): ln_out = LayerNorm(out row; ln_gamma, ln_beta, ln_eps)
+  const float* ln_gamma;
+  const float* ln_beta;
+  void* ln_out;     // bf16 [rows, ld_ln]
+  long long ld_ln;
+  float ln_eps;
 };
 
 struct alignas(64) GemmParams {

@@ -477,6 +477,13 @@ class PoseEngine:
         halves = ((0, B0 * T, B0), (B0 * T, M, B - B0))
         split_open = False
         x_cur = t["x"]               # residual stream entering the current layer
+        # LayerNorm fused into the producing projection's epilogue (row-owning kernel, gemm_rowln.cu): N = D <= 384 (ViT-S;
+        # D = 768 / 1024 exceed the 512 accumulator columns of one SM).  OPT-IN (DP_FUSE_LN=1): measured on the benchmark
+        # step it is SLOWER, 3.97 vs 3.87 ms (gpurun_out/rowln_bench*.log; kernel level 29.5 vs 17.9 + 6.3 us for proj + LN):
+        # one tile per CTA means the 63 MB residual-stream epilogue of all 129 CTAs lands in one HBM burst with nothing to
+        # overlap, and a fifth of the SMs idle in the single wave.  The 25 LayerNorm launches stay.
+        fuse_ln = D in (128, 256, 384) and bool(int(os.environ.get("DP_FUSE_LN", "0")))
+        ln1_done = ln2_done = False
         for i in range(L):
             lp = f"backbone.encoder.layer.{i}."
             last = i == L - 1
@@ -540,8 +547,10 @@ class PoseEngine:
             if split_open:
                 be.sync("main_wait")              # both halves done: the remaining layers run on the whole batch
                 split_open = False
-            be.layernorm_fwd(t["x"], self.p(lp + "norm1.weight"), self.p(lp + "norm1.bias"), t["xn"], None, rows=M, D=D,
-                             eps=LN_EPS)
+            if not ln1_done:
+                be.layernorm_fwd(t["x"], self.p(lp + "norm1.weight"), self.p(lp + "norm1.bias"), t["xn"], None, rows=M, D=D,
+                                 eps=LN_EPS)
+            ln1_done = False
             be.gemm(t["xn"], fz[f"wqkv{i}"], t["qkv"], M=M, N=3 * D, K=D, bias=fz[f"bqkv{i}"], name=f"qkv{i}",
                     **self.tile("qkv", M))
             be.attention_fwd(t["qkv"], t["ctx"], B=B, T=T, heads=heads, scale=scale)
@@ -564,16 +573,30 @@ class PoseEngine:
                     be.gemm(t["ctx"], t["wo_m"], x_att, M=M, N=D, K=D, bias=t["bo_m"], out_dtype="f32",
                             ls=self.p(lp + "layer_scale1.lambda1"), residual=x_in, name="proj_last_merged")
             else:
+                # row-owning projection with the sub-block's NEXT LayerNorm fused into its epilogue (gemm_rowln.cu)
+                ln2 = dict(ln=dict(gamma=self.p(lp + "norm2.weight"), beta=self.p(lp + "norm2.bias"), out=t["xn"],
+                                   eps=LN_EPS)) if fuse_ln else {}
                 be.gemm(t["ctx"], fz[f"wo{i}"], x_att, M=M, N=D, K=D, bias=fz[f"bo{i}"], out_dtype="f32",
-                        ls=self.p(lp + "layer_scale1.lambda1"), residual=x_in, name=f"proj{i}", **self.tile("proj", M))
-            be.layernorm_fwd(x_att, self.p(lp + "norm2.weight"), self.p(lp + "norm2.bias"), t["xn"], None, rows=M, D=D,
-                             eps=LN_EPS)
+                        ls=self.p(lp + "layer_scale1.lambda1"), residual=x_in, name=f"proj{i}",
+                        **(ln2 if fuse_ln else self.tile("proj", M)))
+                ln2_done = fuse_ln
+            if not ln2_done:
+                be.layernorm_fwd(x_att, self.p(lp + "norm2.weight"), self.p(lp + "norm2.bias"), t["xn"], None, rows=M, D=D,
+                                 eps=LN_EPS)
+            ln2_done = False
             be.gemm(t["xn"], fz[f"w1{i}"], t["h"], M=M, N=4 * D, K=D, bias=self.p(lp + "mlp.fc1.bias"), act="gelu",
                     aux_out=t["pre"] if (last and training) else None, ld_aux=4 * D, name=f"fc1_{i}",
                     **self.tile("fc1", M))
             x_out = t["x_last"] if (last and training) else t["x"]
+            # fc2 + LayerScale + residual, and -- when the next layer is a plain frozen one -- ITS norm1 in the same epilogue
+            nxt = f"backbone.encoder.layer.{i + 1}."
+            fuse_next = fuse_ln and not last and (i + 1) not in lw and not split
+            ln1 = dict(ln=dict(gamma=self.p(nxt + "norm1.weight"), beta=self.p(nxt + "norm1.bias"), out=t["xn"],
+                               eps=LN_EPS)) if fuse_next else {}
             be.gemm(t["h"], fz[f"w2{i}"], x_out, M=M, N=D, K=4 * D, bias=self.p(lp + "mlp.fc2.bias"), out_dtype="f32",
-                    ls=self.p(lp + "layer_scale2.lambda1"), residual=x_att, name=f"fc2_{i}", **self.tile("fc2", M))
+                    ls=self.p(lp + "layer_scale2.lambda1"), residual=x_att, name=f"fc2_{i}",
+                    **(ln1 if fuse_next else self.tile("fc2", M)))
+            ln1_done = fuse_next
         if split_open:
             be.sync("main_wait")
         x_fin = t["x_last"] if training else t["x"]

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 5
+#define DP_ABI_VERSION 6
 
 const char* dp_last_error(void);
 int dp_abi_version(void);
@@ -74,7 +74,16 @@ typedef struct {
                              dp_bn_stats: zero on entry, dp_bn_finalize re-zeroes).  With DP_ROWMAP_SHUFFLE2X2
                              the channel of column j is j % map_a. */
   int stats_c;
-  int cta_pair;           /* 0 auto, 1 force the CTA-pair (cta_group::2, 256-row tile) kernel, 2 force single-CTA */
+  int cta_pair;           /* 0 auto, 1 force the CTA-pair (cta_group::2, 256-row tile) kernel, 2 force single-CTA,
+                             3 / 4 the A-stationary kernels (K <= 512; 4 = clusters of two with multicast weight loads) */
+  /* Optional fused LayerNorm of the OUTPUT rows (the nn.LayerNorm that follows the attention / MLP projection in the next
+   * sub-block, HF:371,379): ln_out = bf16 LayerNorm(out[row, :]; ln_gamma, ln_beta, ln_eps), row pitch ld_ln.  Needs
+   * out_dtype fp32, identity row map, a_mode 0 and N in {128, 256, 384} (one CTA owns complete rows). */
+  const float* ln_gamma;
+  const float* ln_beta;
+  void* ln_out;
+  long long ld_ln;
+  float ln_eps;
 } dp_gemm_args;
 int dp_gemm_bf16(const dp_gemm_args* a, void* stream);
 

@@ -121,7 +121,7 @@ class TorchEmulator:
     def gemm(self, A, W, out, *, M, N, K, lda=None, ldw=None, ldo=None, out_dtype="bf16", bias=None, scale=None,
              ls=None, residual=None, ldr=None, aux_out=None, aux_in=None, ld_aux=0, act="none", row_map="identity",
              n_valid=0, map_a=0, map_b=0, conv=None, OH=0, OW=0, NB=0, block_n=0, stats=None, stats_c=0, cta_pair=0,
-             name="gemm"):
+             ln=None, name="gemm"):
         def fn():
             Wf = W.float()[:N, :K]
             if conv is not None:
@@ -166,6 +166,9 @@ class TorchEmulator:
                 if residual is not None:
                     v = v + residual.float()[:M, :nv]
                 out[:M, :nv] = v.to(out.dtype)
+                if ln is not None:      # fused LayerNorm of the output rows (row-owning kernel)
+                    y = F.layer_norm(v.float(), (nv,), ln["gamma"], ln["beta"], ln.get("eps", 1e-6))
+                    ln["out"][:M, :nv] = y.to(ln["out"].dtype)
             elif row_map == "patch_tokens":
                 Bn = M // map_a
                 v = v.view(Bn, map_a, nv) + residual[1:1 + map_a, :nv]

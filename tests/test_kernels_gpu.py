@@ -119,6 +119,32 @@ def test_gemm_a_stationary(M, N, K, kind):
     assert rel(x, x0 + ref * ls) < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K", [(16448, 384, 384), (16448, 384, 1536), (257, 384, 384), (1000, 128, 128), (515, 256, 512),
+                                   (129, 384, 64)])
+def test_gemm_row_owning_with_fused_layernorm(M, N, K):
+    """gemm_rowln.cu: one CTA owns 128 complete rows; v = residual + ls * (A W^T + bias) is written in place into the fp32
+    residual stream and LayerNorm(v) leaves the same epilogue as bf16 (HF modeling_dinov2.py:250 + 373-379, 327 + 382-384)."""
+    A = rnd(M, K, dtype=BF)
+    W = rnd(N, K, scale=0.05, seed=1, dtype=BF)
+    bias, ls = rnd(N, seed=2), rnd(N, seed=4)
+    gamma, beta = rnd(N, seed=6).abs() + 0.5, rnd(N, seed=7)
+    x = rnd(M, N, seed=5) * 2.0 + 0.3
+    x0 = x.clone()
+    xn = torch.full((M, N), 7.0, device=dev(), dtype=BF)
+    run(lambda b: b.gemm(A, W, x, M=M, N=N, K=K, bias=bias, ls=ls, residual=x, out_dtype="f32",
+                         ln=dict(gamma=gamma, beta=beta, out=xn, eps=1e-6)))
+    ref = x0 + (A.float() @ W.float().t() + bias) * ls
+    assert rel(x, ref) < 2e-3
+    ref_ln = F.layer_norm(x, (N,), gamma, beta, 1e-6)          # LayerNorm of what the kernel itself wrote
+    assert rel(xn.float(), ref_ln) < 6e-3                       # bf16 rounding of the output
+    # separate output tensor (the last block in training keeps x_mid / x_last apart from the stream)
+    out2 = torch.zeros(M, N, device=dev())
+    xn2 = torch.zeros(M, N, device=dev(), dtype=BF)
+    run(lambda b: b.gemm(A, W, out2, M=M, N=N, K=K, bias=bias, ls=ls, residual=x0, out_dtype="f32",
+                         ln=dict(gamma=gamma, beta=beta, out=xn2, eps=1e-6)))
+    assert rel(out2, ref) < 2e-3 and rel(xn2.float(), F.layer_norm(out2, (N,), gamma, beta, 1e-6)) < 6e-3
+
+
 def test_gemm_epilogues():
     M, N, K = 700, 384, 256
     A = rnd(M, K, dtype=BF)

@@ -19,6 +19,8 @@ SHAPES = {
     "fc1": (M, 1536, 384, "gelu_bf16"),
     "fc2": (M, 384, 1536, "res_f32"),
     "fc2dg": (M, 1536, 384, "auxin_bf16"),     # last block's fc2 input gradient: x gelu'(pre-activation)
+    "proj_ln": (M, 384, 384, "res_f32_ln"),     # row-owning kernel, LayerNorm fused into the epilogue
+    "fc2_ln": (M, 384, 1536, "res_f32_ln"),
     "fc1_B": (M, 3072, 768, "gelu_bf16"),
     "fc2_B": (M, 768, 3072, "res_f32"),
 }
@@ -43,6 +45,13 @@ def bench(name, bn, reps=20, nbuf=6, pair=2):
         elif epi == "gelu_bf16":
             out = torch.empty(m, n, device=dev, dtype=BF)
             be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, act="gelu", block_n=bn, cta_pair=pair)
+        elif epi == "res_f32_ln":
+            out = torch.empty(m, n, device=dev)
+            res = torch.randn(m, n, device=dev)
+            ls = torch.ones(n, device=dev)
+            xn = torch.empty(m, n, device=dev, dtype=BF)
+            be.gemm(A, W, out, M=m, N=n, K=k, bias=bias, ls=ls, residual=res, out_dtype="f32",
+                    ln=dict(gamma=ls, beta=bias, out=xn, eps=1e-6))
         else:
             out = torch.empty(m, n, device=dev)
             res = torch.randn(m, n, device=dev)

@@ -45,6 +45,8 @@ class GemmArgs(C.Structure):
         ("row_map", C.c_int), ("n_valid", C.c_int), ("map_a", C.c_int), ("map_b", C.c_int),
         ("stats", c_vp), ("stats_c", C.c_int), ("cta_pair", C.c_int),
         ("ln_gamma", c_vp), ("ln_beta", c_vp), ("ln_out", c_vp), ("ld_ln", c_ll), ("ln_eps", C.c_float),
+        ("lora_A", c_vp), ("lora_B", c_vp), ("lora_y_out", c_vp), ("ld_lora_y", c_ll), ("lora_u_out", c_vp),
+        ("lora_seed", c_vp), ("lora_scaling", C.c_float), ("lora_p_drop", C.c_float), ("lora_rank", C.c_int),
     ]
 
 

@@ -197,10 +197,12 @@ class CudaBackend:
     def gemm(self, A, W, out, *, M, N, K, lda=None, ldw=None, ldo=None, out_dtype="bf16", bias=None, scale=None,
              ls=None, residual=None, ldr=None, aux_out=None, aux_in=None, ld_aux=0, act="none", row_map="identity",
              n_valid=0, map_a=0, map_b=0, conv=None, OH=0, OW=0, NB=0, block_n=0, stats=None, stats_c=0, cta_pair=0,
-             ln=None, name="gemm"):
+             ln=None, lora=None, name="gemm"):
         """out = epilogue(A[M,K] @ W[N,K]^T).  ``conv`` = dict(KH, KW, pad, OH, OW) makes A an NHWC
         [NB,IH,IW,C] activation (any strides with unit channel stride) read as an implicit conv.
-        ``ln`` = dict(gamma, beta, out, eps): LayerNorm of the output rows fused into the epilogue (row-owning kernel)."""
+        ``ln`` = dict(gamma, beta, out, eps): LayerNorm of the output rows fused into the epilogue (row-owning kernel).
+        ``lora`` = dict(A, B, scaling, p_drop, seed, y_out, u_out): rank-8 LoRA adapter on the projection output fused
+        into the same kernel's epilogue (out = residual + ls * (y + scaling * dropout(y A B)))."""
         _chk(W, torch.bfloat16, name + ".W", contiguous=False)
         a = GemmArgs()
         a.A, a.W, a.out = _p(A), _p(W), _p(out)
@@ -249,6 +251,17 @@ class CudaBackend:
             a.ln_gamma, a.ln_beta, a.ln_out = _p(ln["gamma"]), _p(ln["beta"]), _p(ln["out"])
             a.ld_ln, a.ln_eps = ln["out"].stride(0), float(ln.get("eps", 1e-6))
             lnk = (ln["gamma"], ln["beta"], ln["out"])
+        if lora is not None:
+            for nm in ("A", "B"):
+                _chk(lora[nm], torch.float32, f"{name}.lora_{nm}")
+            a.lora_A, a.lora_B, a.lora_rank = _p(lora["A"]), _p(lora["B"]), lora["A"].shape[1]
+            a.lora_scaling, a.lora_p_drop = float(lora["scaling"]), float(lora.get("p_drop", 0.0))
+            a.lora_seed = _p(lora.get("seed"))
+            y_out, u_out = lora.get("y_out"), lora.get("u_out")
+            _chk(y_out, torch.float32, name + ".lora_y_out", contiguous=False)
+            _chk(u_out, torch.float32, name + ".lora_u_out")
+            a.lora_y_out, a.ld_lora_y, a.lora_u_out = _p(y_out), (y_out.stride(0) if y_out is not None else N), _p(u_out)
+            lnk = (lora["A"], lora["B"], lora.get("seed"), y_out, u_out)
         self.prog.add(name, self.lib.dp_gemm_bf16, C.byref(a), kernel="gemm_kmajor_tcgen05", flops=2.0 * M * N * K,
                       keep=(a, A, W, out, bias, scale, ls, residual, aux_out, aux_in, stats) + lnk)
 

@@ -19,7 +19,7 @@ struct GemmVariant {
 };
 const GemmVariant* select_gemm_variant(const Epilogue& e, int a_mode, int block_n, int pair, bool tma_out_ok);
 cudaError_t launch_wgrad(const WgradParams& p, int block_n, int grid, cudaStream_t s);
-cudaError_t launch_gemm_rowln(const GemmParams& p, int nacc, cudaStream_t s);
+cudaError_t launch_gemm_rowln(const GemmParams& p, int nacc, int mode, cudaStream_t s);
 
 static thread_local char g_err[512] = "";
 int set_error(int code, const char* fmt, ...) {
@@ -161,15 +161,25 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
       return set_error(-9, "dp_gemm_bf16: tensor too large for 32-bit epilogue offsets");
   }
   // ---- fused LayerNorm of the output rows: row-owning kernel (gemm_rowln.cu)
-  if (a->ln_out) {
-    if (!a->ln_gamma || !a->ln_beta) return set_error(-1, "dp_gemm_bf16: ln_out without ln_gamma / ln_beta");
+  if (a->ln_out || a->lora_A) {
+    const bool lora = a->lora_A != nullptr;
+    if (lora && a->ln_out) return set_error(-3, "dp_gemm_bf16: fused LoRA and fused LayerNorm cannot be combined");
+    if (lora && (!a->lora_B || a->lora_rank != 8)) return set_error(-3, "dp_gemm_bf16: fused LoRA needs lora_B and rank 8");
+    if (!lora && (!a->ln_gamma || !a->ln_beta)) return set_error(-1, "dp_gemm_bf16: ln_out without ln_gamma / ln_beta");
     if (a->a_mode != 0 || e.out_dtype != DP_OUT_F32 || e.row_map != DP_ROWMAP_IDENTITY || e.scale || e.aux_out || e.aux_in ||
         e.stats || a->act != DP_ACT_NONE || e.res_is_bf16 || (a->N != 128 && a->N != 256 && a->N != 384) || (a->K % 64))
       return set_error(-3, "dp_gemm_bf16: fused LayerNorm needs a plain fp32-output projection with N in {128,256,384}, K %% 64 == 0");
-    if ((a->ld_ln % 4) || (e.ldo % 4) || (e.residual && (e.ldr % 4)))
-      return set_error(-7, "dp_gemm_bf16: fused LayerNorm needs row pitches that are multiples of 4");
-    if ((long long)a->M * a->ld_ln + a->N >= 0xffffffffLL) return set_error(-9, "dp_gemm_bf16: tensor too large for 32-bit offsets");
-    e.ln_gamma = a->ln_gamma; e.ln_beta = a->ln_beta; e.ln_out = a->ln_out; e.ld_ln = a->ld_ln; e.ln_eps = a->ln_eps;
+    const long long ld2 = lora ? a->ld_lora_y : a->ld_ln;
+    if ((ld2 % 4) || (e.ldo % 4) || (e.residual && (e.ldr % 4)))
+      return set_error(-7, "dp_gemm_bf16: fused LayerNorm / LoRA needs row pitches that are multiples of 4");
+    if ((long long)a->M * ld2 + a->N >= 0xffffffffLL) return set_error(-9, "dp_gemm_bf16: tensor too large for 32-bit offsets");
+    if (lora) {
+      e.lora_A = a->lora_A; e.lora_B = a->lora_B; e.lora_u_out = a->lora_u_out; e.lora_seed = a->lora_seed;
+      e.lora_scaling = a->lora_scaling; e.lora_p_drop = a->lora_p_drop;
+      e.ln_out = a->lora_y_out; e.ld_ln = a->ld_lora_y;     // the kernel's second output slot carries y (fp32) in LoRA mode
+    } else {
+      e.ln_gamma = a->ln_gamma; e.ln_beta = a->ln_beta; e.ln_out = a->ln_out; e.ld_ln = a->ld_ln; e.ln_eps = a->ln_eps;
+    }
     p.N = a->N; p.n_tiles = 1; p.a_mode = 0; p.M = a->M;
     p.m_tiles = (a->M + 127) / 128;
     p.num_k_blocks = a->K / 64;
@@ -186,7 +196,8 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
       const uint32_t box[2] = {64, 128};
       if ((rc2 = make_tmap(&p.tmB, a->W, 2, dims, st, box))) return rc2;
     }
-    return cuda_error(launch_gemm_rowln(p, a->N / 128, static_cast<cudaStream_t>(stream)), "dp_gemm_bf16 (fused LayerNorm) launch");
+    return cuda_error(launch_gemm_rowln(p, a->N / 128, lora ? 1 : 0, static_cast<cudaStream_t>(stream)),
+                      "dp_gemm_bf16 (row-owning kernel) launch");
   }
   // ---- tile shape: CTA-pair 256 x {192, 256, 128} tiles when a variant is compiled for this epilogue and N divides,
   // else single-CTA 128 x {128, 64, 32}.  block_n fixes the width, cta_pair (1 pair / 2 single) the kind.

@@ -42,6 +42,12 @@ struct Epilogue {
   void* ln_out;     // bf16 [rows, ld_ln]
   long long ld_ln;
   float ln_eps;
+  // same kernel, LoRA mode: x_out = residual + ls * (y + lora_scaling * dropout(y lora_A lora_B)); ln_out then receives y (fp32)
+  const float* lora_A;                  // [N, 8]
+  const float* lora_B;                  // [8, N]
+  float* lora_u_out;                    // [rows, 8] (saved for the backward) or nullptr
+  const unsigned long long* lora_seed;  // device scalar
+  float lora_scaling, lora_p_drop;
 };
 
 struct alignas(64) GemmParams {

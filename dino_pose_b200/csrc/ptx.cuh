@@ -243,6 +243,16 @@ __device__ __forceinline__ float gelu_fast_both(float x, float& dgelu) {
   dgelu = fmaf(hx * fmaf(-th, th, 1.f), q, fmaf(0.5f, th, 0.5f));
   return fmaf(hx, th, hx);
 }
+// Counter-based dropout mask: keep iff hash(seed, index) >= p * 2^32.  Same function in every forward and backward kernel.
+__device__ __forceinline__ uint32_t mix32(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return uint32_t((z ^ (z >> 31)) >> 16);
+}
+__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
+  return mix32(seed * 0xD1342543DE82EF95ull + idx) >= thresh;
+}
 __device__ __forceinline__ long long global_timer_ns() {
   long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));

@@ -376,16 +376,7 @@ cudaError_t launch_fill_cls(float* x, const float* cls_row, int B, int T, int D,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Counter-based dropout mask: keep iff hash(seed, index) >= p * 2^32.  Same function in fwd and bwd.
-__device__ __forceinline__ uint32_t mix32(uint64_t z) {
-  z += 0x9E3779B97F4A7C15ull;
-  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-  return uint32_t((z ^ (z >> 31)) >> 16);
-}
-__device__ __forceinline__ bool dropout_keep(uint64_t seed, uint64_t idx, uint32_t thresh) {
-  return mix32(seed * 0xD1342543DE82EF95ull + idx) >= thresh;
-}
+// (counter-based dropout mask: mix32 / dropout_keep live in ptx.cuh, shared with the LoRA-fused GEMM epilogue)
 
 // LoRA adapter on the attention-block output (reference model/lora.py:26-28,57-59) fused with
 // LayerScale + residual (HF:373-376):

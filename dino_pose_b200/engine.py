@@ -557,8 +557,20 @@ class PoseEngine:
             x_in = t["x"]
             x_att = t["x_mid"] if (last and training) else t["x"]
             if last and use_lora:
-                if lora_train:
-                    # explicit adapter (dropout + saved activations for the backward)
+                lora_fused = (lora_train and D in (128, 256, 384) and self.lora["rank"] == 8
+                              and bool(int(os.environ.get("DP_LORA_FUSED", "1"))))
+                if lora_fused:
+                    # the adapter INSIDE the projection GEMM (row-owning tcgen05 kernel, gemm_rowln.cu MODE 1): the rank-8 side
+                    # product, the dropout mask, LayerScale and the residual are applied to the accumulator tile in tensor
+                    # memory; y and u are saved for dp_lora_bwd (reference model/lora.py:26-28,53-59, dinov2_pose.py:197-204)
+                    be.gemm(t["ctx"], fz[f"wo{i}"], x_att, M=M, N=D, K=D, bias=fz[f"bo{i}"], out_dtype="f32",
+                            ls=self.p(lp + "layer_scale1.lambda1"), residual=x_in,
+                            lora=dict(A=self.p(self.lora_prefix + "lora_A"), B=self.p(self.lora_prefix + "lora_B"),
+                                      scaling=self.lora["alpha"] / self.lora["rank"],
+                                      p_drop=float(self.lora.get("dropout", 0.0)), seed=self.seed, y_out=t["y"], u_out=t["u"]),
+                            name="proj_last_lora")
+                elif lora_train:
+                    # explicit adapter (dropout + saved activations for the backward): ViT-B / L (D > 384) or rank != 8
                     be.gemm(t["ctx"], fz[f"wo{i}"], t["y"], M=M, N=D, K=D, bias=fz[f"bo{i}"], out_dtype="f32",
                             name="proj_last")
                     be.lora_fwd(t["y"], self.p(self.lora_prefix + "lora_A"), self.p(self.lora_prefix + "lora_B"),

@@ -84,6 +84,20 @@ typedef struct {
   void* ln_out;
   long long ld_ln;
   float ln_eps;
+  /* Optional fused LoRA adapter on the projection output (reference model/lora.py:26-28,53-59 + LayerScale + residual,
+   * HF:373-376), same row-owning kernel:  y = A W^T + bias;  out = residual + ls * (y + lora_scaling * dropout(y lora_A lora_B)).
+   * lora_A fp32 [N, 8], lora_B fp32 [8, N] (rank 8); the dropout mask is the counter-based hash of dp_lora_bwd (key =
+   * *lora_seed, element row * N + column, probability lora_p_drop).  lora_y_out fp32 [rows, ld_lora_y] and lora_u_out fp32
+   * [rows, 8] receive y and u = y lora_A, the activations dp_lora_bwd reads (either may be NULL).  Same shape limits as the
+   * fused LayerNorm; the two cannot be combined. */
+  const float* lora_A;
+  const float* lora_B;
+  float* lora_y_out;
+  long long ld_lora_y;
+  float* lora_u_out;
+  const unsigned long long* lora_seed;
+  float lora_scaling, lora_p_drop;
+  int lora_rank;
 } dp_gemm_args;
 int dp_gemm_bf16(const dp_gemm_args* a, void* stream);
 

@@ -121,7 +121,7 @@ class TorchEmulator:
     def gemm(self, A, W, out, *, M, N, K, lda=None, ldw=None, ldo=None, out_dtype="bf16", bias=None, scale=None,
              ls=None, residual=None, ldr=None, aux_out=None, aux_in=None, ld_aux=0, act="none", row_map="identity",
              n_valid=0, map_a=0, map_b=0, conv=None, OH=0, OW=0, NB=0, block_n=0, stats=None, stats_c=0, cta_pair=0,
-             ln=None, name="gemm"):
+             ln=None, lora=None, name="gemm"):
         def fn():
             Wf = W.float()[:N, :K]
             if conv is not None:
@@ -160,6 +160,15 @@ class TorchEmulator:
                 v = F.gelu(v)
             if aux_in is not None:
                 v = v * aux_in.view(-1, ld_aux)[:M, :nv].float()
+            if lora is not None:       # fused LoRA adapter: v + scaling * dropout(v A B); y and u saved for the backward
+                u = v @ lora["A"].float()
+                if lora.get("y_out") is not None:
+                    lora["y_out"][:M, :nv] = v
+                if lora.get("u_out") is not None:
+                    lora["u_out"][:M] = u
+                d = u @ lora["B"].float()
+                assert float(lora.get("p_drop", 0.0)) == 0.0, "emulator: dropout parity is tested statistically on the GPU only"
+                v = v + d * float(lora["scaling"])
             if ls is not None:
                 v = v * ls[:nv]
             if row_map == "identity":

@@ -145,6 +145,34 @@ def test_gemm_row_owning_with_fused_layernorm(M, N, K):
     assert rel(out2, ref) < 2e-3 and rel(xn2.float(), F.layer_norm(out2, (N,), gamma, beta, 1e-6)) < 6e-3
 
 
+@pytest.mark.parametrize("M,N,K,p_drop", [(16448, 384, 384, 0.0), (1000, 384, 384, 0.1), (257, 128, 128, 0.0), (515, 128, 512, 0.1)])
+def test_gemm_with_fused_lora_adapter(M, N, K, p_drop):
+    """gemm_rowln.cu MODE 1: out = residual + ls * (y + s * dropout(y A B)), y = ctx W^T + bias, rank 8 (reference
+    model/lora.py:26-28,53-59 + HF:373-376).  Checked against the torch expression and, with dropout, against the separate
+    dp_lora_fwd kernel on the SAME seed (the masks must be identical: the backward regenerates them from the seed)."""
+    A = rnd(M, K, dtype=BF)
+    W = rnd(N, K, scale=0.05, seed=1, dtype=BF)
+    bias, ls = rnd(N, seed=2), rnd(N, seed=4)
+    la, lb = rnd(N, 8, scale=0.2, seed=6), rnd(8, N, scale=0.2, seed=7)
+    x_in = rnd(M, N, seed=5)
+    seed = torch.tensor([12345], device=dev(), dtype=torch.int64)
+    out = torch.zeros(M, N, device=dev())
+    y = torch.zeros(M, N, device=dev())
+    u = torch.zeros(M, 8, device=dev())
+    run(lambda b: b.gemm(A, W, out, M=M, N=N, K=K, bias=bias, ls=ls, residual=x_in, out_dtype="f32",
+                         lora=dict(A=la, B=lb, scaling=2.0, p_drop=p_drop, seed=seed, y_out=y, u_out=u)))
+    y_ref = A.float() @ W.float().t() + bias
+    assert rel(y, y_ref) < 2e-3 and rel(u, y_ref @ la) < 2e-3
+    # the separate adapter kernel on the y the fused kernel saved: same arithmetic, same mask
+    sep = torch.zeros(M, N, device=dev())
+    u2 = torch.zeros(M, 8, device=dev())
+    run(lambda b: b.lora_fwd(y, la, lb, ls, x_in, sep, u2, rows=M, D=N, R=8, scaling=2.0, p_drop=p_drop, seed=seed))
+    assert rel(out, sep) < 1e-5, rel(out, sep)
+    assert rel(u, u2) < 1e-5
+    if p_drop == 0.0:
+        assert rel(out, x_in + (y_ref + (y_ref @ la @ lb) * 2.0) * ls) < 2e-3
+
+
 def test_gemm_epilogues():
     M, N, K = 700, 384, 256
     A = rnd(M, K, dtype=BF)

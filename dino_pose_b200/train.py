@@ -18,6 +18,8 @@ How it differs from the reference loop, all deliberate (SURVEY 7.2-6, 8f-1, 8f-2
 """
 from __future__ import annotations
 
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -65,6 +67,10 @@ class PoseTrainer:
         self.group = process_group
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         self.lr, self.wd, self.betas, self.eps = lr, weight_decay, betas, eps
+        # DP_BUCKET_MB / DP_NO_ALLREDUCE: A/B switches for the scaling analysis (profiles/r2_scaling.md); the second one skips
+        # the gradient exchange altogether (replicas diverge: measurement only)
+        bucket_mb = float(os.environ.get("DP_BUCKET_MB", bucket_mb))
+        self.no_allreduce = bool(int(os.environ.get("DP_NO_ALLREDUCE", "0")))
         self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
         self.use_graph = use_graph and self.device.type == "cuda"
         self.comm_stream = torch.cuda.Stream(device=self.device) if (self.world > 1 and self.device.type == "cuda") else None
@@ -191,7 +197,7 @@ class PoseTrainer:
 
         def on_mark(tag):
             kind, upto = tag
-            if kind != "grads_final" or self.world == 1:
+            if kind != "grads_final" or self.world == 1 or self.no_allreduce:
                 return
             if upto - sent[0] < self.bucket_elems and upto < total:
                 return

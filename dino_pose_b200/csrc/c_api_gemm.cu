@@ -42,6 +42,11 @@ int sm_count() {
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     if (n <= 0) n = 148;
+    // DP_RESERVE_SMS=k: the persistent (one CTA per SM) GEMM / weight-gradient grids leave k SMs free, so that the CTAs of
+    // a concurrent NCCL all-reduce can become resident beside them (data-parallel training; A/B in profiles/r2_scaling.md)
+    const char* v = getenv("DP_RESERVE_SMS");
+    const int k = v ? atoi(v) : 0;
+    if (k > 0 && k < n - 16) n -= k;
   }
   return n;
 }

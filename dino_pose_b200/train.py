@@ -73,7 +73,11 @@ class PoseTrainer:
         self.no_allreduce = bool(int(os.environ.get("DP_NO_ALLREDUCE", "0")))
         self.bucket_elems = max(1, int(bucket_mb * (1 << 20) / 4))
         self.use_graph = use_graph and self.device.type == "cuda"
-        self.comm_stream = torch.cuda.Stream(device=self.device) if (self.world > 1 and self.device.type == "cuda") else None
+        # the exchange runs on its own HIGH-priority stream: NCCL's CTAs are scheduled ahead of the backward's whenever an SM
+        # frees up (DP_COMM_PRIORITY=0: default priority, A/B)
+        prio = -1 if int(os.environ.get("DP_COMM_PRIORITY", "-1")) < 0 else 0
+        self.comm_stream = (torch.cuda.Stream(device=self.device, priority=prio)
+                            if (self.world > 1 and self.device.type == "cuda") else None)
         self.buckets_sent = []          # [(lo, hi)] of the last step, for tests / introspection
         self._flatten_parameters()
         dev = self.device
@@ -223,7 +227,7 @@ class PoseTrainer:
         plan["fwd"].run()
         st["loss"].run()
         eng.backward(plan, "static", "static", on_mark=self._on_mark(plan["gflat"]))
-        if self.comm_stream is not None:
+        if self.comm_stream is not None and not self.no_allreduce:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         st["opt"].run()
 

@@ -14,6 +14,12 @@ except Exception as e:
 PY
 }
 run default A=1
+if [ "${AB:-0}" = "2" ]; then
+  run prio0 DP_COMM_PRIORITY=0
+  run reserve4 DP_RESERVE_SMS=4 NCCL_MAX_CTAS=4
+  run reserve8 DP_RESERVE_SMS=8 NCCL_MAX_CTAS=8
+  run reserve16 DP_RESERVE_SMS=16 NCCL_MAX_CTAS=16
+fi
 if [ "${AB:-0}" = "1" ]; then
   run noallreduce DP_NO_ALLREDUCE=1
   run maxctas4 NCCL_MAX_CTAS=4

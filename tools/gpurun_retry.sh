@@ -1,8 +1,9 @@
 #!/bin/bash
-# usage: tools/gpurun_retry.sh <timeout> <command...>: retries while the pod answers busy / transient (exit code 3)
+# usage: [GPUS=N] tools/gpurun_retry.sh <timeout> <command...>: retries while the pod answers busy / transient (exit code 3)
 T=$1; shift
+G=""; [ -n "$GPUS" ] && G="--gpus $GPUS"
 for i in $(seq 1 30); do
-  /usr/local/graft/bin/gpurun --timeout $T -- "$@" > /tmp/gpurun_last.log 2>&1; rc=$?
+  /usr/local/graft/bin/gpurun $G --timeout $T -- "$@" > /tmp/gpurun_last.log 2>&1; rc=$?
   if [ $rc -ne 3 ] && ! grep -q "status=transient" /tmp/gpurun_last.log; then break; fi
   sleep 60
 done

@@ -116,7 +116,7 @@ SIGNATURES = {
     "dp_relu_mask": [c_vp, c_vp, c_vp, c_ll, f, c_vp],
     "dp_pose_loss": [c_vp, c_vp, c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, i, i, f, f, c_vp],
     "dp_adamw": [c_vp, c_vp, c_vp, c_vp, c_ll, f, f, f, f, f, f, c_vp, c_vp],
-    "dp_adamw_dev": [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, f, f, f, f, c_vp, c_vp],
+    "dp_adamw_dev": [c_vp, c_vp, c_vp, c_vp, c_ll, c_vp, f, f, f, f, c_vp, i, c_vp],
     "dp_pack_weights_bf16": [c_vp, i, c_ll, c_vp],
     "dp_add_i64": [c_vp, i, c_ll, c_vp],
 }

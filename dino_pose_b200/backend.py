@@ -464,7 +464,7 @@ class CudaBackend:
                       _p(state), _p(out), _p(scales), _p(dhm), _p(dz), B, K, HW, momentum, rate,
                       keep=(hm, thm, kps, z, tz, sums, state, out, scales, dhm, dz), bytes=B * K * HW * 4.0 * 5, launches=3)
 
-    def adamw(self, p, g, m, v, step_dev, *, n, lr, beta1, beta2, eps, weight_decay, grad_scale, hyper=None):
+    def adamw(self, p, g, m, v, step_dev, *, n, lr, beta1, beta2, eps, weight_decay, grad_scale, hyper=None, bump=True):
         """hyper: optional device fp32 {lr, weight_decay}; when given, lr / weight_decay arguments are ignored and a
         scheduler can change the rate between replays of a captured step."""
         for t, nm in ((p, "params"), (g, "grads"), (m, "exp_avg"), (v, "exp_avg_sq")):
@@ -472,8 +472,10 @@ class CudaBackend:
         if hyper is not None:
             _chk(hyper, torch.float32, "adamw.hyper")
             self.prog.add("adamw", self.lib.dp_adamw_dev, _p(p), _p(g), _p(m), _p(v), n, _p(hyper), beta1, beta2, eps,
-                          grad_scale, _p(step_dev), keep=(p, g, m, v, step_dev, hyper), bytes=n * 4.0 * 7, launches=2)
+                          grad_scale, _p(step_dev), int(bump), keep=(p, g, m, v, step_dev, hyper), bytes=n * 4.0 * 7,
+                          launches=2 if bump else 1)
             return
+        assert bump, "slice-wise AdamW needs the device hyper-parameter form (dp_adamw_dev)"
         self.prog.add("adamw", self.lib.dp_adamw, _p(p), _p(g), _p(m), _p(v), n, lr, beta1, beta2, eps, weight_decay,
                       grad_scale, _p(step_dev), keep=(p, g, m, v, step_dev), bytes=n * 4.0 * 7, launches=2)
 

@@ -38,6 +38,7 @@ constexpr int kRowBytes = kDh * 2;                 // 128 B: one row of a [rows]
 constexpr int kTile128 = 128 * kRowBytes;          // 16 KB
 constexpr int kTile64 = 64 * kRowBytes;            // 8 KB
 constexpr int kBThreads = 192;                     // warp 0 MMA issue, warp 1 TMEM alloc + TMA, warps 2..5 softmax (thread = row)
+constexpr int kDkvThreads = 64 + 8 * 32;           // dK / dV kernel: eight softmax warps (two per TMEM lane quarter)
 
 struct BwdParams {
   CUtensorMap tm128;   // qkv: 2-D {3*D, B*T} bf16, box {64, 128}, 128B swizzle
@@ -362,7 +363,7 @@ __global__ void __launch_bounds__(kBThreads, 2) attention_bwd_dq_tc_kernel(const
 // [128 q rows][128 B]).  TMEM (512 columns, one CTA per SM): S [0,128), dP [128,256), dV [256,320), dK [320,384).
 constexpr int kDkvSmem = 2 * kTile128 + 4 * kTile128 + 4 * kTile128 + 256;
 
-__global__ void __launch_bounds__(kBThreads, 1) attention_bwd_dkv_tc_kernel(const __grid_constant__ BwdParams p) {
+__global__ void __launch_bounds__(kDkvThreads, 1) attention_bwd_dkv_tc_kernel(const __grid_constant__ BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sK = smem;
   uint8_t* sV = sK + kTile128;
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(kBThreads, 1) attention_bwd_dkv_tc_kernel(cons
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     mbar_init(s_full, 1);
-    mbar_init(pds_ready, 4);
+    mbar_init(pds_ready, 8);
     mbar_init(dkv_full, 1);
     fence_barrier_init();
   }
@@ -450,7 +451,10 @@ __global__ void __launch_bounds__(kBThreads, 1) attention_bwd_dkv_tc_kernel(cons
       umma_commit(dkv_full);
     }
   } else {
+    // EIGHT softmax warps: two per TMEM lane quarter (warp % 4), each taking one 64-key half of the tile -- with one CTA per
+    // SM four warps left the SM at 9 % warp occupancy (ncu, profiles/r2_full_attnbwd.md)
     const int q = warp & 3, r = q * 32 + lane;
+    const int half = (warp - 2) >> 2;
     const uint32_t trow = tmem_base + (uint32_t(q * 32) << 16);
     const float sl = p.scale_log2;
     for (int i = 0; i < q_tiles; ++i) {
@@ -467,7 +471,7 @@ __global__ void __launch_bounds__(kBThreads, 1) attention_bwd_dkv_tc_kernel(cons
       tc_fence_after();
       if (warp_needed) {
 #pragma unroll 1
-        for (int c = 0; c < nk; c += 16) {
+        for (int c = half * 64; c < min(nk, half * 64 + 64); c += 16) {
           uint32_t s[16], d[16];
           tmem_ld_32x16(trow + uint32_t(c), s);
           tmem_ld_32x16(trow + 128 + uint32_t(c), d);
@@ -500,25 +504,20 @@ __global__ void __launch_bounds__(kBThreads, 1) attention_bwd_dkv_tc_kernel(cons
     tc_fence_after();
     const int key = kt * 128 + r;
     if (q * 32 < keys_valid) {   // warp-uniform (tcgen05.ld is warp-collective); the stores are predicated per key row
-      __nv_bfloat16* dk = p.dqkv + (long long)(row0 + key) * (3 * p.D) + p.D + h * kDh;
-      __nv_bfloat16* dv = dk + p.D;
+      // half 0 writes dV (TMEM [256,320)), half 1 writes dK (TMEM [320,384), times the softmax scale)
+      __nv_bfloat16* dst = p.dqkv + (long long)(row0 + key) * (3 * p.D) + (half == 0 ? 2 : 1) * p.D + h * kDh;
+      const float mul = half == 0 ? 1.f : p.scale;
 #pragma unroll
       for (int c = 0; c < kDh; c += 16) {
-        uint32_t v[16], w[16];
-        tmem_ld_32x16(trow + 256 + uint32_t(c), v);
-        tmem_ld_32x16(trow + 320 + uint32_t(c), w);
+        uint32_t v[16];
+        tmem_ld_32x16(trow + (half == 0 ? 256u : 320u) + uint32_t(c), v);
         tmem_ld_wait();
-        uint32_t pv[8], pk[8];
+        uint32_t pv[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          pv[e] = pack_bf16x2(__uint_as_float(v[2 * e]), __uint_as_float(v[2 * e + 1]));
-          pk[e] = pack_bf16x2(__uint_as_float(w[2 * e]) * p.scale, __uint_as_float(w[2 * e + 1]) * p.scale);
-        }
+        for (int e = 0; e < 8; ++e) pv[e] = pack_bf16x2(__uint_as_float(v[2 * e]) * mul, __uint_as_float(v[2 * e + 1]) * mul);
         if (key < p.T) {
-          reinterpret_cast<uint4*>(dv + c)[0] = make_uint4(pv[0], pv[1], pv[2], pv[3]);
-          reinterpret_cast<uint4*>(dv + c)[1] = make_uint4(pv[4], pv[5], pv[6], pv[7]);
-          reinterpret_cast<uint4*>(dk + c)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          reinterpret_cast<uint4*>(dk + c)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          reinterpret_cast<uint4*>(dst + c)[0] = make_uint4(pv[0], pv[1], pv[2], pv[3]);
+          reinterpret_cast<uint4*>(dst + c)[1] = make_uint4(pv[4], pv[5], pv[6], pv[7]);
         }
       }
     }
@@ -586,7 +585,7 @@ cudaError_t launch_attention_bwd(const __nv_bfloat16* qkv, const __nv_bfloat16* 
   if (stages < 0) { const char* v = getenv("DP_ATTN_BWD_STAGES"); stages = v ? atoi(v) : 7; }
   if (stages & 1) launch_k<attention_bwd_stats_kernel>(grid, kBThreads, kStatsSmem, s, p);
   if (stages & 2) launch_k<attention_bwd_dq_tc_kernel>(grid, kBThreads, kDqSmem, s, p);
-  if (stages & 4) launch_k<attention_bwd_dkv_tc_kernel>(grid, kBThreads, kDkvSmem, s, p);
+  if (stages & 4) launch_k<attention_bwd_dkv_tc_kernel>(grid, kDkvThreads, kDkvSmem, s, p);
   return cudaGetLastError();
 }
 

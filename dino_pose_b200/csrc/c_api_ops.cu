@@ -276,7 +276,7 @@ namespace dp {
 cudaError_t launch_pose_loss(const float*, const float*, const float*, int, const float*, const float*, double*, float*, float*,
                              float*, float*, float*, int, int, int, float, float, int, cudaStream_t);
 cudaError_t launch_adamw(float*, const float*, float*, float*, long long, float, float, float, float, float, float, long long*,
-                         const float*, int, cudaStream_t);
+                         const float*, int, int, cudaStream_t);
 }  // namespace dp
 extern "C" int dp_pose_loss(const float* heatmaps, const float* target_heatmaps, const float* keypoints, int kp_stride,
                             const float* z, const float* target_z, double* sums, float* state, float* out, float* scales,
@@ -292,15 +292,15 @@ extern "C" int dp_adamw(float* params, const float* grads, float* exp_avg, float
   if (!params || !grads || !exp_avg || !exp_avg_sq || !step_dev) return set_error(-1, "dp_adamw: null pointer");
   if (n <= 0 || (n % 4)) return set_error(-2, "dp_adamw: n must be a positive multiple of 4");
   return cuda_error(launch_adamw(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, weight_decay, grad_scale,
-                                 step_dev, nullptr, sm_count(), ST), "dp_adamw");
+                                 step_dev, nullptr, 1, sm_count(), ST), "dp_adamw");
 }
 extern "C" int dp_adamw_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n,
                             const float* hyper_dev, float beta1, float beta2, float eps, float grad_scale, long long* step_dev,
-                            void* stream) {
+                            int bump_step, void* stream) {
   if (!params || !grads || !exp_avg || !exp_avg_sq || !step_dev || !hyper_dev) return set_error(-1, "dp_adamw_dev: null pointer");
   if (n <= 0 || (n % 4)) return set_error(-2, "dp_adamw_dev: n must be a positive multiple of 4");
   return cuda_error(launch_adamw(params, grads, exp_avg, exp_avg_sq, n, 0.f, beta1, beta2, eps, 0.f, grad_scale, step_dev,
-                                 hyper_dev, sm_count(), ST), "dp_adamw_dev");
+                                 hyper_dev, bump_step, sm_count(), ST), "dp_adamw_dev");
 }
 
 namespace dp {

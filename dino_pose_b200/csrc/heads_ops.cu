@@ -749,7 +749,7 @@ struct BnBwdFused {
   int eval_mode;
 };
 template <typename RawT, bool FUSED>
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(
+__global__ void __launch_bounds__(kBnThreads, 4) bn_bwd_apply_kernel(
     const __nv_bfloat16* __restrict__ dout, const RawT* __restrict__ raw, const __nv_bfloat16* __restrict__ add1,
     const float* __restrict__ scale, const float* __restrict__ shift, const float* __restrict__ coef,
     __nv_bfloat16* __restrict__ draw, __nv_bfloat16* __restrict__ dres, long long P, int C4, int relu, int mode,
@@ -1185,19 +1185,33 @@ cudaError_t launch_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, 
                                                         dw, NB, H, W, C8);
   return cudaGetLastError();
 }
-// backward kernels: 4 channels per thread, 2 rows per iteration, up to 5 resident blocks per SM
-static unsigned bn_grid4(long long P, int C4) {
+// backward kernels: 4 channels per thread, 2 rows per iteration, grid-stride over the rows.  The grid is ONE wave of
+// resident blocks of the kernel actually launched (occupancy query, cached per instantiation): the round-1 cap of 5 blocks
+// per SM was 1.25 waves for the reduce kernel (55 registers: 4 resident blocks) and 1.67 for the apply kernel (80
+// registers: 3), i.e. a second, mostly empty wave per launch (ncu: 37-43 % / 30 % warps active).
+template <typename K>
+static int bn_resident_blocks(K kernel) {
+  static int blocks = 0;
+  if (blocks == 0) {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, kernel, kBnThreads, 0) != cudaSuccess || b < 1) b = 3;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    blocks = b * (sms > 0 ? sms : 148);
+  }
+  return blocks;
+}
+static unsigned bn_grid4(long long P, int C4, int resident) {
   const int rpb = kBnThreads / C4;
   long long g = (P + 2 * rpb - 1) / (2 * rpb);
-  const long long cap = 148 * 5;
-  if (g > cap) g = cap;
+  if (g > resident) g = resident;
   return unsigned(g < 1 ? 1 : g);
 }
-static unsigned bn_grid(long long P, int C8) {
+static unsigned bn_grid(long long P, int C8, int resident) {
   const int rpb = kBnThreads / C8;
   long long g = (P + rpb - 1) / rpb;
-  const long long cap = 148 * 4;
-  if (g > cap) g = cap;
+  if (g > resident) g = resident;      // one wave of resident blocks (see bn_resident_blocks)
   return unsigned(g < 1 ? 1 : g);
 }
 static bool bn_c_ok(int C) { return C % 8 == 0 && kBnThreads % (C / 8) == 0 && C / 8 <= kBnThreads; }
@@ -1205,9 +1219,9 @@ static bool bn_c_ok(int C) { return C % 8 == 0 && kBnThreads % (C / 8) == 0 && C
 cudaError_t launch_bn_stats(const void* raw, int raw_f32, double* sums, long long P, int C, cudaStream_t s) {
   if (!bn_c_ok(C)) return cudaErrorInvalidValue;
   if (raw_f32)
-    launch_k<bn_stats_kernel<float>>(bn_grid(P, C / 8), kBnThreads, 0, s, reinterpret_cast<const float*>(raw), sums, P, C / 8);
+    launch_k<bn_stats_kernel<float>>(bn_grid(P, C / 8, bn_resident_blocks(bn_stats_kernel<float>)), kBnThreads, 0, s, reinterpret_cast<const float*>(raw), sums, P, C / 8);
   else
-    launch_k<bn_stats_kernel<__nv_bfloat16>>(bn_grid(P, C / 8), kBnThreads, 0, s, reinterpret_cast<const __nv_bfloat16*>(raw), sums, P, C / 8);
+    launch_k<bn_stats_kernel<__nv_bfloat16>>(bn_grid(P, C / 8, bn_resident_blocks(bn_stats_kernel<__nv_bfloat16>)), kBnThreads, 0, s, reinterpret_cast<const __nv_bfloat16*>(raw), sums, P, C / 8);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_finalize(double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,
@@ -1229,9 +1243,9 @@ cudaError_t launch_bn_apply(const void* raw, int raw_f32, const float* scale, co
   auto a2 = reinterpret_cast<const __nv_bfloat16*>(add2);
   auto o = reinterpret_cast<__nv_bfloat16*>(out);
   if (raw_f32)
-    launch_k<bn_apply_kernel<float>>(bn_grid(P, C / 8), kBnThreads, 0, s, reinterpret_cast<const float*>(raw), scale, shift, a1, a2, o, P, C / 8, relu, mode);
+    launch_k<bn_apply_kernel<float>>(bn_grid(P, C / 8, bn_resident_blocks(bn_apply_kernel<float>)), kBnThreads, 0, s, reinterpret_cast<const float*>(raw), scale, shift, a1, a2, o, P, C / 8, relu, mode);
   else
-    launch_k<bn_apply_kernel<__nv_bfloat16>>(bn_grid(P, C / 8), kBnThreads, 0, s, reinterpret_cast<const __nv_bfloat16*>(raw), scale, shift, a1, a2, o, P, C / 8, relu, mode);
+    launch_k<bn_apply_kernel<__nv_bfloat16>>(bn_grid(P, C / 8, bn_resident_blocks(bn_apply_kernel<__nv_bfloat16>)), kBnThreads, 0, s, reinterpret_cast<const __nv_bfloat16*>(raw), scale, shift, a1, a2, o, P, C / 8, relu, mode);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_finalize_apply(const void* raw, int raw_f32, double* sums, const float* gamma, const float* beta, float* rm,
@@ -1245,11 +1259,11 @@ cudaError_t launch_bn_finalize_apply(const void* raw, int raw_f32, double* sums,
   // ticket counter: last 4 bytes of the coefficient-scratch block of `sums` (see launch_bn_bwd_apply)
   unsigned int* counter = reinterpret_cast<unsigned int*>(sums + (long long)kBnBwdReplicas * 2 * C) + 3 * C;
   if (raw_f32)
-    launch_k<bn_finalize_apply_kernel<float>>(bn_grid(P, C / 8), kBnThreads, 0, s, reinterpret_cast<const float*>(raw), sums, counter,
+    launch_k<bn_finalize_apply_kernel<float>>(bn_grid(P, C / 8, bn_resident_blocks(bn_finalize_apply_kernel<float>)), kBnThreads, 0, s, reinterpret_cast<const float*>(raw), sums, counter,
                                               gamma, beta, rm, rv, scale, shift, mean, invstd, a1, a2, o, P, C / 8, relu, mode,
                                               double(P), eps, momentum);
   else
-    launch_k<bn_finalize_apply_kernel<__nv_bfloat16>>(bn_grid(P, C / 8), kBnThreads, 0, s, reinterpret_cast<const __nv_bfloat16*>(raw),
+    launch_k<bn_finalize_apply_kernel<__nv_bfloat16>>(bn_grid(P, C / 8, bn_resident_blocks(bn_finalize_apply_kernel<__nv_bfloat16>)), kBnThreads, 0, s, reinterpret_cast<const __nv_bfloat16*>(raw),
                                                       sums, counter, gamma, beta, rm, rv, scale, shift, mean, invstd, a1, a2, o, P,
                                                       C / 8, relu, mode, double(P), eps, momentum);
   return cudaGetLastError();
@@ -1261,9 +1275,9 @@ cudaError_t launch_bn_bwd_reduce(const void* dout, const void* raw, int raw_f32,
   auto d = reinterpret_cast<const __nv_bfloat16*>(dout);
   auto a1 = reinterpret_cast<const __nv_bfloat16*>(add1);
   if (raw_f32)
-    launch_k<bn_bwd_reduce_kernel<float>>(bn_grid4(P, C / 4), kBnThreads, 0, s, d, reinterpret_cast<const float*>(raw), a1, scale, shift, sums, P, C / 4, relu, mode);
+    launch_k<bn_bwd_reduce_kernel<float>>(bn_grid4(P, C / 4, bn_resident_blocks(bn_bwd_reduce_kernel<float>)), kBnThreads, 0, s, d, reinterpret_cast<const float*>(raw), a1, scale, shift, sums, P, C / 4, relu, mode);
   else
-    launch_k<bn_bwd_reduce_kernel<__nv_bfloat16>>(bn_grid4(P, C / 4), kBnThreads, 0, s, d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, sums, P, C / 4, relu, mode);
+    launch_k<bn_bwd_reduce_kernel<__nv_bfloat16>>(bn_grid4(P, C / 4, bn_resident_blocks(bn_bwd_reduce_kernel<__nv_bfloat16>)), kBnThreads, 0, s, d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, sums, P, C / 4, relu, mode);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_bwd_apply(const void* dout, const void* raw, int raw_f32, const void* add1, const float* gamma,
@@ -1285,18 +1299,18 @@ cudaError_t launch_bn_bwd_apply(const void* dout, const void* raw, int raw_f32, 
     fz.gamma = gamma; fz.mean = mean; fz.invstd = invstd; fz.dgamma = dgamma; fz.dbeta = dbeta;
     fz.invP = 1.0 / double(P); fz.eval_mode = eval_mode;
     if (raw_f32)
-      launch_k<bn_bwd_apply_kernel<float, true>>(bn_grid4(P, C / 4), kBnThreads, 0, s, d, reinterpret_cast<const float*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow, fz);
+      launch_k<bn_bwd_apply_kernel<float, true>>(bn_grid4(P, C / 4, bn_resident_blocks(bn_bwd_apply_kernel<float, true>)), kBnThreads, 0, s, d, reinterpret_cast<const float*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow, fz);
     else
-      launch_k<bn_bwd_apply_kernel<__nv_bfloat16, true>>(bn_grid4(P, C / 4), kBnThreads, 0, s, d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow, fz);
+      launch_k<bn_bwd_apply_kernel<__nv_bfloat16, true>>(bn_grid4(P, C / 4, bn_resident_blocks(bn_bwd_apply_kernel<__nv_bfloat16, true>)), kBnThreads, 0, s, d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow, fz);
     return cudaGetLastError();
   }
   const BnBwdFused none = {};
   launch_k<bn_bwd_coeffs_kernel>((C + 127) / 128, 128, 0, s, sums, gamma, scale, mean, invstd, coef, dgamma, dbeta, C, 1.0 / double(P),
                                                       eval_mode);
   if (raw_f32)
-    launch_k<bn_bwd_apply_kernel<float, false>>(bn_grid4(P, C / 4), kBnThreads, 0, s, d, reinterpret_cast<const float*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow, none);
+    launch_k<bn_bwd_apply_kernel<float, false>>(bn_grid4(P, C / 4, bn_resident_blocks(bn_bwd_apply_kernel<float, false>)), kBnThreads, 0, s, d, reinterpret_cast<const float*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow, none);
   else
-    launch_k<bn_bwd_apply_kernel<__nv_bfloat16, false>>(bn_grid4(P, C / 4), kBnThreads, 0, s, d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow, none);
+    launch_k<bn_bwd_apply_kernel<__nv_bfloat16, false>>(bn_grid4(P, C / 4, bn_resident_blocks(bn_bwd_apply_kernel<__nv_bfloat16, false>)), kBnThreads, 0, s, d, reinterpret_cast<const __nv_bfloat16*>(raw), a1, scale, shift, coef, dr, ds, P, C / 4, relu, mode, shuffle_oh, shuffle_ow, none);
   return cudaGetLastError();
 }
 cudaError_t launch_zero_f64(double* p, int n, cudaStream_t s) {

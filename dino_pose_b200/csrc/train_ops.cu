@@ -168,14 +168,15 @@ cudaError_t launch_pose_loss(const float* hm, const float* thm, const float* kps
 }
 
 cudaError_t launch_adamw(float* p, const float* g, float* m, float* v, long long n, float lr, float b1, float b2, float eps,
-                         float wd, float grad_scale, long long* step_dev, const float* hyper, int sms, cudaStream_t s) {
+                         float wd, float grad_scale, long long* step_dev, const float* hyper, int bump_step, int sms,
+                         cudaStream_t s) {
   const long long n4 = n / 4;
   int grid = int((n4 + 255) / 256);
   if (grid > sms * 8) grid = sms * 8;
   if (grid < 1) grid = 1;
   launch_k<adamw_kernel>(grid, 256, 0, s, reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
                                     reinterpret_cast<float4*>(v), n4, lr, b1, b2, eps, wd, grad_scale, step_dev, hyper);
-  launch_k<bump_step_kernel>(1, 1, 0, s, step_dev);
+  if (bump_step) launch_k<bump_step_kernel>(1, 1, 0, s, step_dev);
   return cudaGetLastError();
 }
 

@@ -362,6 +362,23 @@ class PoseEngine:
             return dict(block_n=256, cta_pair=1)
         return {}
 
+    def head_tile(self, M, N, K):
+        """Tile shape of the heads' implicit-GEMM convolutions (forward and input gradients).  DP_HEAD_TILE: "pair" = CTA-pair
+        256-row tiles (cta_group::2) where the shape allows, "wide" = single-CTA tiles 256 columns wide, "default" = 128 x
+        128.  The long-K convolutions (K = 9 C) are bound by L2 -> SM operand traffic at 128 x 128 (64 FLOP/B)."""
+        mode = os.environ.get("DP_HEAD_TILE", "pair")
+        kmin = int(os.environ.get("DP_HEAD_TILE_KMIN", "1024"))
+        if mode == "default" or M < 4096 or K < kmin:
+            return {}
+        if mode == "pair":
+            for bn in (256, 192, 128):
+                if N % bn == 0:
+                    return dict(block_n=bn, cta_pair=1)
+            return {}
+        if mode == "wide" and N % 256 == 0:
+            return dict(block_n=256)
+        return {}
+
     # ------------------------------------------------------------------ plans
     def get_plan(self, B, H, W, training, scope="model"):
         key = (B, H, W, bool(training)) if scope == "model" else (B, H, W, bool(training), scope)
@@ -670,19 +687,21 @@ class PoseEngine:
         if L.kind == "conv" and L.k == 1:
             be.gemm(x.reshape(-1, L.cin), L.t["wf"], out, M=P_out, N=L.cout, K=L.cin,
                     bias=be_shift if fold else bias, scale=be_scale if fold else None, act=act if fold else "none",
-                    name=L.name, **st)
+                    name=L.name, **st, **(self.head_tile(P_out, L.cout, L.cin) if (training and L.bn is not None) else {}))
         elif L.kind in ("conv", "convT_s1"):
             pad = L.pad if L.kind == "conv" else L.k - 1 - L.pad
             xin = x.view(NB, L.ih, L.iw, L.cin) if x.dim() == 2 else x
             be.gemm(xin, L.t["wf"], out, M=P_out, N=L.cout, K=kk * L.cin, bias=be_shift if fold else bias,
                     scale=be_scale if fold else None, act=act if fold else "none",
-                    conv=dict(KH=L.k, KW=L.k, pad=pad, OH=L.oh, OW=L.ow), name=L.name, **st)
+                    conv=dict(KH=L.k, KW=L.k, pad=pad, OH=L.oh, OW=L.ow), name=L.name, **st,
+                    **(self.head_tile(P_out, L.cout, kk * L.cin) if (training and L.bn is not None) else {}))
         elif L.kind == "conv_s2":
             L.t["col"] = self.new((P_out, kk * L.cin), self.adt)
             be.im2col(x, L.t["col"], NB=NB, IH=L.ih, IW=L.iw, C=L.cin, OH=L.oh, OW=L.ow, KH=L.k, KW=L.k, stride=L.stride,
                       pad=L.pad)
             be.gemm(L.t["col"], L.t["wf"], out, M=P_out, N=L.cout, K=kk * L.cin, bias=be_shift if fold else bias,
-                    scale=be_scale if fold else None, act=act if fold else "none", name=L.name, **st)
+                    scale=be_scale if fold else None, act=act if fold else "none", name=L.name, **st,
+                    **(self.head_tile(P_out, L.cout, kk * L.cin) if (training and L.bn is not None) else {}))
         elif L.kind == "convT2":
             P_in = NB * L.ih * L.iw
             L.t["bias4"] = self.new((kk * L.cout,), F32)
@@ -1003,7 +1022,7 @@ class PoseEngine:
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
                     be.gemm(draw, L.t["wd"], dx, M=P_out, N=ci, K=draw.shape[1], residual=dx_residual,
-                            name=L.name + ".dgrad")
+                            name=L.name + ".dgrad", **self.head_tile(P_out, ci, draw.shape[1]))
             elif L.kind == "conv":
                 d4 = draw.view(B, L.oh, L.ow, co)
                 x4 = x_in.view(B, L.ih, L.iw, ci) if x_in.dim() == 2 else x_in
@@ -1019,7 +1038,8 @@ class PoseEngine:
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
                     be.gemm(d4, L.t["wd"], dx, M=P_in, N=ci, K=kk * co, residual=dx_residual,
-                            conv=dict(KH=k, KW=k, pad=k - 1 - L.pad, OH=L.ih, OW=L.iw), name=L.name + ".dgrad")
+                            conv=dict(KH=k, KW=k, pad=k - 1 - L.pad, OH=L.ih, OW=L.iw), name=L.name + ".dgrad",
+                            **self.head_tile(P_in, ci, kk * co))
             elif L.kind == "convT_s1":
                 x4 = x_in.view(B, L.ih, L.iw, ci)
                 d4 = draw.view(B, L.oh, L.ow, co)
@@ -1028,7 +1048,8 @@ class PoseEngine:
                 if want_dx:
                     dx = self.new((P_in, ci), self.adt)
                     be.gemm(d4, L.t["wd"], dx, M=P_in, N=ci, K=kk * co, residual=dx_residual,
-                            conv=dict(KH=k, KW=k, pad=L.pad, OH=L.ih, OW=L.iw), name=L.name + ".dgrad")
+                            conv=dict(KH=k, KW=k, pad=L.pad, OH=L.ih, OW=L.iw), name=L.name + ".dgrad",
+                            **self.head_tile(P_in, ci, kk * co))
             elif L.kind == "conv_s2":
                 wg(draw, L.t["col"], gw, Mc=co, Nc=kk * ci, so_m=ci * kk, so_n=kk, so_no=1, n_inner=ci, P=P_out,
                          name=L.name + ".wgrad", workspace=ws)

@@ -186,37 +186,74 @@ class PoseTrainer:
         st["loss"] = be.begin()
         be.pose_loss(hm, st["thm"], st["kps"], plan["t"]["z"], st["tz"], self.loss_sums, self.loss_state, self.loss_out,
                      self.loss_scales, plan["t"]["dhm"], plan["t"]["dz"], B=B, K=K, HW=hm.shape[2] * hm.shape[3])
+        # AdamW in two launches over disjoint slices of the flat buffers: [0, split) = the head parameters, whose gradients are
+        # final (and, data-parallel, all-reduced) while the backbone part of the backward (final LayerNorm, last block's MLP,
+        # LoRA / un-frozen layers) is still running -- that slice is updated on the side stream underneath it; [split, total)
+        # follows the last gradient.  DP_SPLIT_ADAMW=0: one launch at the end (A/B).
+        total, split = self.layout["total"], self.layout["group_end"].get("fr0", 0)
+        if not (0 < split < total) or not bool(int(os.environ.get("DP_SPLIT_ADAMW", "1"))):
+            split = 0
+        st["opt_split"] = split
+        kw = dict(lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.wd,
+                  grad_scale=1.0 / self.world, hyper=self.hyper)
+        g = plan["gflat"]
+        if split:
+            st["opt_head"] = be.begin()
+            be.adamw(self.flat_params[:split], g[:split], self.exp_avg[:split], self.exp_avg_sq[:split], self.step_dev,
+                     n=split, bump=False, **kw)
         st["opt"] = be.begin()
-        be.adamw(self.flat_params, plan["gflat"], self.exp_avg, self.exp_avg_sq, self.step_dev, n=self.layout["total"],
-                 lr=self.lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.wd,
-                 grad_scale=1.0 / self.world, hyper=self.hyper)
+        be.adamw(self.flat_params[split:], g[split:], self.exp_avg[split:], self.exp_avg_sq[split:], self.step_dev,
+                 n=total - split, **kw)
         st["graph"] = None
         return st
 
-    def _on_mark(self, flat):
-        """Bucketing: called by the backward program when flat[:upto] is final."""
+    def _on_mark(self, flat, st=None):
+        """Bucketing: called by the backward program when flat[:upto] is final.  At the head / backbone boundary
+        (``st['opt_split']``) the bucket is flushed whatever its size and the head slice's AdamW is issued right behind
+        its all-reduce (data-parallel: on the exchange stream; single GPU: on a side stream)."""
         sent = [0]
         total = flat.numel()
         self.buckets_sent = []
+        split = st.get("opt_split", 0) if st is not None else 0
+        head_done = [False]
+        exchange = self.world > 1 and not self.no_allreduce
+
+        def side_stream():
+            if self.device.type != "cuda":
+                return None
+            if self.comm_stream is not None:
+                return self.comm_stream
+            if getattr(self, "opt_stream", None) is None:
+                self.opt_stream = torch.cuda.Stream(device=self.device)
+            return self.opt_stream
 
         def on_mark(tag):
             kind, upto = tag
-            if kind != "grads_final" or self.world == 1 or self.no_allreduce:
+            if kind != "grads_final":
                 return
-            if upto - sent[0] < self.bucket_elems and upto < total:
-                return
-            lo, hi = sent[0], upto
-            if hi <= lo:
-                return
-            sent[0] = hi
-            self.buckets_sent.append((lo, hi))
-            if self.comm_stream is not None:
-                cur = torch.cuda.current_stream()
-                self.comm_stream.wait_stream(cur)
-                with torch.cuda.stream(self.comm_stream):
+            at_split = split and upto >= split and not head_done[0]
+            if exchange and (upto - sent[0] >= self.bucket_elems or upto >= total or at_split) and upto > sent[0]:
+                lo, hi = sent[0], upto
+                sent[0] = hi
+                self.buckets_sent.append((lo, hi))
+                if self.comm_stream is not None:
+                    cur = torch.cuda.current_stream()
+                    self.comm_stream.wait_stream(cur)
+                    with torch.cuda.stream(self.comm_stream):
+                        dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+                else:   # CPU (gloo) test path
                     dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
-            else:   # CPU (gloo) test path
-                dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+            if at_split:
+                head_done[0] = True
+                ss = side_stream()
+                if ss is None:
+                    st["opt_head"].run()
+                else:
+                    if ss is not self.comm_stream or not exchange:
+                        ss.wait_stream(torch.cuda.current_stream())
+                    with torch.cuda.stream(ss):
+                        st["opt_head"].run()
+                    st["side_used"] = ss
         return on_mark
 
     @torch.no_grad()
@@ -226,9 +263,12 @@ class PoseTrainer:
         eng.seed.add_(1)
         plan["fwd"].run()
         st["loss"].run()
-        eng.backward(plan, "static", "static", on_mark=self._on_mark(plan["gflat"]))
+        st["side_used"] = None
+        eng.backward(plan, "static", "static", on_mark=self._on_mark(plan["gflat"], st))
         if self.comm_stream is not None and not self.no_allreduce:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
+        elif st.get("side_used") is not None:
+            torch.cuda.current_stream().wait_stream(st["side_used"])
         st["opt"].run()
 
     def _capture(self, st):

@@ -254,9 +254,12 @@ int dp_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_s
              float beta2, float eps, float weight_decay, float grad_scale, long long* step_dev, void* stream);
 /* Same step with the learning rate and the weight decay read from DEVICE memory, hyper_dev = fp32 {lr, weight_decay}:
  * the reference's ReduceLROnPlateau (train.py:286-293,341) changes the rate between steps, and a step captured in a
- * CUDA graph would otherwise keep the value it was recorded with. */
+ * CUDA graph would otherwise keep the value it was recorded with.
+ * bump_step = 0 leaves the step counter alone: the optimizer step may be issued as several launches over disjoint slices of
+ * the flat buffers (the slice whose gradients are final first is updated while the backward of the rest still runs); the
+ * last launch of a step passes 1. */
 int dp_adamw_dev(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, const float* hyper_dev,
-                 float beta1, float beta2, float eps, float grad_scale, long long* step_dev, void* stream);
+                 float beta1, float beta2, float eps, float grad_scale, long long* step_dev, int bump_step, void* stream);
 
 /* Re-pack trainable conv weights (fp32 [d0,d1,kh,kw] nn.Parameters, reference model/pose_heads.py) into the bf16 GEMM
  * layouts, all layers in one launch.  jobs_dev: device table, 16 int64 per job =

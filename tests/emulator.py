@@ -102,7 +102,7 @@ class TorchEmulator:
             dz.view(B, K).copy_(s1 * mask.view(B, K) * torch.sign(zd))
         self.prog.calls.append(fn)
 
-    def adamw(self, p, g, m, v, step_dev, *, n, lr, beta1, beta2, eps, weight_decay, grad_scale, hyper=None):
+    def adamw(self, p, g, m, v, step_dev, *, n, lr, beta1, beta2, eps, weight_decay, grad_scale, hyper=None, bump=True):
         lr0, wd0 = lr, weight_decay
 
         def fn():
@@ -114,7 +114,8 @@ class TorchEmulator:
             v[:n].mul_(beta2).addcmul_(gg, gg, value=1 - beta2)
             denom = v[:n].sqrt() / (1 - beta2 ** t) ** 0.5 + eps
             p[:n].addcdiv_(m[:n], denom, value=-lr / (1 - beta1 ** t))
-            step_dev.add_(1)
+            if bump:
+                step_dev.add_(1)
         self.prog.calls.append(fn)
 
     # ------------------------------------------------------------------ GEMM family

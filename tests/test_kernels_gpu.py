@@ -283,6 +283,31 @@ def test_gemm_implicit_conv(NB, H, W, Cin, Cout, k, pad, OH, OW):
     assert rel(out.float().view(NB, OH, OW, Cout).permute(0, 3, 1, 2), ref) < 1e-2
 
 
+@pytest.mark.parametrize("NB,H,Cin,Cout,bn", [(8, 16, 128, 512, 256), (8, 16, 512, 256, 256), (3, 48, 128, 128, 128), (5, 16, 128, 384, 192)])
+def test_gemm_implicit_conv_cta_pair(NB, H, Cin, Cout, bn):
+    """CTA-pair (cta_group::2, 256-pixel tiles) implicit 3x3 convolution: fp32 output + fused BatchNorm statistics (the heads'
+    forward), and bf16 output + bf16 residual (their input gradients); odd tile counts leave a phantom half."""
+    k, pad = 3, 1
+    x = rnd(NB, H, H, Cin, dtype=BF)
+    w = rnd(Cout, Cin, k, k, scale=0.05, seed=1)
+    Wm = w.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin).contiguous().to(BF)
+    bias = rnd(Cout, seed=2)
+    P = NB * H * H
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), Wm.float().view(Cout, k, k, Cin).permute(0, 3, 1, 2), bias, padding=pad)
+    ref = ref.permute(0, 2, 3, 1).reshape(P, Cout)
+    out = torch.zeros(P, Cout, device=dev())
+    sums = torch.zeros(2 * Cout, device=dev(), dtype=torch.float64)
+    run(lambda b: b.gemm(x, Wm, out, M=P, N=Cout, K=k * k * Cin, bias=bias, out_dtype="f32", stats=sums, stats_c=Cout,
+                         conv=dict(KH=k, KW=k, pad=pad, OH=H, OW=H), block_n=bn, cta_pair=1))
+    assert rel(out, ref) < 2e-3
+    assert rel(sums[:Cout], out.double().sum(0)) < 1e-4 and rel(sums[Cout:], (out.double() ** 2).sum(0)) < 1e-4
+    res = rnd(P, Cout, seed=7, dtype=BF)
+    out2 = torch.zeros(P, Cout, device=dev(), dtype=BF)
+    run(lambda b: b.gemm(x, Wm, out2, M=P, N=Cout, K=k * k * Cin, residual=res, conv=dict(KH=k, KW=k, pad=pad, OH=H, OW=H),
+                         block_n=bn, cta_pair=1))
+    assert rel(out2.float(), ref - bias + res.float()) < 1e-2
+
+
 def test_gemm_implicit_conv_token_view():
     """A = patch tokens inside the [B,T,D] final-LayerNorm output (CLS skipped by pointer offset)."""
     B, g, D, Cout = 2, 16, 128, 128

@@ -169,7 +169,8 @@ def run_reference(args, cfg):
         "impl": "reference", "metric": metric_name(cfg), "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{cfg['text']} (BASELINE.json configs[{cfg['idx']}]); CPU{bounded}", "global_batch": batch},
+        "config": {"workload": f"{cfg['text']} (BASELINE.json configs[{cfg['idx']}])", "name": args.config,
+                   "global_batch": batch, "arm": f"reference arithmetic on the host CPU (oracle port){bounded}"},
         "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

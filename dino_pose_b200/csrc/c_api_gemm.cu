@@ -230,13 +230,13 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   if (a->cta_pair >= 3 && !var) return set_error(-3, "dp_gemm_bf16: no A-stationary variant for this shape / epilogue");
   if (var) {
   } else if (a->block_n != 0) {
-    if (may_pair) var = select_gemm_variant(e, a->a_mode, a->block_n, 1, false);
+    if (may_pair) var = select_gemm_variant(e, a->a_mode, a->block_n, 1, tma_out_ok);
     if (!var && may_single) var = select_gemm_variant(e, a->a_mode, a->block_n, 0, tma_out_ok);
   } else {
     if (may_pair) {
       const int cand[3] = {192, 256, 128};
       for (int i = 0; i < 3 && !var; ++i)
-        if (a->N % cand[i] == 0 && a->N >= 2 * cand[i] - 128) var = select_gemm_variant(e, a->a_mode, cand[i], 1, false);
+        if (a->N % cand[i] == 0 && a->N >= 2 * cand[i] - 128) var = select_gemm_variant(e, a->a_mode, cand[i], 1, tma_out_ok);
     }
     if (!var && may_single) var = select_gemm_variant(e, a->a_mode, a->N >= 128 ? 128 : (a->N > 32 ? 64 : 32), 0, tma_out_ok);
   }

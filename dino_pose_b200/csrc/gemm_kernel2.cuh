@@ -52,6 +52,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
+    if constexpr ((OPT & OP_TMA_OUT) != 0) tma_prefetch_desc(&p.tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < C::kStages; ++i) {
@@ -150,10 +151,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
     float* stg = staging + (warp - 2) * (32 * 32);
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t nstore = 0;   // OP_TMA_OUT: tile stores issued by this warp so far
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
       DP_PAIR_COORDS(tile, m_blk, n_blk)
-      epilogue_tile<BN, OUT, ACT, MAP, OPT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk, stg, colstats,
-                                            &tfull_bar[acc], acc_phase);
+      if constexpr ((OPT & OP_TMA_OUT) != 0) {
+        // plain bf16 outputs (QKV, fc1): thread = row out of TMEM, staged bf16 tiles, TMA tile stores (rows of the phantom
+        // half of an odd last pair lie beyond M and are clipped by the tensor map)
+        TmaEpiBias<BN> pre;
+        epilogue_tma_prefetch<BN>(p, half, lane, n_blk, pre);
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tc_fence_after();
+        epilogue_tile_tma<BN, ACT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk,
+                                   reinterpret_cast<uint8_t*>(stg), nstore, pre);
+      } else {
+        epilogue_tile<BN, OUT, ACT, MAP, OPT>(p, tmem_base + uint32_t(acc * BN), q, half, lane, m_blk, n_blk, stg, colstats,
+                                              &tfull_bar[acc], acc_phase);
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -182,6 +195,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
           }
         }
       }
+    }
+    if constexpr ((OPT & OP_TMA_OUT) != 0) {
+      if (lane == 0) bulk_wait_read<0>();   // shared memory must stay allocated until the last tile store has read it
     }
   }
 #undef DP_PAIR_COORDS

@@ -12,7 +12,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdinopose_sm100a.so")
 
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 c_ll = C.c_longlong
 c_vp = C.c_void_p
@@ -98,7 +98,7 @@ SIGNATURES = {
     "dp_dwconv3x3_wgrad": [c_vp, c_vp, c_vp, i, i, i, i, c_vp],
     "dp_bn_stats": [c_vp, i, c_vp, c_ll, i, c_vp],
     "dp_bn_finalize": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, d, f, f, c_vp],
-    "dp_bn_fold_eval": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, f, c_vp],
+    "dp_bn_fold_eval": [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, i, f, c_vp],
     "dp_bn_apply": [c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, c_vp],
     "dp_preprocess_workspace_bytes": [i, i, i, i, i],
     "dp_preprocess_u8": [c_vp, i, i, i, i, i, c_vp, c_vp, c_vp, c_vp, c_ll, c_vp],

@@ -397,9 +397,10 @@ class CudaBackend:
                       _p(shift), _p(mean), _p(invstd), C, float(count), eps, momentum,
                       keep=(sums, gamma, beta, rm, rv, scale, shift, mean, invstd))
 
-    def bn_fold_eval(self, gamma, beta, rm, rv, conv_bias, scale, shift, *, C, eps=1e-5):
+    def bn_fold_eval(self, gamma, beta, rm, rv, conv_bias, scale, shift, *, C, eps=1e-5, mean=None, invstd=None):
         self.prog.add("bn_fold_eval", self.lib.dp_bn_fold_eval, _p(gamma), _p(beta), _p(rm), _p(rv), _p(conv_bias),
-                      _p(scale), _p(shift), C, eps, keep=(gamma, beta, rm, rv, conv_bias, scale, shift))
+                      _p(scale), _p(shift), _p(mean), _p(invstd), C, eps,
+                      keep=(gamma, beta, rm, rv, conv_bias, scale, shift, mean, invstd))
 
     def bn_apply(self, raw, scale, shift, add1, add2, out, *, P, C, relu=True, mode=0):
         self.prog.add("bn_apply", self.lib.dp_bn_apply, _p(raw), int(raw.dtype == torch.float32), _p(scale), _p(shift),
@@ -424,7 +425,7 @@ class CudaBackend:
         self.prog.add("bn_bwd_apply", self.lib.dp_bn_bwd_apply, _p(dout), _p(raw), int(raw.dtype == torch.float32),
                       _p(add1), _p(gamma), _p(scale),
                       _p(shift), _p(mean), _p(invstd), _p(sums), _p(draw), _p(dres), _p(dgamma), _p(dbeta), P, C,
-                      int(relu), mode, int(eval_mode), shuffle_oh, shuffle_ow,
+                      int(relu), mode, int(eval_mode), shuffle_oh, shuffle_ow,   # eval_mode 2: frozen statistics
                       keep=(dout, raw, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta),
                       launches=1 if C <= 512 else 2)
 

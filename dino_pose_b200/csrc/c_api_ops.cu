@@ -35,8 +35,8 @@ cudaError_t launch_dwconv3x3_wgrad(const void*, const void*, float*, int, int, i
 cudaError_t launch_bn_stats(const void*, int, double*, long long, int, cudaStream_t);
 cudaError_t launch_bn_finalize(double*, const float*, const float*, float*, float*, float*, float*, float*, float*, int,
                                double, float, float, cudaStream_t);
-cudaError_t launch_bn_fold_eval(const float*, const float*, const float*, const float*, const float*, float*, float*, int,
-                                float, cudaStream_t);
+cudaError_t launch_bn_fold_eval(const float*, const float*, const float*, const float*, const float*, float*, float*, float*,
+                                float*, int, float, cudaStream_t);
 long long preprocess_workspace_bytes(int, int, int, int, int);
 cudaError_t launch_preprocess(const void*, int, int, int, int, int, const float*, const float*, float*, void*, long long, int*,
                               cudaStream_t);
@@ -153,9 +153,11 @@ extern "C" int dp_bn_finalize(double* sums, const float* gamma, const float* bet
                     "dp_bn_finalize");
 }
 extern "C" int dp_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
-                               const float* conv_bias, float* scale, float* shift, int C, float eps, void* stream) {
+                               const float* conv_bias, float* scale, float* shift, float* mean_out, float* invstd_out,
+                               int C, float eps, void* stream) {
   if (!gamma || !beta || !rm || !rv || !scale || !shift) return set_error(-1, "dp_bn_fold_eval: bad args");
-  return cuda_error(launch_bn_fold_eval(gamma, beta, rm, rv, conv_bias, scale, shift, C, eps, ST), "dp_bn_fold_eval");
+  return cuda_error(launch_bn_fold_eval(gamma, beta, rm, rv, conv_bias, scale, shift, mean_out, invstd_out, C, eps, ST),
+                    "dp_bn_fold_eval");
 }
 extern "C" int dp_bn_apply(const void* raw, int raw_f32, const float* scale, const float* shift, const void* add1,
                            const void* add2, void* out, long long P, int C, int relu, int mode, void* stream) {
@@ -199,7 +201,7 @@ extern "C" int dp_bn_bwd_apply(const void* dout, const void* raw, int raw_f32, c
                                const float* shift, const float* mean, const float* invstd, double* sums, void* draw,
                                void* dres, float* dgamma, float* dbeta, long long P, int C, int relu, int mode,
                                int eval_mode, int shuffle_oh, int shuffle_ow, void* stream) {
-  if (!dout || !raw || !scale || !shift || !draw || !sums || C % 8 || (!eval_mode && (!gamma || !mean || !invstd)))
+  if (!dout || !raw || !scale || !shift || !draw || !sums || C % 8 || (!eval_mode && !gamma) || (eval_mode != 1 && (!mean || !invstd)))
     return set_error(-1, "dp_bn_bwd_apply: bad args");
   return cuda_error(launch_bn_bwd_apply(dout, raw, raw_f32, add1, gamma, scale, shift, mean, invstd, sums, draw, dres, dgamma, dbeta,
                                         P, C, relu, mode, eval_mode, shuffle_oh, shuffle_ow, ST),

@@ -461,13 +461,18 @@ __global__ void bn_finalize_kernel(double* __restrict__ sums, const float* __res
 __global__ void bn_fold_eval_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
                                     const float* __restrict__ rm, const float* __restrict__ rv,
                                     const float* __restrict__ conv_bias, float* __restrict__ scale,
-                                    float* __restrict__ shift, int C, float eps) {
+                                    float* __restrict__ shift, float* __restrict__ mean_out,
+                                    float* __restrict__ invstd_out, int C, float eps) {
   pdl_grid_sync();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
-  const float sc = gamma[c] * rsqrtf(rv[c] + eps);
+  const float is = rsqrtf(rv[c] + eps);
+  const float sc = gamma[c] * is;
   scale[c] = sc;
   shift[c] = beta[c] + ((conv_bias ? conv_bias[c] : 0.f) - rm[c]) * sc;
+  // training step with the heads in eval mode (frozen statistics): the backward reads these like saved batch statistics
+  if (mean_out != nullptr) mean_out[c] = rm[c];
+  if (invstd_out != nullptr) invstd_out[c] = is;
 }
 
 // apply: y = raw*scale + shift;  mode 0: out = relu?(y) + add1 + add2      (HourglassModule 3-way sum, :285)
@@ -713,10 +718,15 @@ __global__ void bn_bwd_coeffs_kernel(double* __restrict__ sums, const float* __r
     sums[(long long)rpl * 2 * C + C + c] = 0.0;
   }
   if (eval_mode) {
+    // 1: identity pass (element-wise adds routed through this kernel); 2: BatchNorm with frozen (running) statistics --
+    // the input gradient is dy * scale, gamma's gradient is sum dy * xhat with xhat from the running statistics
     coef[c] = scale[c];
     coef[C + c] = 0.f;
     coef[2 * C + c] = 0.f;
-    if (dgamma != nullptr) { dgamma[c] = 0.f; dbeta[c] = float(S1); }
+    if (dgamma != nullptr) {
+      dgamma[c] = eval_mode == 2 ? float(double(invstd[c]) * (Q - double(mean[c]) * S1)) : 0.f;
+      dbeta[c] = float(S1);
+    }
     return;
   }
   const double mu = double(mean[c]), is = double(invstd[c]);
@@ -770,7 +780,8 @@ __global__ void __launch_bounds__(kBnThreads, 4) bn_bwd_apply_kernel(
       }
       float A, B, K, dg;
       if (fz.eval_mode) {
-        A = __ldg(scale + c); B = 0.f; K = 0.f; dg = 0.f;
+        A = __ldg(scale + c); B = 0.f; K = 0.f;
+        dg = fz.eval_mode == 2 ? float(double(__ldg(fz.invstd + c)) * (Q - double(__ldg(fz.mean + c)) * S1)) : 0.f;
       } else {
         const double mu = double(__ldg(fz.mean + c)), is = double(__ldg(fz.invstd + c));
         const double S2 = is * (Q - mu * S1);
@@ -1232,8 +1243,10 @@ cudaError_t launch_bn_finalize(double* sums, const float* gamma, const float* be
   return cudaGetLastError();
 }
 cudaError_t launch_bn_fold_eval(const float* gamma, const float* beta, const float* rm, const float* rv,
-                                const float* conv_bias, float* scale, float* shift, int C, float eps, cudaStream_t s) {
-  launch_k<bn_fold_eval_kernel>((C + 127) / 128, 128, 0, s, gamma, beta, rm, rv, conv_bias, scale, shift, C, eps);
+                                const float* conv_bias, float* scale, float* shift, float* mean_out, float* invstd_out, int C,
+                                float eps, cudaStream_t s) {
+  launch_k<bn_fold_eval_kernel>((C + 127) / 128, 128, 0, s, gamma, beta, rm, rv, conv_bias, scale, shift, mean_out, invstd_out, C,
+                                eps);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_apply(const void* raw, int raw_f32, const float* scale, const float* shift, const void* add1,

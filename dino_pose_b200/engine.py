@@ -27,6 +27,7 @@ import torch.nn.functional as F
 BF16 = torch.bfloat16
 F32 = torch.float32
 PATCH = 14
+FROZEN_HEADS = 2                     # `training` value of a training step whose pose heads are in eval mode
 PATCH_K = 3 * PATCH * PATCH          # 588
 PATCH_KP = 640                       # padded to a multiple of the 64-wide k-block
 LN_EPS = 1e-6
@@ -381,12 +382,18 @@ class PoseEngine:
 
     # ------------------------------------------------------------------ plans
     def get_plan(self, B, H, W, training, scope="model"):
-        key = (B, H, W, bool(training)) if scope == "model" else (B, H, W, bool(training), scope)
+        """training: False (inference program), True (training step), or FROZEN_HEADS = 2: a training step whose pose
+        heads are in eval mode -- `model.train(); model.pose_heads.eval()` in the reference's terms: BatchNorm
+        normalises with the running statistics and leaves them alone, the z-head's Dropout is off, gradients still
+        flow to every trainable tensor."""
+        mode = int(training)
+        key = (B, H, W, mode) if scope == "model" else (B, H, W, mode, scope)
         if key not in self.plans:
             if scope in ("model", "backbone"):
-                self.plans[key] = self.build_plan(B, H, W, bool(training), scope)
+                plan = self.build_plan(B, H, W, mode > 0, scope, bn_frozen=mode == FROZEN_HEADS)
             else:
-                self.plans[key] = self.build_scope_plan(scope, B, H // PATCH, bool(training))
+                plan = self.build_scope_plan(scope, B, H // PATCH, mode > 0, bn_frozen=mode == FROZEN_HEADS)
+            self.plans[key] = plan
         return self.plans[key]
 
     # layers of the head table that belong to each stand-alone module scope (reference model/pose_heads.py)
@@ -400,7 +407,7 @@ class PoseEngine:
             return {}
         return Ls
 
-    def build_scope_plan(self, scope, B, g, training):
+    def build_scope_plan(self, scope, B, g, training, bn_frozen=False):
         """Plan for a stand-alone sub-module of the heads (reference model/pose_heads.py:268-285 HourglassModule,
         :345-361 SpatialAwareHeatmapHead, :161-162 ZCoordinateHead, :395-400 SpatialAwarePoseHeads): the same recorded
         launches as inside the full model, starting from the module's own input buffer."""
@@ -409,7 +416,7 @@ class PoseEngine:
             self.seed = torch.zeros(1, dtype=torch.int64, device=self.device)
         N = g * g
         plan = {"B": B, "H": g * PATCH, "W": g * PATCH, "training": training, "g": g, "N": N, "T": N + 1, "M": B * (N + 1),
-                "scope": scope, "lw": {}, "saved": {}}
+                "scope": scope, "lw": {}, "saved": {}, "bn_frozen": bool(bn_frozen and training)}
         t = plan["t"] = {}
         if scope in ("pose_heads", "heatmap_head"):
             t["feat"] = self.new((B * N, self.D), self.adt)        # NHWC rows, what the final LayerNorm writes in the model
@@ -432,7 +439,7 @@ class PoseEngine:
             self.record_backward(plan)
         return plan
 
-    def build_plan(self, B, H, W, training, scope="model"):
+    def build_plan(self, B, H, W, training, scope="model", bn_frozen=False):
         if H % PATCH or W % PATCH or H != W:
             raise ValueError(f"pixel_values must be square with sides a multiple of {PATCH} "
                              f"(reference model/dinov2_pose.py:151 assumes H = W = sqrt(N)); got {H}x{W}")
@@ -446,7 +453,8 @@ class PoseEngine:
         N = g * g
         T = N + 1
         M = B * T
-        plan = {"B": B, "H": H, "W": W, "training": training, "g": g, "N": N, "T": T, "M": M, "scope": scope}
+        plan = {"B": B, "H": H, "W": W, "training": training, "g": g, "N": N, "T": T, "M": M, "scope": scope,
+                "bn_frozen": bool(bn_frozen and training)}
         fz = self.frozen
         t = plan["t"] = {}
         t["px"] = self.new((B, 3, H, W), F32)
@@ -669,7 +677,7 @@ class PoseEngine:
         # 8 replicas of 2c for the backward reduce (DP_BN_BWD_REPLICAS) + one 2c block of coefficient scratch
         L.t["sums"] = self.new((2 * c * 9,), torch.float64)
 
-    def _conv_forward(self, L, x, NB, training, out_override=None):
+    def _conv_forward(self, L, x, NB, training, out_override=None, bn_frozen=False):
         """Records conv (no BN) of layer L on NHWC input x; returns raw (train) or activated (eval) output.
         x: 4-D NHWC view for implicit convs, 2-D [P, C] otherwise."""
         be = self.be
@@ -680,7 +688,8 @@ class PoseEngine:
             act = "relu" if L.relu else "none"
         bias = self.p(L.name + ".bias")
         # train-mode BatchNorm statistics are accumulated by the producing GEMM's epilogue (no separate pass)
-        st = dict(stats=L.t["sums"], stats_c=L.cout) if (training and L.bn is not None and L.kind not in ("convT", "dw")) else {}
+        st = dict(stats=L.t["sums"], stats_c=L.cout) if (training and L.bn is not None and not bn_frozen
+                                                         and L.kind not in ("convT", "dw")) else {}
         L.t["stats_fused"] = bool(st)
         out = out_override if out_override is not None else self.new((P_out, L.cout), self.rdt if (training and L.bn is not None) else self.adt)
         kk = L.k * L.k
@@ -751,11 +760,20 @@ class PoseEngine:
                 L.t["shift_nb"].copy_(L.t["shift"] - self.p(L.name + ".bias").detach() * L.t["scale"])
         return fn
 
-    def _bn_forward(self, L, raw, NB, add1=None, add2=None, mode=0, out=None):
+    def _bn_forward(self, L, raw, NB, add1=None, add2=None, mode=0, out=None, bn_frozen=False):
         """train-mode BatchNorm (+ReLU, + fused adds) on raw [P, C]."""
         be = self.be
         P = NB * L.oh * L.ow
         bn = L.bn
+        if bn_frozen:
+            # heads in eval mode inside a training step: running statistics, re-derived every step because gamma / beta
+            # train; mean / invstd feed the backward where the batch statistics would
+            be.bn_fold_eval(self.p(bn + ".weight"), self.p(bn + ".bias"), self.p(bn + ".running_mean"),
+                            self.p(bn + ".running_var"), None, L.t["scale"], L.t["shift"], C=L.cout, mean=L.t["mean"],
+                            invstd=L.t["invstd"])
+            out = out if out is not None else self.new((P, L.cout), self.adt)
+            be.bn_apply(raw, L.t["scale"], L.t["shift"], add1, add2, out, P=P, C=L.cout, relu=L.relu, mode=mode)
+            return out
         if not L.t.get("stats_fused"):
             be.bn_stats(raw, L.t["sums"], P=P, C=L.cout)
         out = out if out is not None else self.new((P, L.cout), self.adt)
@@ -773,6 +791,7 @@ class PoseEngine:
     def record_heads_forward(self, plan):
         be = self.be
         B, g, training = plan["B"], plan["g"], plan["training"]
+        bn_frozen = bool(plan.get("bn_frozen"))
         t = plan["t"]
         Ls = plan["layers"]
         scope = plan.get("scope", "model")
@@ -800,7 +819,7 @@ class PoseEngine:
                 be.mean_tokens(t["feat"], t["zin"], B=B, N=plan["N"], D=self.D)
             zp = "pose_heads.z_head.mlp."
             cur = t["zin"]
-            p_drop = float(self.cfg.get("z_dropout", 0.0)) if training else 0.0
+            p_drop = float(self.cfg.get("z_dropout", 0.0)) if (training and not bn_frozen) else 0.0   # heads.eval(): Dropout off
             t["zact"] = [cur]
             for j in range(len(dims) - 1):
                 lastl = j == len(dims) - 2
@@ -823,8 +842,8 @@ class PoseEngine:
         def unit(key, x, **kw):
             L = Ls[key]
             if training:
-                r[key] = self._conv_forward(L, x, B, True)
-                a[key] = self._bn_forward(L, r[key], B, **kw)
+                r[key] = self._conv_forward(L, x, B, True, bn_frozen=bn_frozen)
+                a[key] = self._bn_forward(L, r[key], B, bn_frozen=bn_frozen, **kw)
             else:
                 a[key] = self._conv_forward(L, x, B, False)
             return a[key]
@@ -913,7 +932,7 @@ class PoseEngine:
             raise NotImplementedError(f"heat-map resize {s48} -> {self.hm_size} (only 1x and 2x reductions occur "
                                       "for 224^2 / 448^2 inputs)")
         be.join()                # z head (second stream)
-        if training:
+        if training and not bn_frozen:
             # torch BatchNorm bookkeeping (momentum is fixed, the value is unused): one launch for the 14 counters
             counters = [self.Bufs[L.bn + ".num_batches_tracked"] for L in Ls.values() if L.bn is not None]
             be.add_i64(counters, 1)
@@ -971,7 +990,7 @@ class PoseEngine:
         be.fork()
         dims = plan.get("zdims", [0])
         zp = "pose_heads.z_head.mlp."
-        p_drop = float(self.cfg.get("z_dropout", 0.0))
+        p_drop = 0.0 if plan.get("bn_frozen") else float(self.cfg.get("z_dropout", 0.0))
         dcur = t.get("dz")
         nl = len(dims) - 1
         for j in reversed(range(nl if has_z else 0)):
@@ -1004,7 +1023,13 @@ class PoseEngine:
             draw = self.new((P, L.cout), self.adt)
             be.bn_bwd_apply(dact, r[key], add1, self.p(bn + ".weight"), L.t["scale"], L.t["shift"], L.t["mean"],
                             L.t["invstd"], L.t["sums"], draw, dres, G[bn + ".weight"], G[bn + ".bias"], P=P, C=L.cout,
-                            relu=L.relu, mode=mode, shuffle_oh=L.oh if shuffle else 0, shuffle_ow=L.ow if shuffle else 0)
+                            relu=L.relu, mode=mode, eval_mode=2 if plan.get("bn_frozen") else 0,
+                            shuffle_oh=L.oh if shuffle else 0, shuffle_ow=L.ow if shuffle else 0)
+            if plan.get("bn_frozen") and (L.name + ".bias") in G:
+                # frozen statistics: the conv bias is no longer cancelled by the batch mean.  y = scale * (conv + b) + shift,
+                # so db = sum draw = scale * sum dy = scale * dbeta (one [C] product; this mode is not the benchmarked one)
+                gb, gbeta, sc = G[L.name + ".bias"], G[bn + ".bias"], L.t["scale"]
+                be.host("conv_bias_grad", lambda gb=gb, gbeta=gbeta, sc=sc: torch.mul(sc, gbeta, out=gb))
             return draw
 
         def conv_bwd(key, draw, x_in, want_dx=True, dx_residual=None):

@@ -32,7 +32,7 @@ class _PoseFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, pixel_values, *trainable):
         eng = model._get_engine(pixel_values.device)
-        plan = eng.forward(pixel_values, training=True)
+        plan = eng.forward(pixel_values, training=model.engine_mode())
         ctx.eng, ctx.plan, ctx.names = eng, plan, model._trainable_names
         # The saved activations of this graph are the plan's STATIC buffers.  A later train-mode forward with the same
         # (batch, H, W) overwrites them; the stamp lets backward() detect that instead of returning wrong gradients.
@@ -124,6 +124,14 @@ class _Dinov2PoseBase(BasePoseModel):
         if e.cfg.get("z_dropout") != zp or (e.lora is not None and e.lora.get("dropout") != lp):
             self._engine = None    # probabilities are baked into the recorded programs
 
+    def engine_mode(self):
+        """False: inference program.  True: training step.  2: training step with `model.pose_heads.eval()` -- the
+        reference's nn.Module semantics for that call: BatchNorm2d of the heads normalises with its running statistics
+        and does not update them, the z-head's Dropout is the identity, gradients flow as usual."""
+        if not self.training:
+            return False
+        return True if self.pose_heads.training else 2
+
     def forward(self, pixel_values):
         """reference model/dinov2_pose.py:143-157 / :292-306."""
         self._sync_dropout_config()
@@ -142,7 +150,7 @@ class _Dinov2PoseBase(BasePoseModel):
             params = [p for p in self.parameters() if p.requires_grad]
             return _PoseFunction.apply(self, pixel_values, *params)
         eng = self._get_engine(pixel_values.device)
-        plan = eng.forward(pixel_values, training=self.training)
+        plan = eng.forward(pixel_values, training=self.engine_mode())
         return plan["t"]["hm"].clone(), plan["t"]["z"].clone()
 
     # ---- CoreML export hooks (reference :56-131, :221-278) -- export-time only, not on the CUDA path

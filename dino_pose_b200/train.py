@@ -93,7 +93,7 @@ class PoseTrainer:
         self.loss_state = torch.tensor([0.0, 0.0, 0.0, 0.1], device=dev)   # kp_avg, z_avg, started, weight (train.py:18)
         self.loss_out = torch.zeros(3, device=dev)
         self.loss_scales = torch.zeros(2, device=dev)
-        self._steps = {}     # (B, H, W) -> dict(plan, programs, static inputs, graph)
+        self._steps = {}     # (B, H, W) [+ (mode,) for heads-in-eval steps] -> dict(plan, programs, static inputs, graph)
 
     # ------------------------------------------------------------------ parameters
     def _flatten_parameters(self):
@@ -175,9 +175,9 @@ class PoseTrainer:
         return {"kp_loss_avg": s[0] if s[2] else None, "z_loss_avg": s[1] if s[2] else None, "weight": s[3]}
 
     # ------------------------------------------------------------------ step construction
-    def _build(self, B, H, W):
+    def _build(self, B, H, W, mode=True):
         eng, be, dev = self.engine, self.engine.be, self.device
-        plan = eng.get_plan(B, H, W, True)
+        plan = eng.get_plan(B, H, W, mode)     # mode 2: heads in eval mode (frozen BatchNorm statistics, see engine.get_plan)
         K, hm = eng.K, plan["t"]["hm"]
         st = {"plan": plan}
         st["thm"] = torch.zeros_like(hm)
@@ -328,10 +328,11 @@ class PoseTrainer:
             model.train()
         self.engine.check_frozen()
         B, _, H, W = pixel_values.shape
-        key = (B, H, W)
+        mode = model.engine_mode() if hasattr(model, "engine_mode") else True
+        key = (B, H, W) if mode is True else (B, H, W, mode)
         st = self._steps.get(key)
         if st is None or st["plan"] is not self.engine.plans.get((B, H, W, True)):
-            st = self._steps[key] = self._build(B, H, W)
+            st = self._steps[key] = self._build(B, H, W, mode)
         self._load_inputs(st, (pixel_values, target_heatmaps, keypoints, target_z))
         if not self.use_graph:
             self._run(st)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DP_ABI_VERSION 6
+#define DP_ABI_VERSION 7
 
 const char* dp_last_error(void);
 int dp_abi_version(void);
@@ -192,8 +192,11 @@ int dp_bn_stats(const void* raw, int raw_is_f32, double* sums, long long P, int 
 int dp_bn_finalize(double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                    float* scale, float* shift, float* mean, float* invstd, int C, double count, float eps,
                    float momentum, void* stream);
+/* mean_out / invstd_out (nullable): the running mean and 1/sqrt(running_var + eps), in the layout the backward entry
+ * points read saved batch statistics in -- used by a training step whose heads are in eval mode (frozen statistics). */
 int dp_bn_fold_eval(const float* gamma, const float* beta, const float* running_mean, const float* running_var,
-                    const float* conv_bias, float* scale, float* shift, int C, float eps, void* stream);
+                    const float* conv_bias, float* scale, float* shift, float* mean_out, float* invstd_out, int C,
+                    float eps, void* stream);
 int dp_bn_apply(const void* raw, int raw_is_f32, const float* scale, const float* shift, const void* add1,
                 const void* add2, void* out, long long P, int C, int relu, int mode, void* stream);
 /* dp_bn_finalize + dp_bn_apply in ONE launch (pose_heads.py train-mode nn.BatchNorm2d + ReLU / adds): every thread
@@ -208,7 +211,10 @@ int dp_bn_finalize_apply(const void* raw, int raw_is_f32, double* sums, const fl
 /* BatchNorm backward.  `sums` here is fp64 [DP_BN_BWD_REPLICAS + 1][2*C]: the first DP_BN_BWD_REPLICAS blocks are
  * accumulators, zero on entry of dp_bn_bwd_reduce (the thread blocks spread their atomics over the replicas);
  * dp_bn_bwd_apply first adds the replicas up, forms the per-channel coefficients (scratch = the last block), writes
- * dgamma / dbeta and RE-ZEROES the accumulators, then applies draw = A*dy + B*raw + K. */
+ * dgamma / dbeta and RE-ZEROES the accumulators, then applies draw = A*dy + B*raw + K.
+ * eval_mode 0: train-mode BatchNorm (batch statistics in mean / invstd).  1: identity pass, draw = dy * scale, dgamma = 0.
+ * 2: BatchNorm with frozen statistics (`module.eval()` inside a training step, torch nn.BatchNorm2d eval semantics):
+ *    mean / invstd hold the running statistics (dp_bn_fold_eval), draw = dy * scale, dgamma = sum dy * xhat. */
 #define DP_BN_BWD_REPLICAS 8
 int dp_bn_bwd_reduce(const void* dout, const void* raw, int raw_is_f32, const void* add1, const float* scale, const float* shift,
                      const float* mean, const float* invstd, double* sums, long long P, int C, int relu, int mode,

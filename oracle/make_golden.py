@@ -35,6 +35,11 @@ MODEL_CASES = [
     ("small_lora_b2_448_train", "facebook/dinov2-small", 8, 2, 448, "train"),
     ("base_lora_b2_224_train", "facebook/dinov2-base", 8, 2, 224, "train"),
     ("large_frozen_b1_224_eval", "facebook/dinov2-large", 0, 1, 224, "eval"),
+    # training step with the heads in eval mode (model.train(); model.pose_heads.eval()): BatchNorm on its running
+    # statistics -- no batch-statistics cancellation, so the gradient fixtures are tight (mode "trainfz")
+    ("tiny_lora_b3_224_trainfz", "test/dinov2-tiny", 8, 3, 224, "trainfz"),
+    ("small_lora_b4_224_trainfz", "facebook/dinov2-small", 8, 4, 224, "trainfz"),
+    ("base_lora_b2_224_trainfz", "facebook/dinov2-base", 8, 2, 224, "trainfz"),
 ]
 
 # Dinov2PoseModel(unfreeze_last_n_layers=n) (reference model/dinov2_pose.py:25-39):
@@ -42,6 +47,7 @@ MODEL_CASES = [
 UNFREEZE_CASES = [
     ("tiny_unfreeze2_b3_224_train", "test/dinov2-tiny", 0, 3, 224, "train", 2),
     ("small_unfreeze2_b2_224_train", "facebook/dinov2-small", 0, 2, 224, "train", 2),
+    ("small_unfreeze2_b2_224_trainfz", "facebook/dinov2-small", 0, 2, 224, "trainfz", 2),
 ]
 
 
@@ -107,6 +113,8 @@ def run_model_case(dp, losses, name, arch, lora_rank, batch, res, mode, unfreeze
     else:
         kp_loss_fn, z_loss_fn, DLW = losses
         m.train()
+        if mode == "trainfz":
+            m.pose_heads.eval()
         hm, z = m(inp["pixel_values"])
         conf = inp["keypoints"][..., 2]
         kp = kp_loss_fn(hm, inp["heatmaps"], conf)

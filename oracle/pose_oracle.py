@@ -188,18 +188,22 @@ def pose_heads(sd, fmap, training, heatmap_size=48, z_dropout=0.0, aux=None):
     return hm, z
 
 
-def model_forward(sd, px, arch, lora=None, training=False, heatmap_size=48, z_dropout=0.0, aux=None):
+def model_forward(sd, px, arch, lora=None, training=False, heatmap_size=48, z_dropout=0.0, aux=None,
+                  heads_training=None):
     """reference model/dinov2_pose.py:143-157 / :292-306.
 
     ``sd`` BatchNorm running statistics are updated IN PLACE when ``training``
-    (torch semantics) -- pass clones if that matters.
+    (torch semantics) -- pass clones if that matters.  ``heads_training=False`` with
+    ``training=True`` is ``model.train(); model.pose_heads.eval()`` (nn.Module.train is
+    per sub-module): BatchNorm2d / Dropout of the heads in eval mode, LoRA dropout active.
     """
+    heads_training = training if heads_training is None else heads_training
     tok = backbone(sd, px, arch, lora, training, aux)
     patch = tok[:, 1:, :]
     B, N, D = patch.shape
     H = W = int(N ** 0.5)
     fmap = patch.contiguous().view(B, H, W, D).permute(0, 3, 1, 2).contiguous()
-    return pose_heads(sd, fmap, training, heatmap_size, z_dropout, aux)
+    return pose_heads(sd, fmap, heads_training, heatmap_size, z_dropout, aux)
 
 
 # --------------------------------------------------------------------------- losses (train.py:89-120)
@@ -261,7 +265,7 @@ def trainable_names(sd, lora, unfreeze=0, arch=None):
     return out
 
 
-def loss_and_grads(sd, batch, arch, lora, training=True, z_dropout=0.0, unfreeze=0):
+def loss_and_grads(sd, batch, arch, lora, training=True, z_dropout=0.0, unfreeze=0, heads_training=None):
     """One forward + reference losses + backward.  Loss = kp + 0.1 * z on the first step
     (``DynamicLossWeighting.get_balanced_loss`` falls back to ``kp + weight*z`` with
     weight 0.1 until averages exist -- but ``update`` is called first in train.py:154-163,
@@ -269,7 +273,8 @@ def loss_and_grads(sd, batch, arch, lora, training=True, z_dropout=0.0, unfreeze
     names = trainable_names(sd, lora, unfreeze, arch)
     for n in names:
         sd[n].requires_grad_(True)
-    hm, z = model_forward(sd, batch["pixel_values"], arch, lora, training, z_dropout=z_dropout)
+    hm, z = model_forward(sd, batch["pixel_values"], arch, lora, training, z_dropout=z_dropout,
+                          heads_training=heads_training)
     conf = batch["keypoints"][..., 2]
     kp = keypoint_loss(hm, batch["heatmaps"], conf)
     zl = z_loss(z, batch["z"], conf)

@@ -405,12 +405,16 @@ class TorchEmulator:
         self.bn_finalize(sums, gamma, beta, rm, rv, scale, shift, mean, invstd, C=C, count=P, eps=eps, momentum=momentum)
         self.bn_apply(raw, scale, shift, add1, add2, out, P=P, C=C, relu=relu, mode=mode)
 
-    def bn_fold_eval(self, gamma, beta, rm, rv, conv_bias, scale, shift, *, C, eps=1e-5):
+    def bn_fold_eval(self, gamma, beta, rm, rv, conv_bias, scale, shift, *, C, eps=1e-5, mean=None, invstd=None):
         def fn():
             sc = gamma.detach() * torch.rsqrt(rv + eps)
             scale.copy_(sc)
             cb = conv_bias.detach() if conv_bias is not None else 0.0
             shift.copy_(beta.detach() + (cb - rm) * sc)
+            if mean is not None:
+                mean.copy_(rm)
+            if invstd is not None:
+                invstd.copy_(torch.rsqrt(rv + eps))
         self.prog.calls.append(fn)
 
     def bn_apply(self, raw, scale, shift, add1, add2, out, *, P, C, relu=True, mode=0):

@@ -723,6 +723,54 @@ def test_batchnorm_train_fwd_bwd(mode, rawdt, C, fused):
             assert rel(dres.float(), a1.grad) < 1e-2
 
 
+@pytest.mark.parametrize("mode,rawdt,C", [(0, BF, 128), (1, torch.float32, 64), (0, torch.float32, 1024)])
+def test_batchnorm_frozen_statistics_fwd_bwd(mode, rawdt, C):
+    """nn.BatchNorm2d in eval mode inside a training step (model.pose_heads.eval()): dp_bn_fold_eval derives scale / shift
+    AND the saved mean / invstd from the running statistics, dp_bn_bwd_apply(eval_mode=2) returns dy * scale and
+    dgamma = sum dy * xhat.  C = 1024 takes the two-launch (coefficient kernel) form, the others the fused one."""
+    P = 3 * 16 * 16
+    raw = (rnd(P, C) * 1.5 + 0.2).to(rawdt)
+    gamma, beta = rnd(C, seed=1) * 0.1 + 1, rnd(C, seed=2) * 0.1
+    rm, rv = rnd(C, seed=3) * 0.1, rnd(C, seed=4).abs() + 0.5
+    add1 = rnd(P, C, seed=5, dtype=BF)
+    add2 = rnd(P, C, seed=6, dtype=BF) if mode == 0 else None
+    sums = torch.zeros(2 * C * 9, device=dev(), dtype=torch.float64)
+    scale, shift, mean, invstd = [torch.zeros(C, device=dev()) for _ in range(4)]
+    rm2, rv2 = rm.clone(), rv.clone()
+    out = torch.zeros(P, C, device=dev(), dtype=BF)
+
+    def fwd(b):
+        b.bn_fold_eval(gamma, beta, rm2, rv2, None, scale, shift, C=C, mean=mean, invstd=invstd)
+        b.bn_apply(raw, scale, shift, add1, add2, out, P=P, C=C, relu=True, mode=mode)
+    run(fwd)
+    rr = raw.float().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    a1 = add1.float().requires_grad_(True)
+    y = F.batch_norm(rr.view(1, P, C).permute(0, 2, 1), rm, rv, gr, br, False, 0.1, 1e-5).permute(0, 2, 1).reshape(P, C)
+    ref = F.relu(y + a1) if mode == 1 else F.relu(y) + a1 + add2.float()
+    assert rel(out.float(), ref) < 1.5e-2
+    assert torch.equal(rm2, rm) and torch.equal(rv2, rv)            # running statistics untouched
+    assert torch.equal(mean, rm) and rel(invstd, torch.rsqrt(rv + 1e-5)) < 1e-6
+    dout = rnd(P, C, seed=7, dtype=BF)
+    ref.backward(dout.float())
+    draw = torch.zeros(P, C, device=dev(), dtype=BF)
+    dres = torch.zeros(P, C, device=dev(), dtype=BF) if mode == 1 else None
+    dg, db = torch.zeros(C, device=dev()), torch.zeros(C, device=dev())
+
+    def bwd(b):
+        b.bn_bwd_reduce(dout, raw, add1 if mode == 1 else None, scale, shift, mean, invstd, sums, P=P, C=C, relu=True,
+                        mode=mode)
+        b.bn_bwd_apply(dout, raw, add1 if mode == 1 else None, gamma, scale, shift, mean, invstd, sums, draw, dres, dg,
+                       db, P=P, C=C, relu=True, mode=mode, eval_mode=2)
+    for _ in range(2):
+        run(bwd)
+        assert sums[:2 * C * 8].abs().max().item() == 0      # the accumulators (the ninth block is coefficient scratch)
+        assert rel(draw.float(), rr.grad) < 1e-2
+        assert rel(dg, gr.grad) < 1e-2 and rel(db, br.grad) < 1e-2
+        if mode == 1:
+            assert rel(dres.float(), a1.grad) < 1e-2
+
+
 def test_small_ops():
     # avgpool2 == bilinear(align_corners=False) at scale 1/2
     x = rnd(2 * 24, 96, 96)

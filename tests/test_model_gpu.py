@@ -40,7 +40,9 @@ def build(arch, lora_rank, device="cuda", backend_factory=None, unfreeze=0):
 
 
 EVAL_CASES = [c for c in MODEL_CASES if c[5] == "eval"]
-TRAIN_CASES = [c for c in MODEL_CASES if c[5] == "train"] + UNFREEZE_CASES
+TRAIN_CASES = [c for c in MODEL_CASES + UNFREEZE_CASES if c[5] == "train"]
+# training step with the heads in eval mode (model.train(); model.pose_heads.eval()): BatchNorm on running statistics
+FROZEN_CASES = [c for c in MODEL_CASES + UNFREEZE_CASES if c[5] == "trainfz"]
 
 
 @pytest.mark.parametrize("case", EVAL_CASES, ids=lambda c: c[0])
@@ -67,16 +69,19 @@ def _loss(hm, z, inp):
     return w.balanced(kp, zl), kp, zl
 
 
-@pytest.mark.parametrize("case", TRAIN_CASES, ids=lambda c: c[0])
+@pytest.mark.parametrize("case", TRAIN_CASES + FROZEN_CASES, ids=lambda c: c[0])
 def test_train_step_vs_reference_golden(golden_dir, case):
-    name, arch, lora_rank, batch, res, _ = case[:6]
+    name, arch, lora_rank, batch, res, mode = case[:6]
+    frozen = mode == "trainfz"
     unfreeze = case[6] if len(case) > 6 else 0     # Dinov2PoseModel(unfreeze_last_n_layers=n): full backward of n layers
     g = np.load(os.path.join(golden_dir, name + ".npz"))
     m = build(arch, lora_rank, unfreeze=unfreeze).train()
+    if frozen:
+        m.pose_heads.eval()
     inp = {k: v.cuda() for k, v in make_inputs(batch, res, res, 0).items()}
     hm, z = m(inp["pixel_values"])
     print(name, "train hm max-rel", relmax(hm.detach(), g["heatmaps"]), "z", relmax(z.detach(), g["z"]))
-    assert relmax(hm.detach(), g["heatmaps"]) < TOL_TRAIN_HM
+    assert relmax(hm.detach(), g["heatmaps"]) < (TOL if frozen else TOL_TRAIN_HM)
     assert relmax(z.detach(), g["z"]) < TOL
     loss, kp, zl = _loss(hm, z, inp)
     assert abs(kp.item() - float(g["kp_loss"])) / float(g["kp_loss"]) < 2e-2
@@ -110,7 +115,11 @@ def test_train_step_vs_reference_golden(golden_dir, case):
         # Measured worst case over all golden cases: relL2 0.33, cos 0.946 (batch 2-4).  The norm ratio is the scale check:
         # bf16 noise is nearly orthogonal to the gradient, a wrong factor is not (a 1.3x error fails; the tight version of
         # this check, at batch 64 where the BatchNorm statistics are stable, is tests/test_parity_bench_shape_gpu.py).
-        if rel > 0.4 or cos < 0.93 or not (0.8 < ratio < 1.2):
+        # Heads in eval mode (frozen statistics, "trainfz" goldens): no cancellation, the same program is held to
+        # relL2 0.15 / cos 0.99 / ratio within 5 % per tensor (torch emulation of the op graph measures 0.12 / 0.993 at
+        # tiny batch 3 and 0.095 / 0.9955 at ViT-S batch 4 from bf16 storage alone, tests/test_engine_emulated.py).
+        lim = (0.15, 0.99, 0.95, 1.05) if frozen else (0.4, 0.93, 0.8, 1.2)
+        if rel > lim[0] or cos < lim[1] or not (lim[2] < ratio < lim[3]):
             bad[pname] = (float(rel), cos, ratio)
     assert n == int(g["num_grad_tensors"])
     assert not bad, bad
@@ -118,14 +127,37 @@ def test_train_step_vs_reference_golden(golden_dir, case):
     gcos = float(np.dot(fa, fr) / (np.linalg.norm(fa) * np.linalg.norm(fr)))
     gratio = float(np.linalg.norm(fa) / np.linalg.norm(fr))
     print(f"  all trainable gradients: cosine {gcos:.4f} norm ratio {gratio:.4f}")
-    assert gcos > 0.97, gcos
-    assert 0.95 < gratio < 1.05, gratio
+    assert gcos > (0.995 if frozen else 0.97), gcos
+    assert (0.98 if frozen else 0.95) < gratio < (1.02 if frozen else 1.05), gratio
     bufs = dict(m.named_buffers())
     for k in g.files:
         if k.startswith("buf."):
-            assert relmax(subsample(bufs[k[4:]]), g[k]) < TOL, k
+            assert relmax(subsample(bufs[k[4:]]), g[k]) < (1e-7 if frozen else TOL), k
         if k.startswith("buf.") and k.endswith("running_mean"):
-            assert int(bufs[k[4:].replace("running_mean", "num_batches_tracked")].item()) == 1
+            assert int(bufs[k[4:].replace("running_mean", "num_batches_tracked")].item()) == (0 if frozen else 1)
+
+
+def test_heads_in_eval_mode_gradient_is_additive_over_the_batch():
+    """CUDA twin of tests/test_engine_emulated.py's additivity check: with frozen BatchNorm statistics
+    the gradient of the concatenated batch equals the sum of the shard gradients -- what an N-rank all-reduced step
+    computes against a 1-rank step.  Tile shapes / split-K depend on the batch, so agreement is at the bf16 rounding
+    level of the saved activations, not bit-exact."""
+    arch = "facebook/dinov2-small"
+    inp = {k: v.cuda() for k, v in make_inputs(8, 224, 224, 11).items()}
+    gen = torch.Generator().manual_seed(3)
+    w_hm, w_z = torch.randn(8, 24, 48, 48, generator=gen).cuda(), torch.randn(8, 24, generator=gen).cuda()
+
+    def grads(sl):
+        m = build(arch, 8).train()
+        m.pose_heads.eval()
+        hm, z = m(inp["pixel_values"][sl])
+        ((hm * w_hm[sl]).sum() + (z * w_z[sl]).sum()).backward()
+        torch.cuda.synchronize()
+        return torch.cat([p.grad.reshape(-1) for p in m.parameters() if p.requires_grad])
+    full, a, b = (grads(sl) for sl in (slice(0, 8), slice(0, 4), slice(4, 8)))
+    err = ((a + b - full).norm() / full.norm()).item()
+    print("additivity over the batch, heads in eval mode: rel-L2", err)
+    assert err < 2e-2, err
 
 
 def test_train_step_cuda_vs_emulated_op_graph():

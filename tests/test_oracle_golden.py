@@ -44,7 +44,9 @@ def test_model_oracle_matches_reference(golden_dir, case):
                          ("up0", aux["up0"]), ("up1", aux["up1"]), ("pred0", aux["pred0"])):
             assert _relmax(subsample(val), g["sub." + key]) < tol, key
     else:
-        out = pose_oracle.loss_and_grads(sd, inp, arch, lora, training=True, unfreeze=unfreeze)
+        frozen = mode == "trainfz"      # model.train(); model.pose_heads.eval()
+        out = pose_oracle.loss_and_grads(sd, inp, arch, lora, training=True, unfreeze=unfreeze,
+                                         heads_training=False if frozen else None)
         hm, z = out["heatmaps"], out["z"]
         assert abs(out["kp_loss"].item() - g["kp_loss"]) < 1e-6
         assert abs(out["z_loss"].item() - g["z_loss"]) < 1e-6
@@ -65,7 +67,8 @@ def test_model_oracle_matches_reference(golden_dir, case):
                 # un-frozen backbone layers sit one more cancelling stage upstream: at tiny / batch 3 the fp32 oracle, the
                 # fp32 reference and an fp64 run of the oracle differ pairwise by 3e-3 .. 7.5e-3 (measured); at ViT-S the
                 # same comparison gives <= 5e-4
-                assert rel < (1.5e-2 if unfreeze else 5e-3), (pname, rel)
+                # heads in eval mode: no batch-statistics cancellation; measured worst case 6.5e-4 (tiny, feature_refine.0.weight)
+                assert rel < (2e-3 if frozen else 1.5e-2 if unfreeze else 5e-3), (pname, rel)
             n += 1
         assert n == int(g["num_grad_tensors"])
         for k in g.files:

@@ -79,6 +79,7 @@ SIGNATURES = {
     "dp_gemm_bf16": [C.POINTER(GemmArgs), c_vp],
     "dp_wgrad_bf16": [C.POINTER(WgradArgs), c_vp],
     "dp_debug_read_trace": [c_vp, i],
+    "dp_set_reserved_sms": [i],
     "dp_layernorm_fwd": [c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, f, c_vp],
     "dp_layernorm_bwd": [c_vp, i, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_ll, i, i, i, f, c_vp],
     "dp_patch_im2col": [c_vp, c_vp, i, i, i, i, c_vp],

@@ -51,6 +51,18 @@ int sm_count() {
   return n;
 }
 
+// SMs left free by the persistent GEMM / weight-gradient grids launched from now on (dp_set_reserved_sms): the data-parallel
+// trainer sets it while gradient all-reduces are in flight.  A persistent grid with one CTA per SM and ~200 KB of shared
+// memory cannot share an SM with an NCCL CTA: the CTA that loses its SM runs its tiles as a second wave and the whole
+// GEMM takes twice as long; a grid that leaves those SMs alone only loses their share of the throughput.
+static int g_reserved_sms = 0;
+extern "C" int dp_set_reserved_sms(int k) {
+  const int prev = g_reserved_sms;
+  g_reserved_sms = (k > 0 && k < sm_count() - 16) ? k : 0;
+  return prev;
+}
+static int sm_avail() { return sm_count() - g_reserved_sms; }
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -293,18 +305,18 @@ extern "C" int dp_gemm_bf16(const dp_gemm_args* a, void* stream) {
   int grid;
   if (var->pair == 2) {
     const int tiles = p.m_tiles * p.n_tiles;
-    grid = tiles < sm_count() ? tiles : sm_count();
+    grid = tiles < sm_avail() ? tiles : sm_avail();
   } else if (var->pair == 3) {
     const int tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
-    const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+    const int clusters = tiles < sm_avail() / 2 ? tiles : sm_avail() / 2;
     grid = 2 * clusters;
   } else if (var->pair) {
     const int tiles = ((p.m_tiles + 1) / 2) * p.n_tiles;
-    const int clusters = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+    const int clusters = tiles < sm_avail() / 2 ? tiles : sm_avail() / 2;
     grid = 2 * clusters;
   } else {
     const int tiles = p.m_tiles * p.n_tiles;
-    grid = tiles < sm_count() ? tiles : sm_count();
+    grid = tiles < sm_avail() ? tiles : sm_avail();
   }
   static int trace_on = -1;
   if (trace_on < 0) { const char* v = getenv("DP_GEMM_TRACE"); trace_on = v ? atoi(v) : 0; }
@@ -425,6 +437,6 @@ extern "C" int dp_wgrad_bf16(const dp_wgrad_args* a, void* stream) {
     p.debug = dbg;
   }
   const int items = base_items * splits;
-  const int grid = items < sm_count() ? items : sm_count();
+  const int grid = items < sm_avail() ? items : sm_avail();
   return cuda_error(launch_wgrad(p, bn, grid, static_cast<cudaStream_t>(stream)), "dp_wgrad_bf16 launch");
 }

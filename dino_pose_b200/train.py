@@ -78,6 +78,9 @@ class PoseTrainer:
         prio = -1 if int(os.environ.get("DP_COMM_PRIORITY", "-1")) < 0 else 0
         self.comm_stream = (torch.cuda.Stream(device=self.device, priority=prio)
                             if (self.world > 1 and self.device.type == "cuda") else None)
+        # SMs the persistent GEMM grids of the backward leave to NCCL once the first bucket is in flight (0 = none; A/B in
+        # profiles/r2_scaling.md)
+        self.reserve_sms = int(os.environ.get("DP_COMM_RESERVE_SMS", "0")) if self.comm_stream is not None else 0
         self.buckets_sent = []          # [(lo, hi)] of the last step, for tests / introspection
         self._flatten_parameters()
         dev = self.device
@@ -241,6 +244,11 @@ class PoseTrainer:
                     self.comm_stream.wait_stream(cur)
                     with torch.cuda.stream(self.comm_stream):
                         dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
+                    if self.reserve_sms and not st.get("reserved"):
+                        # from the first exchange on, the persistent GEMM grids of the rest of the backward leave SMs to
+                        # NCCL's CTAs (see dp_set_reserved_sms); _run() gives them back after the backward
+                        st["reserved"] = True
+                        self.engine.be.lib.dp_set_reserved_sms(self.reserve_sms)
                 else:   # CPU (gloo) test path
                     dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=self.group)
             if at_split:
@@ -264,7 +272,12 @@ class PoseTrainer:
         plan["fwd"].run()
         st["loss"].run()
         st["side_used"] = None
-        eng.backward(plan, "static", "static", on_mark=self._on_mark(plan["gflat"], st))
+        st["reserved"] = False
+        try:
+            eng.backward(plan, "static", "static", on_mark=self._on_mark(plan["gflat"], st))
+        finally:
+            if st.get("reserved"):
+                self.engine.be.lib.dp_set_reserved_sms(0)
         if self.comm_stream is not None and not self.no_allreduce:
             torch.cuda.current_stream().wait_stream(self.comm_stream)
         elif st.get("side_used") is not None:

@@ -129,6 +129,10 @@ int dp_wgrad_bf16(const dp_wgrad_args* a, void* stream);
 /* Tuning aid, not part of the reference surface: with DP_GEMM_TRACE=2 in the environment CTA 0 of every dp_gemm_bf16 launch
  * records a cycle / nanosecond timeline in a device buffer; this copies its first n (<= 4096) int64 entries to the host. */
 int dp_debug_read_trace(long long* host, int n);
+/* Persistent GEMM / weight-gradient grids launched after this call leave k SMs free (0 = use all); returns the previous
+ * value.  Host-side state read at launch time (under stream capture: at capture time).  Used by the data-parallel trainer
+ * while NCCL all-reduces run beside the backward (no reference counterpart: the reference is single-device). */
+int dp_set_reserved_sms(int k);
 
 /* ---------------------------------------------------------------- backbone row-wise kernels */
 

@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libdinopose_sm100a.so")
-SOURCES = ["gemm_tc.cu", "gemm_fwd_a.cu", "gemm_fwd_b.cu", "gemm_fwd_c.cu", "gemm_fwd_d.cu", "gemm_fwd_generic.cu", "gemm_fwd_pair.cu", "gemm_fwd_astat.cu", "gemm_rowln.cu", "c_api_gemm.cu", "c_api_ops.cu", "rowwise.cu", "heads_ops.cu", "attention_tc.cu", "attention_flash_tc.cu", "attention_bwd_tc.cu", "pred_ops.cu", "decode.cu", "train_ops.cu", "preprocess.cu"]
+SOURCES = ["gemm_tc.cu", "gemm_fwd_a.cu", "gemm_fwd_b.cu", "gemm_fwd_c.cu", "gemm_fwd_d.cu", "gemm_fwd_generic.cu", "gemm_fwd_pair.cu", "gemm_fwd_astat.cu", "gemm_rowln.cu", "c_api_gemm.cu", "c_api_ops.cu", "rowwise.cu", "lora_bwd_mma.cu", "heads_ops.cu", "attention_tc.cu", "attention_flash_tc.cu", "attention_bwd_tc.cu", "pred_ops.cu", "decode.cu", "train_ops.cu", "preprocess.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-diag-suppress", "177"]

@@ -681,10 +681,22 @@ static cudaError_t lora_bwd_t(const float* g, const float* y, const float* u_sav
   return cudaGetLastError();
 }
 
+cudaError_t launch_lora_bwd_mma(const float* g, const float* y, const float* u, const float* Bm, const float* lambda1,
+                                float* dA, float* dB, long long rows, int D, int R, float scaling, float p_drop,
+                                const unsigned long long* seed, int sms, cudaStream_t s);
+
 cudaError_t launch_lora_bwd(const float* g, const float* y, const float* u_saved, const float* Bm, const float* lambda1,
                             float* dA, float* dB, float* gu_ws, long long rows, int D, int R, float scaling, float p_drop,
                             const unsigned long long* seed, int sms, cudaStream_t s) {
   if (D % 128) return cudaErrorInvalidValue;
+  // rank 8, D <= 384: one pass over g and y with warp-level MMAs (lora_bwd_mma.cu); DP_LORA_BWD_MMA=0 keeps the two fp32
+  // kernels below (A/B, and the shapes the MMA kernel does not cover)
+  static int use_mma = -1;
+  if (use_mma < 0) { const char* v = getenv("DP_LORA_BWD_MMA"); use_mma = v ? atoi(v) : 1; }
+  if (use_mma) {
+    const cudaError_t e = launch_lora_bwd_mma(g, y, u_saved, Bm, lambda1, dA, dB, rows, D, R, scaling, p_drop, seed, sms, s);
+    if (e != cudaErrorNotSupported) return e;
+  }
   DP_LORA_DISPATCH(lora_bwd_t, g, y, u_saved, Bm, lambda1, dA, dB, gu_ws, rows, D, scaling, p_drop, seed, sms, s)
 }
 

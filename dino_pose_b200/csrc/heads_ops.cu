@@ -408,9 +408,13 @@ __device__ __forceinline__ void bn_block_reduce_atomic(float (&s)[8], float (&q)
   }
 }
 
+// The ~600 blocks spread their fp64 atomics over the kBnBwdReplicas copies of the accumulator that the backward uses
+// anyway (one copy = 600 dependent read-modify-writes per address in L2, ~20 us of a 40 us launch); the last block to
+// finish (ticket counter shared with the fused finalize kernels) folds the copies into the first and re-zeroes the
+// others, so dp_bn_finalize / dp_bn_finalize_apply see the [2*C] layout they always did.
 template <typename RawT>
 __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const RawT* __restrict__ raw, double* __restrict__ sums,
-                                                              long long P, int C8) {
+                                                              unsigned int* __restrict__ counter, long long P, int C8) {
   pdl_grid_sync();
   const int C = C8 * 8;
   const int c8 = threadIdx.x % C8;
@@ -418,16 +422,40 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const RawT* __rest
   float s[8], q[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] = q[j] = 0.f;
-  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C8; row < P; row += (long long)gridDim.x * rpb) {
-    float f[8];
-    load8(raw + row * C + c8 * 8, f);
+  // two rows per iteration, both loads issued before the math
+  const long long stride = (long long)gridDim.x * rpb;
+  for (long long row = (long long)blockIdx.x * rpb + threadIdx.x / C8; row < P; row += 2 * stride) {
+    float f0[8], f1[8];
+    const bool two = row + stride < P;
+    load8(raw + row * C + c8 * 8, f0);
+    load8(raw + (two ? row + stride : row) * C + c8 * 8, f1);
+    const float w1 = two ? 1.f : 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      s[j] += f[j];
-      q[j] += f[j] * f[j];
+      const float b = f1[j] * w1;
+      s[j] += f0[j] + b;
+      q[j] = fmaf(f0[j], f0[j], fmaf(b, f1[j], q[j]));
     }
   }
-  bn_block_reduce_atomic(s, q, c8, C8, C, sums);
+  bn_block_reduce_atomic(s, q, c8, C8, C, sums + (long long)(blockIdx.x % kBnBwdReplicas) * 2 * C);
+  __shared__ bool s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {
+    __threadfence();
+    for (int c = threadIdx.x; c < 2 * C; c += kBnThreads) {
+      double a = __ldcg(sums + c);
+#pragma unroll
+      for (int r = 1; r < kBnBwdReplicas; ++r) {
+        a += __ldcg(sums + (long long)r * 2 * C + c);
+        sums[(long long)r * 2 * C + c] = 0.0;
+      }
+      sums[c] = a;
+    }
+    if (threadIdx.x == 0) *counter = 0u;
+  }
 }
 
 // finalize: batch mean / biased var -> scale, shift (y = raw*scale + shift), saved mean / invstd,
@@ -1229,10 +1257,12 @@ static bool bn_c_ok(int C) { return C % 8 == 0 && kBnThreads % (C / 8) == 0 && C
 
 cudaError_t launch_bn_stats(const void* raw, int raw_f32, double* sums, long long P, int C, cudaStream_t s) {
   if (!bn_c_ok(C)) return cudaErrorInvalidValue;
+  // ticket counter: the last float slot of the coefficient block behind the replicas (same slot as the fused kernels)
+  unsigned int* counter = reinterpret_cast<unsigned int*>(sums + (long long)kBnBwdReplicas * 2 * C) + 3 * C;
   if (raw_f32)
-    launch_k<bn_stats_kernel<float>>(bn_grid(P, C / 8, bn_resident_blocks(bn_stats_kernel<float>)), kBnThreads, 0, s, reinterpret_cast<const float*>(raw), sums, P, C / 8);
+    launch_k<bn_stats_kernel<float>>(bn_grid(P, C / 8, bn_resident_blocks(bn_stats_kernel<float>)), kBnThreads, 0, s, reinterpret_cast<const float*>(raw), sums, counter, P, C / 8);
   else
-    launch_k<bn_stats_kernel<__nv_bfloat16>>(bn_grid(P, C / 8, bn_resident_blocks(bn_stats_kernel<__nv_bfloat16>)), kBnThreads, 0, s, reinterpret_cast<const __nv_bfloat16*>(raw), sums, P, C / 8);
+    launch_k<bn_stats_kernel<__nv_bfloat16>>(bn_grid(P, C / 8, bn_resident_blocks(bn_stats_kernel<__nv_bfloat16>)), kBnThreads, 0, s, reinterpret_cast<const __nv_bfloat16*>(raw), sums, counter, P, C / 8);
   return cudaGetLastError();
 }
 cudaError_t launch_bn_finalize(double* sums, const float* gamma, const float* beta, float* rm, float* rv, float* scale,

@@ -191,7 +191,8 @@ int dp_dwconv3x3(const void* in, const float* w, const float* bias, const void* 
                  int H, int W, int C, int flip, void* stream);
 int dp_dwconv3x3_wgrad(const void* in, const void* dout, float* dw, int NB, int H, int W, int C, void* stream);
 /* train-mode BatchNorm2d (eps, momentum as torch): sums fp64 [2*C] must be zero on entry of dp_bn_stats;
- * dp_bn_finalize re-zeroes it.  `raw` (pre-BN conv output, [P,C]) is bf16 or fp32 (raw_is_f32). */
+ * dp_bn_finalize re-zeroes it.  `sums` must be the [DP_BN_BWD_REPLICAS + 1][2*C] buffer described at dp_bn_bwd_reduce
+ * (all zero on first use): dp_bn_stats spreads its atomics over the replicas and folds them into [0, 2*C) itself.  `raw` (pre-BN conv output, [P,C]) is bf16 or fp32 (raw_is_f32). */
 int dp_bn_stats(const void* raw, int raw_is_f32, double* sums, long long P, int C, void* stream);
 int dp_bn_finalize(double* sums, const float* gamma, const float* beta, float* running_mean, float* running_var,
                    float* scale, float* shift, float* mean, float* invstd, int C, double count, float eps,

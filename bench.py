@@ -376,13 +376,14 @@ def run_ours(args, cfg):
         dump = os.environ.get("DP_BENCH_DUMP")
         if dump:
             with open(dump, "w") as f:
-                f.write("idx,name,kernel,ms,gflop,tflops,mbytes,gbs\n")
+                # stream: 0 = the step's main stream, 1 / 2 = the side streams of the recorded programs (engine.py fork / join)
+                f.write("idx,name,kernel,ms,gflop,tflops,mbytes,gbs,stream\n")
                 for i in sorted(per_launch):
                     r = per_launch[i]
                     tf = r["flops"] / (r["ms"] * 1e-3) / 1e12 if r["ms"] > 0 else 0
                     gb = r["bytes"] / (r["ms"] * 1e-3) / 1e9 if r["ms"] > 0 else 0
                     f.write(f'{i},{r["name"]},{r["kernel"]},{r["ms"]:.5f},{r["flops"] / 1e9:.3f},{tf:.1f},'
-                            f'{r["bytes"] / 1e6:.2f},{gb:.0f}\n')
+                            f'{r["bytes"] / 1e6:.2f},{gb:.0f},{int(r.get("side") or 0)}\n')
         per_kernel = {k: round(v["ms"] / reps, 4) for k, v in sorted(agg.items(), key=lambda kv: -kv[1]["ms"])[:14]}
         name, a = max(agg.items(), key=lambda kv: kv[1]["ms"])
         # The event pair around a single eager launch also contains the launch hand-over (~5 us per pair), so `achieved` is

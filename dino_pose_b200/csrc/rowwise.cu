@@ -356,8 +356,51 @@ __global__ void __launch_bounds__(256) patch_im2col_kernel(const float* __restri
   }
 }
 
+// Same result through shared memory: the 3 x 14 image rows of one patch row are read with coalesced 8-byte loads and kept
+// as bf16 [c][ky][x]; the gw output rows (Kp bf16 = 1280 bytes each) then leave as full 16-byte pieces, 8 consecutive k
+// gathered from the staged band (the direct kernel above writes 4-byte pieces 28 bytes apart: 32 us for 60 MB).
+__global__ void __launch_bounds__(256) patch_im2col_staged_kernel(const float* __restrict__ px, __nv_bfloat16* __restrict__ out,
+                                                                  int B, int H, int W, int gh, int gw, int Kp) {
+  pdl_grid_sync();
+  extern __shared__ __nv_bfloat16 s_band[];      // [42][Wv]
+  const int b = blockIdx.x / gh, py = blockIdx.x % gh;
+  const int Wv = gw * 14, Wh = Wv >> 1;
+  const int total = 42 * Wh;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < total; i += 256) {
+    const int r = i / Wh, xh = i - r * Wh;       // r = c * 14 + ky
+    const int c = r / 14, ky = r - c * 14;
+    const float2 v = __ldg(reinterpret_cast<const float2*>(px + (((long long)b * 3 + c) * H + (py * 14 + ky)) * W + 2 * xh));
+    *reinterpret_cast<uint32_t*>(s_band + r * Wv + 2 * xh) = pack_bf16x2(v.x, v.y);
+  }
+  __syncthreads();
+  const int K8 = Kp >> 3;                        // 16-byte pieces per output row
+  const unsigned short* sb = reinterpret_cast<const unsigned short*>(s_band);
+  for (int i = threadIdx.x; i < gw * K8; i += 256) {
+    const int p = i / K8, k0 = (i - p * K8) * 8;
+    uint32_t w[4];
+#pragma unroll
+    for (int h = 0; h < 4; ++h) {
+      uint32_t lo = 0u, hi = 0u;
+      const int ka = k0 + 2 * h, kb = ka + 1;
+      if (ka < 588) { const int r = ka / 14; lo = sb[r * Wv + p * 14 + (ka - r * 14)]; }
+      if (kb < 588) { const int r = kb / 14; hi = sb[r * Wv + p * 14 + (kb - r * 14)]; }
+      w[h] = lo | (hi << 16);
+    }
+    const long long row = ((long long)b * gh + py) * gw + p;
+    *reinterpret_cast<uint4*>(out + row * Kp + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
 cudaError_t launch_patch_im2col(const float* px, __nv_bfloat16* out, int B, int H, int W, int Kp, cudaStream_t s) {
   const int gh = H / 14, gw = W / 14;
+  const size_t smem = size_t(42) * gw * 14 * sizeof(__nv_bfloat16);
+  static int staged = -1;     // DP_PATCH_STAGED=0: the direct kernel (A/B)
+  if (staged < 0) { const char* v = getenv("DP_PATCH_STAGED"); staged = v ? atoi(v) : 1; }
+  if (staged && smem <= 48 * 1024 && Kp % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    launch_k<patch_im2col_staged_kernel>(B * gh, 256, smem, s, px, out, B, H, W, gh, gw, Kp);
+    return cudaGetLastError();
+  }
   launch_k<patch_im2col_kernel>(B * gh, 256, 0, s, px, out, B, H, W, gh, gw, Kp);
   return cudaGetLastError();
 }

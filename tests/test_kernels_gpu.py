@@ -600,12 +600,15 @@ def test_pred1x1_fwd_bwd(NB, HW, K):
 
 def test_patch_im2col_and_cls():
     B, H, W, Kp, D = 2, 28, 42, 640, 128
-    px = rnd(B, 3, H, W)
-    out = torch.full((B * 2 * 3, Kp), 7.0, device=dev(), dtype=BF)
-    run(lambda b: b.patch_im2col(px, out, B=B, H=H, W=W, Kp=Kp))
-    ref = F.unfold(px, 14, stride=14).transpose(1, 2).reshape(B * 6, 588)
-    assert torch.equal(out[:, :588], ref.to(BF))
-    assert out[:, 588:].abs().max().item() == 0
+    for (B, H, W) in ((2, 28, 42), (3, 224, 224), (1, 448, 448)):
+        n = (H // 14) * (W // 14)
+        px = rnd(B, 3, H, W)
+        out = torch.full((B * n, Kp), 7.0, device=dev(), dtype=BF)
+        run(lambda b: b.patch_im2col(px, out, B=B, H=H, W=W, Kp=Kp))
+        ref = F.unfold(px, 14, stride=14).transpose(1, 2).reshape(B * n, 588)
+        assert torch.equal(out[:, :588], ref.to(BF))
+        assert out[:, 588:].abs().max().item() == 0
+    B = 2
     T = 7
     x = torch.zeros(B * T, D, device=dev())
     row = rnd(D, seed=3)

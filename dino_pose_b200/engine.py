@@ -1157,7 +1157,14 @@ class PoseEngine:
         d = conv_bwd("pw", bn_bwd("pw", d_hg), a["dw"])
         ddw = bn_bwd("dw", d)
         Ldw = Ls["dw"]
+        # like the GEMM weight gradients: nothing on the main stream needs it, second stream (DP_DW_WGRAD_SIDE=0: in line)
+        dw_side = overlap and chain["ws"] is None and bool(int(os.environ.get("DP_DW_WGRAD_SIDE", "1")))
+        if dw_side:
+            be.sync("side_wait")
+            be.side(True)
         be.dwconv3x3_wgrad(a["fr0"], ddw, G[Ldw.name + ".weight"], NB=B, H=g, W=g, C=512)
+        if dw_side:
+            be.side(False)
         dskip = bn_bwd("skip", d_hg)
         if hg2:
             be.join(2)

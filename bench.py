@@ -348,7 +348,9 @@ def run_ours(args, cfg):
         if train:
             st = trainer._steps[(B, res, res)]
             plan = st["plan"]
-            progs = [plan["fwd"], st["loss"], plan["bwd"], st["opt"]]
+            # the head slice's AdamW is its own program (issued from the backward's bucket mark, dino_pose_b200/train.py)
+            progs = [plan["fwd"], st["loss"], plan["bwd"]] + ([st["opt_head"]] if st.get("opt_head") is not None else []) \
+                + [st["opt"]]
         else:
             plan = eng.plans[(B, res, res, False)]
             progs = [plan["fwd"]]

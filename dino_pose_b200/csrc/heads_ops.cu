@@ -445,14 +445,28 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const RawT* __rest
   __syncthreads();
   if (s_last) {
     __threadfence();
-    for (int c = threadIdx.x; c < 2 * C; c += kBnThreads) {
-      double a = __ldcg(sums + c);
+    // ALL loads of up to four channels per thread first, then the stores: with the stores in between, the compiler must
+    // keep the 8 x 4 L2 round trips of this one block in order (ncu: the launch took 20 us whatever the tensor size)
+    for (int c0 = threadIdx.x; c0 < 2 * C; c0 += 4 * kBnThreads) {
+      double v[4][kBnBwdReplicas];
 #pragma unroll
-      for (int r = 1; r < kBnBwdReplicas; ++r) {
-        a += __ldcg(sums + (long long)r * 2 * C + c);
-        sums[(long long)r * 2 * C + c] = 0.0;
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + i * kBnThreads;
+#pragma unroll
+        for (int r = 0; r < kBnBwdReplicas; ++r) v[i][r] = c < 2 * C ? __ldcg(sums + (long long)r * 2 * C + c) : 0.0;
       }
-      sums[c] = a;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = c0 + i * kBnThreads;
+        if (c >= 2 * C) break;
+        double a = v[i][0];
+#pragma unroll
+        for (int r = 1; r < kBnBwdReplicas; ++r) {
+          a += v[i][r];
+          sums[(long long)r * 2 * C + c] = 0.0;
+        }
+        sums[c] = a;
+      }
     }
     if (threadIdx.x == 0) *counter = 0u;
   }
